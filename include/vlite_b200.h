@@ -1,0 +1,178 @@
+/* vlite_b200 -- C ABI of the B200-native vlite retrieval hot path.
+ *
+ * The reference (sdan/vlite) has no FFI: its seam is three Python call sites
+ * (SURVEY.md section 8b).  Each entry point below names the reference code it
+ * replaces (paths relative to the reference checkout).  Plain pointers and
+ * sizes only; no torch / C++ types cross this boundary.
+ *
+ * Conventions
+ *   - every function returns 0 on success and a negative VL_E* code on
+ *     failure; vl_last_error() then returns a thread-local message.
+ *   - corpus rows and queries are RAW UBINARY bytes (np.packbits output,
+ *     MSB-first within a byte), width W in {32, 64, 128, 256} bytes per row.  The
+ *     reference's stored encoding int8(u8)-128 (vlite/model.py:44) gives
+ *     identical XOR scores; vl_corpus_append_f32 converts it on the device.
+ *   - pointers named *_any may be host or device memory (the library asks
+ *     the CUDA runtime); *_dev must be device memory on the handle's device.
+ *   - one CUDA stream per handle (vl_corpus_set_stream); calls on one handle
+ *     are serialised by the caller, different handles are independent --
+ *     the same contract the reference's single mutable VLite object has
+ *     (vlite/server.py:14).  When every pointer passed to a call is device
+ *     memory the call only ENQUEUES work on the handle's stream and returns
+ *     without synchronising; with any host pointer it returns after the
+ *     data has landed.
+ *   - results are ordered ascending by (score, global row); slots past the
+ *     number of eligible rows hold VL_SENTINEL_SCORE / VL_SENTINEL_ROW.
+ *   - there is NO CPU fallback: without a usable sm_100 device every compute
+ *     entry point fails with VL_ENODEV.
+ */
+#ifndef VLITE_B200_H
+#define VLITE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VL_OK        0
+#define VL_EINVAL   -1   /* bad argument */
+#define VL_ECUDA    -2   /* CUDA runtime error (message in vl_last_error) */
+#define VL_ENOMEM   -3   /* device or host allocation failed */
+#define VL_ENODEV   -4   /* no usable sm_100 device */
+#define VL_EIO      -5   /* file error in vl_corpus_load_file */
+#define VL_ERANGE   -6   /* stored value outside the encodable range */
+
+#define VL_SENTINEL_SCORE 0xFFFFFFFFu
+#define VL_SENTINEL_ROW   0xFFFFFFFFFFFFFFFFull
+
+/* score function */
+#define VL_METRIC_HAMMING 0  /* popcount(q ^ e): vlite/model.py:71-74 hamming_distance,
+                                vlite/index.py:30 (on unpacked bits) */
+#define VL_METRIC_XORSUM  1  /* sum_j (q_j ^ e_j) on byte values: the live
+                                torch.sum(q.int() ^ E.int(), dim=1), vlite/model.py:82 */
+
+/* source encodings for vl_corpus_append_f32 / vl_corpus_load_file */
+#define VL_SRC_U8          0 /* raw ubinary bytes, W per row */
+#define VL_SRC_F32_OFFSET  1 /* W float32 per row holding int8(u8)-128 in [-256,-1]
+                                (vlite/model.py:44 as stored by vlite/ctx.py:70), or raw [0,255] */
+#define VL_SRC_F32_BITS    2 /* 8*W float32 per row holding 0.0/1.0, one per bit (the legacy
+                                layout of tests/contexts/vlite-bench.ctx) */
+
+typedef struct vl_corpus vl_corpus;
+
+/* ---- library ---------------------------------------------------------- */
+const char* vl_version(void);
+const char* vl_last_error(void);
+/* number of CUDA devices of compute capability 10.x visible to the process */
+int vl_device_count(void);
+/* how many of this library's kernels the calling process has launched so far
+ * (bench.py's "gpu_launches") */
+uint64_t vl_launch_count(void);
+
+/* ---- corpus residency: replaces the per-query rebuild of the (N, W) array
+ * from the Python dict (vlite/main.py:143-146) and the dict appends of
+ * VLite.add / set_batch (vlite/main.py:89-95, :264-268) ------------------- */
+int vl_corpus_create(int device, int width_bytes, uint64_t capacity_rows, vl_corpus** out);
+int vl_corpus_destroy(vl_corpus* c);
+/* stream: a cudaStream_t (as void*); NULL = the legacy default stream */
+int vl_corpus_set_stream(vl_corpus* c, void* cuda_stream);
+int vl_corpus_reserve(vl_corpus* c, uint64_t capacity_rows);
+/* append n rows of raw ubinary bytes in place (capacity doubles when full);
+ * *first_row_out = local index of the first appended row */
+int vl_corpus_append(vl_corpus* c, const uint8_t* rows_any, uint64_t n, uint64_t* first_row_out);
+/* append n rows given as float32 in one of the VL_SRC_F32_* encodings; the
+ * f32 -> ubinary repack runs on the device.  replaces the row-by-row
+ * struct.unpack of vlite/ctx.py:116-119 + np.array() of vlite/main.py:50 */
+int vl_corpus_append_f32(vl_corpus* c, const float* vals_any, uint64_t n, int src_kind,
+                         uint64_t* first_row_out);
+/* stream rows straight from a byte range of a file (a CTX EMBEDDINGS payload,
+ * vlite/ctx.py:112-119) through pinned staging into HBM; src_row_bytes is the
+ * on-disk size of one row in that encoding (e.g. 256 for 64 float32).
+ * max_rows caps how many rows are taken (0 = all that fit in byte_len) */
+int vl_corpus_load_file(vl_corpus* c, const char* path, uint64_t byte_off, uint64_t byte_len,
+                        int src_kind, uint64_t max_rows, uint64_t* first_row_out,
+                        uint64_t* n_rows_out);
+/* overwrite one existing row (VLite.update with a new vector) */
+int vl_corpus_set_row(vl_corpus* c, uint64_t row, const uint8_t* row_any);
+/* delete = clear the row's bit in the live mask (replaces `del self.index[id]`,
+ * vlite/main.py:198); rows keep their indices */
+int vl_corpus_tombstone(vl_corpus* c, const uint64_t* rows_host, uint64_t n);
+int vl_corpus_clear(vl_corpus* c);                       /* VLite.clear, vlite/main.py:296 */
+int vl_corpus_rows(const vl_corpus* c, uint64_t* rows, uint64_t* live_rows);
+int vl_corpus_width(const vl_corpus* c);
+/* global index of local row 0 (row-sharding across GPUs) */
+int vl_corpus_set_base_row(vl_corpus* c, uint64_t base_row);
+/* copy rows [first, first+n) back to the host (CTX save, tests) */
+int vl_corpus_read(vl_corpus* c, uint64_t first, uint64_t n, uint8_t* out_host);
+/* device address of row 0 and of the live mask (borrowed; valid until the next
+ * append that grows the corpus) */
+int vl_corpus_device_ptrs(vl_corpus* c, void** rows_dev, void** live_mask_dev);
+/* fill rows [first, first+n) on the device with the counter-based synthetic
+ * generator of oracle/synth.py (period = 0: all rows distinct); rows past the
+ * current count are appended.  Bench / test data only. */
+int vl_corpus_fill_synthetic(vl_corpus* c, uint64_t seed, uint64_t first, uint64_t n,
+                             uint64_t period);
+/* build a filter mask on the device from the synthetic per-row tags:
+ * bit(row) = tag(seed, base_row + row) < threshold.  mask_dev holds
+ * ceil(n/32) uint32 words.  Bench / test data only. */
+int vl_synth_filter_mask(vl_corpus* c, uint64_t seed, uint64_t threshold, uint32_t* mask_dev);
+
+/* ---- search: replaces EmbeddingModel.search (vlite/model.py:76-90) and the
+ * row -> id step of VLite.rank_and_filter (vlite/main.py:150-156) ---------- */
+/* queries_any: Q x W raw ubinary.  filter_mask_any: optional bit per local row
+ * (bit row&31 of word row>>5; 1 = eligible), ANDed with the live mask INSIDE
+ * the scan -- a true pre-filter, unlike the reference's post-filter over
+ * top_k*4 candidates (vlite/main.py:159-165).  out_score_any: Q x k uint32,
+ * out_row_any: Q x k uint64 global rows (base_row + local).  1 <= k <= VL_MAX_K */
+#define VL_MAX_K 2048
+int vl_search(vl_corpus* c, const uint8_t* queries_any, int n_queries, int k, int metric,
+              const uint32_t* filter_mask_any, uint32_t* out_score_any, uint64_t* out_row_any);
+/* full score vector of ONE query over rows [first, first+n) (parity tests) */
+int vl_scores(vl_corpus* c, const uint8_t* query_any, int metric, uint64_t first, uint64_t n,
+              uint32_t* out_any);
+/* merge n_lists candidate lists (each Q x k_in, ascending (score,row), sentinel
+ * padded) into Q x k_out: the step after the all-gather of per-shard top-k
+ * (SURVEY.md section 8e).  All pointers device memory. */
+int vl_merge_topk(int device, void* cuda_stream, const uint32_t* scores_dev, const uint64_t* rows_dev,
+                  int n_lists, int n_queries, int k_in, int k_out,
+                  uint32_t* out_score_dev, uint64_t* out_row_dev);
+
+/* ---- rescore (north-star piece 3; no reference implementation -- nearest
+ * code is the unused cos_sim, vlite/utils.py:205-208) ----------------------- */
+#define VL_QTYPE_F32 0
+#define VL_QTYPE_I8  1
+/* docs_i8_dev: n_docs x dims int8, row-major, indexed by LOCAL row.
+ * queries_any: Q x dims float32 or int8.  cand_rows_any: Q x C uint64 GLOBAL
+ * rows as vl_search wrote them (sentinels skipped).  Output: top k by
+ * DESCENDING dot product, ties by ascending row; padded with -inf / sentinel. */
+int vl_rescore(vl_corpus* c, const int8_t* docs_i8_dev, uint64_t n_docs, int dims,
+               const void* queries_any, int qtype, const uint64_t* cand_rows_any,
+               int n_queries, int n_cand, int k, float* out_score_any, uint64_t* out_row_any);
+/* sign-quantise float32 embeddings to raw ubinary on the device:
+ * (x > 0) -> packbits MSB-first (vlite/model.py:41-44 without the -128).
+ * x_any: n x dims float32, out_any: n x dims/8 bytes. */
+int vl_quantize_binary(int device, void* cuda_stream, const float* x_any, uint64_t n, int dims,
+                       uint8_t* out_any);
+/* bench data: fill n x dims int8 documents with the synthetic generator */
+int vl_synth_docs_i8(int device, void* cuda_stream, uint64_t seed, uint64_t first_row, uint64_t n,
+                     int dims, int8_t* out_dev);
+
+/* ---- measurement helpers ---------------------------------------------- */
+/* integer-pipe micro-benchmarks: kind 0 = POPC, 1 = LOP3, 2 = IADD3, 3 = IDP4A,
+ * 4 = POPC+LOP3+IADD mix.  Runs `iters` dependent-chain steps per thread on a
+ * full grid; returns lane-operations per second. */
+int vl_microbench(int device, int kind, int iters, double* ops_per_sec_out, double* ms_out);
+/* wall time of the most recent vl_search / vl_rescore on this handle, measured
+ * with CUDA events on the handle's stream around the kernels only (no copies);
+ * scan_ms = the scan kernel alone */
+int vl_last_timing(vl_corpus* c, float* total_ms, float* scan_ms);
+int vl_set_timing(vl_corpus* c, int enabled);
+/* tuning knobs for experiments (0 = automatic) */
+int vl_set_tuning(vl_corpus* c, int row_splits, int reserved);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VLITE_B200_H */

@@ -1,0 +1,210 @@
+"""-m gpu parity tests: the CUDA scan + top-k + merge through the C ABI vs the CPU oracle.
+
+Bar: bit-exact scores and row lists under the (score, row) tie-break.
+"""
+import numpy as np
+import pytest
+
+from oracle import cscan, search as osearch, synth
+
+pytestmark = pytest.mark.gpu
+
+HAMMING, XORSUM = 0, 1
+
+
+def _oracle(corpus, queries, k, metric, mask_words=None, base_row=0):
+    return cscan.search(queries, corpus, k, metric, mask_words, base_row)
+
+
+def _check(c, corpus, queries, k, metric, mask_words=None, base_row=0):
+    s, r = c.search(queries, k, metric, mask_words)
+    es, er = _oracle(corpus, queries, k, metric, mask_words, base_row)
+    np.testing.assert_array_equal(s, es)
+    np.testing.assert_array_equal(r, er)
+
+
+@pytest.mark.parametrize("width", [64, 128])
+@pytest.mark.parametrize("metric", [HAMMING, XORSUM])
+def test_full_score_vector_bit_exact(gpu, width, metric):
+    n = 5000
+    corpus = synth.corpus_rows(3, 0, n, width)
+    q = synth.uniform_queries(4, 1, width)[0]
+    with gpu.Corpus(width) as c:
+        c.append(corpus)
+        got = c.scores(q, metric)
+    np.testing.assert_array_equal(got, cscan.scores(q, corpus, metric))
+    # and the C oracle agrees with the numpy restatement of the reference lines
+    np.testing.assert_array_equal(got.astype(np.int64), osearch.scores(q, corpus, metric))
+
+
+@pytest.mark.parametrize("width", [64, 128])
+@pytest.mark.parametrize("metric", [HAMMING, XORSUM])
+@pytest.mark.parametrize("nq", [1, 2, 3, 5, 8, 13, 24, 40, 64, 65, 130])
+def test_topk_all_query_tilings(gpu, width, metric, nq):
+    n, k = 20011, 10   # ragged: not a multiple of the 256-row tile
+    corpus = synth.corpus_rows(5, 0, n, width)
+    queries = synth.uniform_queries(6, nq, width)
+    queries[0] = corpus[n - 1]            # exact hit on the last row
+    with gpu.Corpus(width) as c:
+        c.append(corpus)
+        _check(c, corpus, queries, k, metric)
+
+
+@pytest.mark.parametrize("k", [1, 5, 10, 32, 33, 100, 128])
+def test_k_values(gpu, k):
+    n = 9000
+    corpus = synth.corpus_rows(7, 0, n, 128)
+    queries = synth.uniform_queries(8, 9, 128)
+    with gpu.Corpus(128) as c:
+        c.append(corpus)
+        _check(c, corpus, queries, k, HAMMING)
+        _check(c, corpus, queries[:2], k, XORSUM)
+
+
+@pytest.mark.parametrize("k", [129, 300, 1000])
+def test_large_k_multipass(gpu, k):
+    n = 6000
+    corpus = synth.corpus_rows(9, 0, n, 128, period=500)   # duplicates: ties straddle pass boundaries
+    queries = synth.uniform_queries(10, 5, 128)
+    with gpu.Corpus(128) as c:
+        c.append(corpus)
+        _check(c, corpus, queries, k, HAMMING)
+
+
+def test_duplicates_tie_break(gpu):
+    # distribution D: every score value is shared by n/period rows
+    n, period = 30000, 97
+    corpus = synth.corpus_rows(11, 0, n, 128, period)
+    queries = synth.corpus_rows(11, 0, 4, 128, period)   # exact copies of rows 0..3
+    with gpu.Corpus(128) as c:
+        c.append(corpus)
+        s, r = c.search(queries, 10, HAMMING)
+        _check(c, corpus, queries, 10, HAMMING)
+    assert (s == 0).all()
+    np.testing.assert_array_equal(r[2], 2 + period * np.arange(10, dtype=np.uint64))
+
+
+def test_clustered_queries_find_their_source(gpu):
+    n = 50000
+    corpus = synth.corpus_rows(13, 0, n, 128)
+    queries, src = synth.clustered_queries(14, 13, n, 16, 128, flip_p=0.10)
+    with gpu.Corpus(128) as c:
+        c.append(corpus)
+        s, r = c.search(queries, 5, HAMMING)
+        _check(c, corpus, queries, 5, HAMMING)
+    np.testing.assert_array_equal(r[:, 0].astype(np.int64), src)
+
+
+def test_k_larger_than_corpus_pads_with_sentinels(gpu):
+    corpus = synth.corpus_rows(15, 0, 7, 64)
+    queries = synth.uniform_queries(16, 3, 64)
+    with gpu.Corpus(64) as c:
+        c.append(corpus)
+        s, r = c.search(queries, 12, XORSUM)
+        _check(c, corpus, queries, 12, XORSUM)
+    assert (s[:, 7:] == 0xFFFFFFFF).all() and (r[:, 7:] == np.uint64(0xFFFFFFFFFFFFFFFF)).all()
+
+
+def test_empty_corpus(gpu):
+    with gpu.Corpus(128) as c:
+        s, r = c.search(synth.uniform_queries(1, 2, 128), 4, HAMMING)
+    assert (s == 0xFFFFFFFF).all() and (r == np.uint64(0xFFFFFFFFFFFFFFFF)).all()
+
+
+@pytest.mark.parametrize("sel", [0.01, 0.10, 0.50])
+@pytest.mark.parametrize("nq", [1, 20])
+def test_filter_mask_in_scan(gpu, sel, nq):
+    n = 40000
+    corpus = synth.corpus_rows(17, 0, n, 128)
+    queries = synth.uniform_queries(18, nq, 128)
+    valid = synth.filter_valid(2, 0, n, sel)
+    mask = synth.pack_mask(valid)
+    with gpu.Corpus(128) as c:
+        c.append(corpus)
+        _check(c, corpus, queries, 10, HAMMING, mask)
+        s, r = c.search(queries, 10, HAMMING, mask)
+    assert valid[r.astype(np.int64)].all()
+    # oracle = numpy search on the filtered subset (SURVEY 8d cfg 5)
+    es, er = osearch.search(queries[:1], corpus, 10, HAMMING, valid=valid)
+    np.testing.assert_array_equal(r[:1], er)
+    np.testing.assert_array_equal(s[:1], es)
+
+
+def test_tombstones_and_append_in_place(gpu):
+    n = 3000
+    corpus = synth.corpus_rows(19, 0, n, 128)
+    queries = synth.uniform_queries(20, 6, 128)
+    with gpu.Corpus(128, capacity_rows=16) as c:      # forces several capacity doublings
+        for lo in range(0, n, 700):
+            assert c.append(corpus[lo:lo + 700]) == lo
+        assert c.rows == n and c.live_rows == n
+        np.testing.assert_array_equal(c.read(), corpus)
+        _, r0 = c.search(queries, 3, HAMMING)
+        dead = np.unique(r0.reshape(-1))
+        c.tombstone(dead)
+        c.tombstone(dead[:2])                           # double delete must not double count
+        assert c.live_rows == n - len(dead)
+        mask = np.ones(n, dtype=bool)
+        mask[dead.astype(np.int64)] = False
+        _check(c, corpus, queries, 8, HAMMING, synth.pack_mask(mask))   # same as filtering them out
+        s, r = c.search(queries, 8, HAMMING)
+        es, er = osearch.search(queries, corpus, 8, HAMMING, valid=mask)
+        np.testing.assert_array_equal(r, er)
+        np.testing.assert_array_equal(s, es)
+        # appended rows after deletes keep global indices
+        extra = synth.corpus_rows(21, 0, 50, 128)
+        assert c.append(extra) == n
+        full = np.concatenate([corpus, extra])
+        mask2 = np.concatenate([mask, np.ones(50, dtype=bool)])
+        s, r = c.search(queries, 8, HAMMING)
+        es, er = osearch.search(queries, full, 8, HAMMING, valid=mask2)
+        np.testing.assert_array_equal(r, er)
+
+
+def test_base_row_offsets_results(gpu):
+    n, base = 5000, 10_000_000_000
+    corpus = synth.corpus_rows(23, base, n, 128)          # a shard of a bigger corpus
+    queries = synth.uniform_queries(24, 3, 128)
+    with gpu.Corpus(128, base_row=base) as c:
+        c.fill_synthetic(23, 0, n)                         # device generator, global rows base..base+n
+        np.testing.assert_array_equal(c.read(), corpus)
+        _check(c, corpus, queries, 10, HAMMING, base_row=base)
+
+
+def test_row_splits_do_not_change_results(gpu):
+    n = 70000
+    corpus = synth.corpus_rows(25, 0, n, 128, period=1000)
+    queries = synth.uniform_queries(26, 70, 128)
+    with gpu.Corpus(128) as c:
+        c.append(corpus)
+        ref = c.search(queries, 10, HAMMING)
+        for splits in (1, 3, 17):
+            c.set_tuning(row_splits=splits)
+            got = c.search(queries, 10, HAMMING)
+            np.testing.assert_array_equal(got[0], ref[0])
+            np.testing.assert_array_equal(got[1], ref[1])
+        for stages in (1, 2, 5):
+            c.set_tuning(row_splits=0, stages=stages)
+            got = c.search(queries, 10, HAMMING)
+            np.testing.assert_array_equal(got[1], ref[1])
+        c.set_tuning()
+    es, er = _oracle(corpus, queries, 10, HAMMING)
+    np.testing.assert_array_equal(ref[1], er)
+
+
+def test_device_resident_queries_and_outputs(gpu):
+    torch = pytest.importorskip("torch")
+    n = 12000
+    corpus = synth.corpus_rows(27, 0, n, 128)
+    queries = synth.uniform_queries(28, 33, 128)
+    dq = torch.from_numpy(queries).cuda()
+    ds = torch.empty((33, 10), dtype=torch.int32, device="cuda")
+    dr = torch.empty((33, 10), dtype=torch.int64, device="cuda")
+    with gpu.Corpus(128) as c:
+        c.set_stream(torch.cuda.current_stream().cuda_stream)
+        c.append(torch.from_numpy(corpus).cuda())
+        c.search(dq, 10, HAMMING, out_scores=ds, out_rows=dr)
+        torch.cuda.synchronize()
+    es, er = _oracle(corpus, queries, 10, HAMMING)
+    np.testing.assert_array_equal(ds.cpu().numpy().view(np.uint32), es)
+    np.testing.assert_array_equal(dr.cpu().numpy().view(np.uint64), er)

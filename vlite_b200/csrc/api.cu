@@ -1,0 +1,1011 @@
+// C ABI of vlite_b200 (see include/vlite_b200.h): corpus residency, search, rescore, CTX
+// embeddings load, measurement helpers.  Host-side orchestration only; the kernels live in
+// scan.cuh / merge.cuh / rescore.cuh / repack.cuh / synth.cuh.
+#include <fcntl.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
+#include <algorithm>
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/vlite_b200.h"
+#include "merge.cuh"
+#include "repack.cuh"
+#include "rescore.cuh"
+#include "scan.cuh"
+#include "synth.cuh"
+
+namespace {
+
+thread_local std::string g_err;
+std::atomic<uint64_t> g_launches{0};
+
+int fail(int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+
+#define CU(expr)                                                                                  \
+    do {                                                                                          \
+        cudaError_t _e = (expr);                                                                  \
+        if (_e != cudaSuccess) {                                                                  \
+            cudaGetLastError();                                                                   \
+            return fail(_e == cudaErrorMemoryAllocation ? VL_ENOMEM : VL_ECUDA, "%s: %s (%s:%d)", \
+                        #expr, cudaGetErrorString(_e), __FILE__, __LINE__);                       \
+        }                                                                                         \
+    } while (0)
+#define TRY(expr)              \
+    do {                       \
+        int _r = (expr);       \
+        if (_r != VL_OK) return _r; \
+    } while (0)
+#define LAUNCHED()                       \
+    do {                                 \
+        g_launches.fetch_add(1);         \
+        CU(cudaGetLastError());          \
+    } while (0)
+
+struct DeviceGuard {
+    int prev = -1;
+    bool ok = true;
+    explicit DeviceGuard(int dev) {
+        if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+        if (prev != dev) ok = (cudaSetDevice(dev) == cudaSuccess);
+    }
+    ~DeviceGuard() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    int ensure(size_t bytes) {
+        if (bytes <= cap) return VL_OK;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        size_t want = std::max(bytes, (size_t)4096);
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            return fail(VL_ENOMEM, "cudaMalloc(%zu) failed: %s", want, cudaGetErrorString(e));
+        }
+        cap = want;
+        return VL_OK;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+};
+
+bool is_device_ptr(const void* p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+}
+
+int check_device(int device, int* sms_out) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) {
+        cudaGetLastError();
+        return fail(VL_ENODEV, "no CUDA device visible; vlite_b200 has no CPU fallback");
+    }
+    if (device < 0 || device >= n) return fail(VL_EINVAL, "device %d out of range (0..%d)", device, n - 1);
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10)
+        return fail(VL_ENODEV, "device %d is sm_%d%d; vlite_b200 is built for sm_100a (B200) only", device,
+                    prop.major, prop.minor);
+    if (sms_out) *sms_out = prop.multiProcessorCount;
+    return VL_OK;
+}
+
+inline unsigned grid_for(uint64_t items, int threads, int sms) {
+    uint64_t blocks = (items + threads - 1) / threads;
+    uint64_t cap = (uint64_t)sms * 16;
+    return (unsigned)std::max<uint64_t>(1, std::min(blocks, cap));
+}
+
+}  // namespace
+
+struct vl_corpus {
+    int device = 0;
+    int w = 0;
+    int sms = 148;
+    cudaStream_t stream = nullptr;
+    uint8_t* rows = nullptr;
+    uint32_t* live = nullptr;
+    uint64_t capacity = 0;  // rows, multiple of kTileRows
+    uint64_t count = 0;
+    uint64_t live_count = 0;
+    uint64_t base_row = 0;
+    DevBuf q_buf, filt_buf, part_s, part_r, out_s, out_r, stage[2], rows_buf, cand_buf, misc;
+    void* pinned[2] = {nullptr, nullptr};
+    size_t pinned_bytes = 0;
+    cudaEvent_t stage_ev[2] = {nullptr, nullptr};
+    int* d_err = nullptr;
+    unsigned long long* d_counter = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr;
+    bool timing = false;
+    bool timed = false;
+    int tune_splits = 0;
+    int tune_stages = 0;
+};
+
+namespace {
+
+using namespace vl;
+
+// reallocate rows + live mask to exactly `cap_rows` (rounded up to whole tiles), keeping contents
+int grow_to(vl_corpus* c, uint64_t cap_rows) {
+    if (cap_rows > 0xFFFFFF00ull) return fail(VL_EINVAL, "a corpus shard holds at most 2^32-256 rows");
+    const uint64_t cap = (cap_rows + kTileRows - 1) / kTileRows * kTileRows;
+    uint8_t* nrows = nullptr;
+    uint32_t* nlive = nullptr;
+    cudaError_t e = cudaMalloc(&nrows, cap * (uint64_t)c->w);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return fail(VL_ENOMEM, "cudaMalloc of %llu rows x %d B failed: %s", (unsigned long long)cap, c->w,
+                    cudaGetErrorString(e));
+    }
+    e = cudaMalloc(&nlive, cap / 8);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        cudaFree(nrows);
+        return fail(VL_ENOMEM, "cudaMalloc of live mask failed: %s", cudaGetErrorString(e));
+    }
+    CU(cudaMemsetAsync(nlive, 0, cap / 8, c->stream));
+    if (c->count) {
+        CU(cudaMemcpyAsync(nrows, c->rows, c->count * (uint64_t)c->w, cudaMemcpyDeviceToDevice, c->stream));
+        CU(cudaMemcpyAsync(nlive, c->live, c->capacity / 8, cudaMemcpyDeviceToDevice, c->stream));
+    }
+    CU(cudaStreamSynchronize(c->stream));
+    if (c->rows) cudaFree(c->rows);
+    if (c->live) cudaFree(c->live);
+    c->rows = nrows;
+    c->live = nlive;
+    c->capacity = cap;
+    return VL_OK;
+}
+
+// append-in-place growth: capacity doubles; if the doubled size does not fit, take exactly `need`
+int ensure_capacity(vl_corpus* c, uint64_t need_rows) {
+    if (need_rows <= c->capacity) return VL_OK;
+    const uint64_t doubled = std::max<uint64_t>(std::max<uint64_t>(need_rows, c->capacity * 2), 4096);
+    int rc = grow_to(c, doubled);
+    if (rc == VL_ENOMEM && doubled > need_rows) rc = grow_to(c, need_rows);
+    return rc;
+}
+
+int mark_appended(vl_corpus* c, uint64_t first, uint64_t n) {
+    if (n == 0) return VL_OK;
+    live_set_range_kernel<<<grid_for((n + 31) / 32 + 1, 256, c->sms), 256, 0, c->stream>>>(c->live, first, n);
+    LAUNCHED();
+    c->count = std::max(c->count, first + n);
+    c->live_count += n;
+    return VL_OK;
+}
+
+int ensure_pinned(vl_corpus* c, size_t bytes) {
+    if (bytes <= c->pinned_bytes) return VL_OK;
+    for (int i = 0; i < 2; ++i) {
+        if (c->pinned[i]) cudaFreeHost(c->pinned[i]);
+        c->pinned[i] = nullptr;
+    }
+    c->pinned_bytes = 0;
+    for (int i = 0; i < 2; ++i) CU(cudaMallocHost(&c->pinned[i], bytes));
+    c->pinned_bytes = bytes;
+    return VL_OK;
+}
+
+// repack `n` rows of f32 already on the device (src_dev) into corpus rows starting at `first`
+int repack_rows(vl_corpus* c, const float* src_dev, uint64_t first, uint64_t n, int kind) {
+    const uint64_t n_words = n * (uint64_t)c->w / 4;
+    uint32_t* dst = reinterpret_cast<uint32_t*>(c->rows + first * (uint64_t)c->w);
+    const unsigned g = grid_for(n_words, 256, c->sms);
+    if (kind == VL_SRC_F32_OFFSET)
+        repack_f32_offset_kernel<<<g, 256, 0, c->stream>>>(src_dev, n_words, dst, c->d_err);
+    else
+        repack_f32_bits_kernel<false><<<g, 256, 0, c->stream>>>(src_dev, n_words, dst, c->d_err);
+    LAUNCHED();
+    return VL_OK;
+}
+
+size_t src_row_bytes(int w, int kind) {
+    return kind == VL_SRC_U8 ? (size_t)w : kind == VL_SRC_F32_OFFSET ? (size_t)w * 4 : (size_t)w * 32;
+}
+
+int check_err_flag(vl_corpus* c, const char* what) {
+    int h = 0;
+    CU(cudaMemcpyAsync(&h, c->d_err, sizeof h, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    if (h) {
+        CU(cudaMemsetAsync(c->d_err, 0, sizeof(int), c->stream));
+        return fail(VL_ERANGE, "%s: stored value is not an integer in the encodable range", what);
+    }
+    return VL_OK;
+}
+
+// ---- scan dispatch -------------------------------------------------------------
+struct ScanPlan {
+    int C, WQ, WR, QT, T, S, stages, occ;
+    size_t smem;
+};
+
+template <int W, int METRIC, int C, int WQ>
+int launch_scan_cfg(vl_corpus* c, ScanParams& p, int n_queries, int k, ScanPlan* plan_out, bool dry) {
+    using Cfg = ScanCfg<W, C, WQ>;
+    auto kern = scan_topk_kernel<W, METRIC, C, WQ>;
+    const size_t fixed = Cfg::smem_bytes(0, k);
+    const size_t max_smem = 227 * 1024;
+    const size_t two_per_sm = 113 * 1024;
+    int stages = (int)std::min<size_t>(8, std::max<size_t>(2, (96 * 1024) / Cfg::TILE_BYTES));
+    if (c->tune_stages > 0) stages = c->tune_stages;
+    auto total = [&](int s) { return fixed + (size_t)s * (Cfg::STAGE_BYTES + 16); };
+    if (c->tune_stages <= 0)
+        while (stages > 2 && total(stages) > two_per_sm) --stages;
+    while (stages > 1 && total(stages) > max_smem) --stages;
+    const size_t smem = total(stages);
+    if (smem > max_smem) return fail(VL_EINVAL, "k=%d needs %zu B of shared memory per CTA (max %zu)", k, smem, max_smem);
+    CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int occ = 0;
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kScanThreads, smem));
+    if (occ < 1) return fail(VL_ECUDA, "scan kernel does not fit on an SM (smem %zu)", smem);
+
+    const int T = (n_queries + Cfg::QT - 1) / Cfg::QT;
+    const long slots = (long)c->sms * occ;
+    const long max_splits = std::max<long>(1, (long)p.n_tiles / 4);
+    long S = 1;
+    if (c->tune_splits > 0) {
+        S = c->tune_splits;
+    } else {
+        double best_eff = -1;
+        for (int waves = 1; waves <= 4; ++waves) {
+            long s = std::max<long>(1, (waves * slots) / T);
+            s = std::min(s, max_splits);
+            const long ctas = s * T;
+            const double eff = (double)ctas / ((double)((ctas + slots - 1) / slots) * slots);
+            if (eff > best_eff + 0.02) {
+                best_eff = eff;
+                S = s;
+            }
+            if (s == max_splits) break;
+        }
+    }
+    S = std::min<long>(S, std::max<long>(1, p.n_tiles));
+    S = std::min<long>(S, 65535);
+    if (plan_out) *plan_out = ScanPlan{C, WQ, Cfg::WR, Cfg::QT, T, (int)S, stages, occ, smem};
+    if (dry) return VL_OK;
+    p.stages = stages;
+    dim3 grid((unsigned)T, (unsigned)S);
+    kern<<<grid, kScanThreads, smem, c->stream>>>(p);
+    LAUNCHED();
+    return VL_OK;
+}
+
+template <int W, int METRIC>
+int launch_scan_wm(vl_corpus* c, ScanParams& p, int nq, int k, ScanPlan* plan, bool dry) {
+    if (nq <= 1) return launch_scan_cfg<W, METRIC, 1, 1>(c, p, nq, k, plan, dry);
+    if (nq <= 2) return launch_scan_cfg<W, METRIC, 2, 1>(c, p, nq, k, plan, dry);
+    if (nq <= 4) return launch_scan_cfg<W, METRIC, 4, 1>(c, p, nq, k, plan, dry);
+    if (nq <= 8) return launch_scan_cfg<W, METRIC, 8, 1>(c, p, nq, k, plan, dry);
+    if (nq <= 16) return launch_scan_cfg<W, METRIC, 8, 2>(c, p, nq, k, plan, dry);
+    if (nq <= 32) return launch_scan_cfg<W, METRIC, 8, 4>(c, p, nq, k, plan, dry);
+    return launch_scan_cfg<W, METRIC, 8, 8>(c, p, nq, k, plan, dry);
+}
+
+int launch_scan(vl_corpus* c, ScanParams& p, int nq, int k, int metric, ScanPlan* plan, bool dry) {
+#define VL_W(Wv)                                                                          \
+    case Wv:                                                                              \
+        return metric == VL_METRIC_HAMMING ? launch_scan_wm<Wv, kHamming>(c, p, nq, k, plan, dry) \
+                                           : launch_scan_wm<Wv, kXorSum>(c, p, nq, k, plan, dry);
+    switch (c->w) {
+        VL_W(64)
+        VL_W(128)
+        default:
+            return fail(VL_EINVAL, "unsupported row width %d", c->w);
+    }
+#undef VL_W
+}
+
+int fill_sentinels(cudaStream_t st, void* s_any, void* r_any, size_t n, bool s_dev, bool r_dev, size_t s_elem = 4) {
+    // 0xFF bytes are both sentinels (and a NaN/-inf is handled by the rescore caller)
+    if (s_dev)
+        CU(cudaMemsetAsync(s_any, 0xFF, n * s_elem, st));
+    else
+        memset(s_any, 0xFF, n * s_elem);
+    if (r_dev)
+        CU(cudaMemsetAsync(r_any, 0xFF, n * 8, st));
+    else
+        memset(r_any, 0xFF, n * 8);
+    return VL_OK;
+}
+
+// stage a filter mask into the handle's padded buffer (whole tiles, 16 B aligned)
+int stage_filter(vl_corpus* c, const uint32_t* filter_any, const uint32_t** out_dev) {
+    const uint64_t n_tiles = (c->count + kTileRows - 1) / kTileRows;
+    const size_t padded = n_tiles * kMaskWordsPerTile * 4;
+    const size_t given = ((c->count + 31) / 32) * 4;
+    const bool dev = is_device_ptr(filter_any);
+    if (dev && given == padded && (reinterpret_cast<uintptr_t>(filter_any) & 15) == 0) {
+        *out_dev = filter_any;
+        return VL_OK;
+    }
+    TRY(c->filt_buf.ensure(padded));
+    if (padded > given)
+        CU(cudaMemsetAsync(static_cast<uint8_t*>(c->filt_buf.p) + given, 0, padded - given, c->stream));
+    CU(cudaMemcpyAsync(c->filt_buf.p, filter_any, given, dev ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice,
+                       c->stream));
+    *out_dev = static_cast<const uint32_t*>(c->filt_buf.p);
+    return VL_OK;
+}
+
+}  // namespace
+
+// =============================== library ===============================
+extern "C" const char* vl_version(void) { return "vlite_b200 0.1.0 (sm_100a)"; }
+extern "C" const char* vl_last_error(void) { return g_err.c_str(); }
+extern "C" uint64_t vl_launch_count(void) { return g_launches.load(); }
+
+extern "C" int vl_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    int ok = 0;
+    for (int i = 0; i < n; ++i) {
+        cudaDeviceProp prop;
+        if (cudaGetDeviceProperties(&prop, i) == cudaSuccess && prop.major == 10) ++ok;
+    }
+    return ok;
+}
+
+// =============================== corpus ===============================
+extern "C" int vl_corpus_create(int device, int width_bytes, uint64_t capacity_rows, vl_corpus** out) {
+    if (!out) return fail(VL_EINVAL, "out is NULL");
+    *out = nullptr;
+    if (width_bytes != 64 && width_bytes != 128)
+        return fail(VL_EINVAL, "width_bytes must be 64 or 128 (got %d)", width_bytes);
+    int sms = 0;
+    TRY(check_device(device, &sms));
+    DeviceGuard g(device);
+    if (!g.ok) return fail(VL_ECUDA, "cudaSetDevice(%d) failed", device);
+    vl_corpus* c = new vl_corpus();
+    c->device = device;
+    c->w = width_bytes;
+    c->sms = sms;
+    auto bail = [&](int rc) {
+        vl_corpus_destroy(c);
+        return rc;
+    };
+    if (cudaMalloc(&c->d_err, sizeof(int)) != cudaSuccess || cudaMalloc(&c->d_counter, 8) != cudaSuccess)
+        return bail(fail(VL_ENOMEM, "cudaMalloc failed"));
+    cudaMemset(c->d_err, 0, sizeof(int));
+    cudaMemset(c->d_counter, 0, 8);
+    cudaEventCreate(&c->ev0);
+    cudaEventCreate(&c->ev1);
+    cudaEventCreate(&c->ev2);
+    for (int i = 0; i < 2; ++i) cudaEventCreateWithFlags(&c->stage_ev[i], cudaEventDisableTiming);
+    int rc = ensure_capacity(c, std::max<uint64_t>(capacity_rows, 1));
+    if (rc != VL_OK) return bail(rc);
+    *out = c;
+    return VL_OK;
+}
+
+extern "C" int vl_corpus_destroy(vl_corpus* c) {
+    if (!c) return VL_OK;
+    DeviceGuard g(c->device);
+    cudaStreamSynchronize(c->stream);
+    if (c->rows) cudaFree(c->rows);
+    if (c->live) cudaFree(c->live);
+    for (DevBuf* b : {&c->q_buf, &c->filt_buf, &c->part_s, &c->part_r, &c->out_s, &c->out_r, &c->stage[0],
+                      &c->stage[1], &c->rows_buf, &c->cand_buf, &c->misc})
+        b->release();
+    for (int i = 0; i < 2; ++i) {
+        if (c->pinned[i]) cudaFreeHost(c->pinned[i]);
+        if (c->stage_ev[i]) cudaEventDestroy(c->stage_ev[i]);
+    }
+    if (c->d_err) cudaFree(c->d_err);
+    if (c->d_counter) cudaFree(c->d_counter);
+    if (c->ev0) cudaEventDestroy(c->ev0);
+    if (c->ev1) cudaEventDestroy(c->ev1);
+    if (c->ev2) cudaEventDestroy(c->ev2);
+    delete c;
+    return VL_OK;
+}
+
+extern "C" int vl_corpus_set_stream(vl_corpus* c, void* cuda_stream) {
+    if (!c) return fail(VL_EINVAL, "corpus is NULL");
+    DeviceGuard g(c->device);
+    CU(cudaStreamSynchronize(c->stream));
+    c->stream = static_cast<cudaStream_t>(cuda_stream);
+    return VL_OK;
+}
+
+extern "C" int vl_corpus_reserve(vl_corpus* c, uint64_t capacity_rows) {
+    if (!c) return fail(VL_EINVAL, "corpus is NULL");
+    DeviceGuard g(c->device);
+    if (capacity_rows <= c->capacity) return VL_OK;
+    return grow_to(c, capacity_rows);  // exact: a 100+ GB shard must not be doubled
+}
+
+extern "C" int vl_corpus_append(vl_corpus* c, const uint8_t* rows_any, uint64_t n, uint64_t* first_row_out) {
+    if (!c) return fail(VL_EINVAL, "corpus is NULL");
+    if (n && !rows_any) return fail(VL_EINVAL, "rows is NULL");
+    DeviceGuard g(c->device);
+    const uint64_t first = c->count;
+    if (first_row_out) *first_row_out = first;
+    if (n == 0) return VL_OK;
+    TRY(ensure_capacity(c, first + n));
+    const bool dev = is_device_ptr(rows_any);
+    CU(cudaMemcpyAsync(c->rows + first * (uint64_t)c->w, rows_any, n * (uint64_t)c->w,
+                       dev ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, c->stream));
+    TRY(mark_appended(c, first, n));
+    if (!dev) CU(cudaStreamSynchronize(c->stream));
+    return VL_OK;
+}
+
+extern "C" int vl_corpus_append_f32(vl_corpus* c, const float* vals_any, uint64_t n, int src_kind,
+                                    uint64_t* first_row_out) {
+    if (!c) return fail(VL_EINVAL, "corpus is NULL");
+    if (src_kind != VL_SRC_F32_OFFSET && src_kind != VL_SRC_F32_BITS)
+        return fail(VL_EINVAL, "src_kind must be VL_SRC_F32_OFFSET or VL_SRC_F32_BITS");
+    if (n && !vals_any) return fail(VL_EINVAL, "vals is NULL");
+    DeviceGuard g(c->device);
+    const uint64_t first = c->count;
+    if (first_row_out) *first_row_out = first;
+    if (n == 0) return VL_OK;
+    TRY(ensure_capacity(c, first + n));
+    const size_t rb = src_row_bytes(c->w, src_kind);
+    if (is_device_ptr(vals_any)) {
+        if (reinterpret_cast<uintptr_t>(vals_any) & 15) return fail(VL_EINVAL, "device f32 rows must be 16 B aligned");
+        TRY(repack_rows(c, vals_any, first, n, src_kind));
+    } else {
+        const uint64_t chunk_rows = std::max<uint64_t>(1, (32ull << 20) / rb);
+        for (uint64_t done = 0, i = 0; done < n; done += chunk_rows, ++i) {
+            const uint64_t m = std::min(chunk_rows, n - done);
+            DevBuf& sb = c->stage[i & 1];
+            TRY(sb.ensure(chunk_rows * rb));
+            CU(cudaMemcpyAsync(sb.p, reinterpret_cast<const uint8_t*>(vals_any) + done * rb, m * rb,
+                               cudaMemcpyHostToDevice, c->stream));
+            TRY(repack_rows(c, static_cast<const float*>(sb.p), first + done, m, src_kind));
+        }
+    }
+    TRY(mark_appended(c, first, n));
+    int rc = check_err_flag(c, "vl_corpus_append_f32");
+    if (rc != VL_OK) {  // roll the append back
+        c->count = first;
+        c->live_count -= n;
+        cudaMemsetAsync(c->live, 0, c->capacity / 8, c->stream);  // conservative: rebuild below
+        if (first) {
+            live_set_range_kernel<<<grid_for(first / 32 + 1, 256, c->sms), 256, 0, c->stream>>>(c->live, 0, first);
+            g_launches.fetch_add(1);
+        }
+        cudaStreamSynchronize(c->stream);
+        return fail(VL_ERANGE, "vl_corpus_append_f32: a stored value is outside the encoding (tombstones were reset)");
+    }
+    return VL_OK;
+}
+
+extern "C" int vl_corpus_load_file(vl_corpus* c, const char* path, uint64_t byte_off, uint64_t byte_len,
+                                   int src_kind, uint64_t max_rows, uint64_t* first_row_out,
+                                   uint64_t* n_rows_out) {
+    if (!c || !path) return fail(VL_EINVAL, "NULL argument");
+    if (src_kind < VL_SRC_U8 || src_kind > VL_SRC_F32_BITS) return fail(VL_EINVAL, "bad src_kind %d", src_kind);
+    DeviceGuard g(c->device);
+    const size_t rb = src_row_bytes(c->w, src_kind);
+    uint64_t n = byte_len / rb;  // floor, like vlite/ctx.py:115
+    if (max_rows && n > max_rows) n = max_rows;
+    const uint64_t first = c->count;
+    if (first_row_out) *first_row_out = first;
+    if (n_rows_out) *n_rows_out = n;
+    if (n == 0) return VL_OK;
+    int fd = open(path, O_RDONLY);
+    if (fd < 0) return fail(VL_EIO, "cannot open %s", path);
+    int rc = ensure_capacity(c, first + n);
+    const uint64_t chunk_rows = std::max<uint64_t>(1, (32ull << 20) / rb);
+    if (rc == VL_OK) rc = ensure_pinned(c, chunk_rows * rb);
+    for (uint64_t done = 0, i = 0; rc == VL_OK && done < n; done += chunk_rows, ++i) {
+        const int b = (int)(i & 1);
+        const uint64_t m = std::min(chunk_rows, n - done);
+        if (i >= 2 && cudaEventSynchronize(c->stage_ev[b]) != cudaSuccess) {
+            rc = fail(VL_ECUDA, "event sync failed");
+            break;
+        }
+        size_t want = m * rb, got = 0;
+        while (got < want) {
+            ssize_t r = pread(fd, static_cast<uint8_t*>(c->pinned[b]) + got, want - got, byte_off + done * rb + got);
+            if (r <= 0) break;
+            got += (size_t)r;
+        }
+        if (got != want) {
+            rc = fail(VL_EIO, "short read from %s", path);
+            break;
+        }
+        cudaError_t e;
+        if (src_kind == VL_SRC_U8) {
+            e = cudaMemcpyAsync(c->rows + (first + done) * (uint64_t)c->w, c->pinned[b], want, cudaMemcpyHostToDevice,
+                                c->stream);
+        } else {
+            rc = c->stage[b].ensure(chunk_rows * rb);
+            if (rc != VL_OK) break;
+            e = cudaMemcpyAsync(c->stage[b].p, c->pinned[b], want, cudaMemcpyHostToDevice, c->stream);
+            if (e == cudaSuccess) rc = repack_rows(c, static_cast<const float*>(c->stage[b].p), first + done, m, src_kind);
+        }
+        if (e != cudaSuccess) {
+            rc = fail(VL_ECUDA, "H2D copy failed: %s", cudaGetErrorString(e));
+            break;
+        }
+        cudaEventRecord(c->stage_ev[b], c->stream);
+    }
+    close(fd);
+    cudaStreamSynchronize(c->stream);
+    if (rc != VL_OK) return rc;
+    if (src_kind != VL_SRC_U8) TRY(check_err_flag(c, "vl_corpus_load_file"));
+    TRY(mark_appended(c, first, n));
+    CU(cudaStreamSynchronize(c->stream));
+    return VL_OK;
+}
+
+extern "C" int vl_corpus_set_row(vl_corpus* c, uint64_t row, const uint8_t* row_any) {
+    if (!c || !row_any) return fail(VL_EINVAL, "NULL argument");
+    if (row >= c->count) return fail(VL_EINVAL, "row %llu out of range", (unsigned long long)row);
+    DeviceGuard g(c->device);
+    const bool dev = is_device_ptr(row_any);
+    CU(cudaMemcpyAsync(c->rows + row * (uint64_t)c->w, row_any, c->w,
+                       dev ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, c->stream));
+    if (!dev) CU(cudaStreamSynchronize(c->stream));
+    return VL_OK;
+}
+
+extern "C" int vl_corpus_tombstone(vl_corpus* c, const uint64_t* rows_host, uint64_t n) {
+    if (!c) return fail(VL_EINVAL, "corpus is NULL");
+    if (n == 0) return VL_OK;
+    if (!rows_host) return fail(VL_EINVAL, "rows is NULL");
+    DeviceGuard g(c->device);
+    TRY(c->misc.ensure(n * 8));
+    CU(cudaMemsetAsync(c->d_counter, 0, 8, c->stream));
+    CU(cudaMemcpyAsync(c->misc.p, rows_host, n * 8, cudaMemcpyHostToDevice, c->stream));
+    live_clear_rows_kernel<<<grid_for(n, 256, c->sms), 256, 0, c->stream>>>(
+        c->live, static_cast<const uint64_t*>(c->misc.p), n, c->count, c->d_counter);
+    LAUNCHED();
+    unsigned long long cleared = 0;
+    CU(cudaMemcpyAsync(&cleared, c->d_counter, 8, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    c->live_count -= cleared;
+    return VL_OK;
+}
+
+extern "C" int vl_corpus_clear(vl_corpus* c) {
+    if (!c) return fail(VL_EINVAL, "corpus is NULL");
+    DeviceGuard g(c->device);
+    CU(cudaMemsetAsync(c->live, 0, c->capacity / 8, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    c->count = 0;
+    c->live_count = 0;
+    return VL_OK;
+}
+
+extern "C" int vl_corpus_rows(const vl_corpus* c, uint64_t* rows, uint64_t* live_rows) {
+    if (!c) return fail(VL_EINVAL, "corpus is NULL");
+    if (rows) *rows = c->count;
+    if (live_rows) *live_rows = c->live_count;
+    return VL_OK;
+}
+
+extern "C" int vl_corpus_width(const vl_corpus* c) { return c ? c->w : VL_EINVAL; }
+
+extern "C" int vl_corpus_set_base_row(vl_corpus* c, uint64_t base_row) {
+    if (!c) return fail(VL_EINVAL, "corpus is NULL");
+    c->base_row = base_row;
+    return VL_OK;
+}
+
+extern "C" int vl_corpus_read(vl_corpus* c, uint64_t first, uint64_t n, uint8_t* out_host) {
+    if (!c || (n && !out_host)) return fail(VL_EINVAL, "NULL argument");
+    if (first + n > c->count) return fail(VL_EINVAL, "rows [%llu, %llu) out of range", (unsigned long long)first,
+                                          (unsigned long long)(first + n));
+    DeviceGuard g(c->device);
+    if (n == 0) return VL_OK;
+    CU(cudaMemcpyAsync(out_host, c->rows + first * (uint64_t)c->w, n * (uint64_t)c->w, cudaMemcpyDeviceToHost,
+                       c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return VL_OK;
+}
+
+extern "C" int vl_corpus_device_ptrs(vl_corpus* c, void** rows_dev, void** live_mask_dev) {
+    if (!c) return fail(VL_EINVAL, "corpus is NULL");
+    if (rows_dev) *rows_dev = c->rows;
+    if (live_mask_dev) *live_mask_dev = c->live;
+    return VL_OK;
+}
+
+extern "C" int vl_corpus_fill_synthetic(vl_corpus* c, uint64_t seed, uint64_t first, uint64_t n, uint64_t period) {
+    if (!c) return fail(VL_EINVAL, "corpus is NULL");
+    if (first > c->count) return fail(VL_EINVAL, "first (%llu) is past the end of the corpus", (unsigned long long)first);
+    DeviceGuard g(c->device);
+    if (n == 0) return VL_OK;
+    TRY(ensure_capacity(c, first + n));
+    synth_fill_kernel<<<grid_for(n * (uint64_t)(c->w / 8), 256, c->sms), 256, 0, c->stream>>>(
+        c->rows, c->w, seed, first, n, period, c->base_row);
+    LAUNCHED();
+    if (first + n > c->count) {
+        const uint64_t added_first = c->count;
+        TRY(mark_appended(c, added_first, first + n - added_first));
+    }
+    return VL_OK;
+}
+
+extern "C" int vl_synth_filter_mask(vl_corpus* c, uint64_t seed, uint64_t threshold, uint32_t* mask_dev) {
+    if (!c || !mask_dev) return fail(VL_EINVAL, "NULL argument");
+    if (!is_device_ptr(mask_dev)) return fail(VL_EINVAL, "mask must be device memory");
+    DeviceGuard g(c->device);
+    const uint64_t n_words = (c->count + 31) / 32;
+    if (n_words == 0) return VL_OK;
+    synth_mask_kernel<<<grid_for(n_words, 128, c->sms), 128, 0, c->stream>>>(mask_dev, c->count, n_words, seed,
+                                                                            c->base_row, threshold);
+    LAUNCHED();
+    return VL_OK;
+}
+
+// =============================== search ===============================
+extern "C" int vl_search(vl_corpus* c, const uint8_t* queries_any, int n_queries, int k, int metric,
+                         const uint32_t* filter_mask_any, uint32_t* out_score_any, uint64_t* out_row_any) {
+    if (!c) return fail(VL_EINVAL, "corpus is NULL");
+    if (!queries_any || !out_score_any || !out_row_any) return fail(VL_EINVAL, "NULL argument");
+    if (n_queries < 1) return fail(VL_EINVAL, "n_queries must be >= 1");
+    if (k < 1 || k > VL_MAX_K) return fail(VL_EINVAL, "k must be in [1, %d]", VL_MAX_K);
+    if (metric != VL_METRIC_HAMMING && metric != VL_METRIC_XORSUM) return fail(VL_EINVAL, "bad metric %d", metric);
+    DeviceGuard g(c->device);
+    cudaStream_t st = c->stream;
+    const bool q_dev = is_device_ptr(queries_any);
+    const bool s_dev = is_device_ptr(out_score_any), r_dev = is_device_ptr(out_row_any);
+    const size_t n_out = (size_t)n_queries * k;
+    c->timed = false;
+    if (c->count == 0 || c->live_count == 0) {
+        TRY(fill_sentinels(st, out_score_any, out_row_any, n_out, s_dev, r_dev));
+        return VL_OK;
+    }
+
+    const uint8_t* q_ptr = queries_any;
+    if (!q_dev || (reinterpret_cast<uintptr_t>(queries_any) & 15)) {
+        TRY(c->q_buf.ensure((size_t)n_queries * c->w));
+        CU(cudaMemcpyAsync(c->q_buf.p, queries_any, (size_t)n_queries * c->w,
+                           q_dev ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, st));
+        q_ptr = static_cast<const uint8_t*>(c->q_buf.p);
+    }
+    const uint32_t* filt = nullptr;
+    if (filter_mask_any) TRY(stage_filter(c, filter_mask_any, &filt));
+
+    uint32_t* o_s = out_score_any;
+    uint64_t* o_r = out_row_any;
+    if (!s_dev) {
+        TRY(c->out_s.ensure(n_out * 4));
+        o_s = static_cast<uint32_t*>(c->out_s.p);
+    }
+    if (!r_dev) {
+        TRY(c->out_r.ensure(n_out * 8));
+        o_r = static_cast<uint64_t*>(c->out_r.p);
+    }
+
+    if (c->timing) CU(cudaEventRecord(c->ev0, st));
+    {
+        // k <= 128: one scan + merge.  Larger k: ceil(k/128) passes, each returning the next 128
+        // keys after a per-query cursor (exact and deterministic for any tie pattern).
+        ScanParams p{};
+        p.rows = c->rows;
+        p.live = c->live;
+        p.filter = filt;
+        p.queries = q_ptr;
+        p.base_row = c->base_row;
+        p.n_rows = (uint32_t)c->count;
+        p.n_tiles = (uint32_t)((c->count + kTileRows - 1) / kTileRows);
+        p.n_queries = n_queries;
+        const int n_pass = (k + kWarpListMaxK - 1) / kWarpListMaxK;
+        uint32_t *cur_s = nullptr, *cur_r = nullptr;
+        if (n_pass > 1) {
+            TRY(c->cand_buf.ensure((size_t)n_queries * 8));
+            cur_s = static_cast<uint32_t*>(c->cand_buf.p);
+            cur_r = cur_s + n_queries;
+        }
+        for (int pass = 0; pass < n_pass; ++pass) {
+            const int k_pass = std::min(kWarpListMaxK, k - pass * kWarpListMaxK);
+            p.k = k_pass;
+            p.cur_score = pass ? cur_s : nullptr;
+            p.cur_row = pass ? cur_r : nullptr;
+            ScanPlan plan{};
+            TRY(launch_scan(c, p, n_queries, k_pass, metric, &plan, /*dry=*/true));
+            const size_t n_lists = (size_t)plan.S * plan.WR;
+            const size_t n_part = n_lists * (size_t)n_queries * k_pass;
+            TRY(c->part_s.ensure(n_part * 4));
+            TRY(c->part_r.ensure(n_part * 8));
+            p.part_scores = static_cast<uint32_t*>(c->part_s.p);
+            p.part_rows = static_cast<uint64_t*>(c->part_r.p);
+            // corpus read once and far larger than L2 -> stream it; otherwise let L2 keep it
+            p.evict_first = (plan.T == 1 && n_pass == 1 && c->count * (uint64_t)c->w > (96ull << 20)) ? 1 : 0;
+            TRY(launch_scan(c, p, n_queries, k_pass, metric, nullptr, /*dry=*/false));
+            if (c->timing && pass == 0) CU(cudaEventRecord(c->ev1, st));
+            const unsigned mg = (unsigned)((n_queries + kMergeWarps - 1) / kMergeWarps);
+            merge_topk_kernel<<<mg, kMergeWarps * 32, kMergeWarps * n_lists * sizeof(uint16_t), st>>>(
+                p.part_scores, p.part_rows, (int)n_lists, n_queries, k_pass, k_pass, o_s, o_r, k,
+                pass * kWarpListMaxK);
+            LAUNCHED();
+            if (pass + 1 < n_pass) {
+                cursor_update_kernel<<<(n_queries + 127) / 128, 128, 0, st>>>(
+                    o_s, o_r, n_queries, k, pass * kWarpListMaxK + k_pass - 1, c->base_row, cur_s, cur_r);
+                LAUNCHED();
+            }
+        }
+    }
+    if (c->timing) {
+        CU(cudaEventRecord(c->ev2, st));
+        c->timed = true;
+    }
+    if (!s_dev) CU(cudaMemcpyAsync(out_score_any, o_s, n_out * 4, cudaMemcpyDeviceToHost, st));
+    if (!r_dev) CU(cudaMemcpyAsync(out_row_any, o_r, n_out * 8, cudaMemcpyDeviceToHost, st));
+    if (!s_dev || !r_dev || !q_dev) CU(cudaStreamSynchronize(st));
+    return VL_OK;
+}
+
+extern "C" int vl_scores(vl_corpus* c, const uint8_t* query_any, int metric, uint64_t first, uint64_t n,
+                         uint32_t* out_any) {
+    if (!c || !query_any || !out_any) return fail(VL_EINVAL, "NULL argument");
+    if (first + n > c->count) return fail(VL_EINVAL, "rows out of range");
+    if (metric != VL_METRIC_HAMMING && metric != VL_METRIC_XORSUM) return fail(VL_EINVAL, "bad metric %d", metric);
+    DeviceGuard g(c->device);
+    if (n == 0) return VL_OK;
+    cudaStream_t st = c->stream;
+    TRY(c->q_buf.ensure(c->w));
+    CU(cudaMemcpyAsync(c->q_buf.p, query_any, c->w,
+                       is_device_ptr(query_any) ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, st));
+    const bool o_dev = is_device_ptr(out_any);
+    uint32_t* o = out_any;
+    if (!o_dev) {
+        TRY(c->out_s.ensure(n * 4));
+        o = static_cast<uint32_t*>(c->out_s.p);
+    }
+    const unsigned gr = grid_for(n, 256, c->sms);
+    if (metric == VL_METRIC_HAMMING)
+        scores_kernel<kHamming><<<gr, 256, c->w, st>>>(c->rows, c->w, static_cast<const uint8_t*>(c->q_buf.p), first, n, o);
+    else
+        scores_kernel<kXorSum><<<gr, 256, c->w, st>>>(c->rows, c->w, static_cast<const uint8_t*>(c->q_buf.p), first, n, o);
+    LAUNCHED();
+    if (!o_dev) {
+        CU(cudaMemcpyAsync(out_any, o, n * 4, cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+    }
+    return VL_OK;
+}
+
+extern "C" int vl_merge_topk(int device, void* cuda_stream, const uint32_t* scores_dev, const uint64_t* rows_dev,
+                             int n_lists, int n_queries, int k_in, int k_out, uint32_t* out_score_dev,
+                             uint64_t* out_row_dev) {
+    if (!scores_dev || !rows_dev || !out_score_dev || !out_row_dev) return fail(VL_EINVAL, "NULL argument");
+    if (n_lists < 1 || n_queries < 1 || k_in < 1 || k_out < 1 || k_in > 65535)
+        return fail(VL_EINVAL, "bad merge shape");
+    TRY(check_device(device, nullptr));
+    DeviceGuard g(device);
+    const size_t smem = (size_t)kMergeWarps * n_lists * sizeof(uint16_t);
+    if (smem > 200 * 1024) return fail(VL_EINVAL, "too many lists (%d)", n_lists);
+    if (smem > 48 * 1024)
+        CU(cudaFuncSetAttribute(merge_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const unsigned mg = (unsigned)((n_queries + kMergeWarps - 1) / kMergeWarps);
+    merge_topk_kernel<<<mg, kMergeWarps * 32, smem, static_cast<cudaStream_t>(cuda_stream)>>>(
+        scores_dev, rows_dev, n_lists, n_queries, k_in, k_out, out_score_dev, out_row_dev, k_out, 0);
+    LAUNCHED();
+    return VL_OK;
+}
+
+// =============================== rescore ===============================
+extern "C" int vl_rescore(vl_corpus* c, const int8_t* docs_i8_dev, uint64_t n_docs, int dims, const void* queries_any,
+                          int qtype, const uint64_t* cand_rows_any, int n_queries, int n_cand, int k,
+                          float* out_score_any, uint64_t* out_row_any) {
+    if (!c || !docs_i8_dev || !queries_any || !cand_rows_any || !out_score_any || !out_row_any)
+        return fail(VL_EINVAL, "NULL argument");
+    if (!is_device_ptr(docs_i8_dev)) return fail(VL_EINVAL, "docs must be device memory");
+    if (dims < 16 || dims % 16) return fail(VL_EINVAL, "dims must be a positive multiple of 16");
+    if (qtype != VL_QTYPE_F32 && qtype != VL_QTYPE_I8) return fail(VL_EINVAL, "bad qtype");
+    if (n_queries < 1 || n_cand < 1 || n_cand > kRescoreMaxCand || k < 1 || k > n_cand)
+        return fail(VL_EINVAL, "need 1 <= k <= n_cand <= %d", kRescoreMaxCand);
+    DeviceGuard g(c->device);
+    cudaStream_t st = c->stream;
+    const size_t qbytes = (size_t)n_queries * dims * (qtype == VL_QTYPE_I8 ? 1 : 4);
+    const void* q_ptr = queries_any;
+    const bool q_dev = is_device_ptr(queries_any);
+    if (!q_dev || (reinterpret_cast<uintptr_t>(queries_any) & 15)) {
+        TRY(c->q_buf.ensure(qbytes));
+        CU(cudaMemcpyAsync(c->q_buf.p, queries_any, qbytes, q_dev ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, st));
+        q_ptr = c->q_buf.p;
+    }
+    const uint64_t* cand = cand_rows_any;
+    const bool c_dev = is_device_ptr(cand_rows_any);
+    if (!c_dev) {
+        TRY(c->misc.ensure((size_t)n_queries * n_cand * 8));
+        CU(cudaMemcpyAsync(c->misc.p, cand_rows_any, (size_t)n_queries * n_cand * 8, cudaMemcpyHostToDevice, st));
+        cand = static_cast<const uint64_t*>(c->misc.p);
+    }
+    const bool s_dev = is_device_ptr(out_score_any), r_dev = is_device_ptr(out_row_any);
+    const size_t n_out = (size_t)n_queries * k;
+    float* o_s = out_score_any;
+    uint64_t* o_r = out_row_any;
+    if (!s_dev) {
+        TRY(c->out_s.ensure(n_out * 4));
+        o_s = static_cast<float*>(c->out_s.p);
+    }
+    if (!r_dev) {
+        TRY(c->out_r.ensure(n_out * 8));
+        o_r = static_cast<uint64_t*>(c->out_r.p);
+    }
+    int n_sort = 4;
+    while (n_sort < n_cand) n_sort <<= 1;
+    RescoreParams p{};
+    p.docs = docs_i8_dev;
+    p.queries = q_ptr;
+    p.cand = cand;
+    p.out_scores = o_s;
+    p.out_rows = o_r;
+    p.base_row = c->base_row;
+    p.n_docs = n_docs;
+    p.dims = dims;
+    p.n_cand = n_cand;
+    p.n_sort = n_sort;
+    p.k = k;
+    const size_t smem = (size_t)n_sort * 12 + (size_t)dims * (qtype == VL_QTYPE_I8 ? 1 : 4);
+    c->timed = false;
+    if (c->timing) CU(cudaEventRecord(c->ev0, st));
+    if (qtype == VL_QTYPE_I8) {
+        CU(cudaFuncSetAttribute(rescore_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        rescore_kernel<true><<<n_queries, kRescoreThreads, smem, st>>>(p);
+    } else {
+        CU(cudaFuncSetAttribute(rescore_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        rescore_kernel<false><<<n_queries, kRescoreThreads, smem, st>>>(p);
+    }
+    LAUNCHED();
+    if (c->timing) {
+        CU(cudaEventRecord(c->ev1, st));
+        CU(cudaEventRecord(c->ev2, st));
+        c->timed = true;
+    }
+    if (!s_dev) CU(cudaMemcpyAsync(out_score_any, o_s, n_out * 4, cudaMemcpyDeviceToHost, st));
+    if (!r_dev) CU(cudaMemcpyAsync(out_row_any, o_r, n_out * 8, cudaMemcpyDeviceToHost, st));
+    if (!s_dev || !r_dev || !q_dev || !c_dev) CU(cudaStreamSynchronize(st));
+    return VL_OK;
+}
+
+extern "C" int vl_quantize_binary(int device, void* cuda_stream, const float* x_any, uint64_t n, int dims,
+                                  uint8_t* out_any) {
+    if (!x_any || !out_any) return fail(VL_EINVAL, "NULL argument");
+    if (dims < 32 || dims % 32) return fail(VL_EINVAL, "dims must be a positive multiple of 32");
+    int sms = 0;
+    TRY(check_device(device, &sms));
+    DeviceGuard g(device);
+    if (n == 0) return VL_OK;
+    cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+    const bool x_dev = is_device_ptr(x_any), o_dev = is_device_ptr(out_any);
+    const size_t in_bytes = n * (size_t)dims * 4, out_bytes = n * (size_t)dims / 8;
+    void *xin = nullptr, *xout = nullptr;
+    const float* src = x_any;
+    uint8_t* dst = out_any;
+    if (!x_dev) {
+        CU(cudaMalloc(&xin, in_bytes));
+        CU(cudaMemcpyAsync(xin, x_any, in_bytes, cudaMemcpyHostToDevice, st));
+        src = static_cast<const float*>(xin);
+    }
+    if (!o_dev) {
+        CU(cudaMalloc(&xout, out_bytes));
+        dst = static_cast<uint8_t*>(xout);
+    }
+    const uint64_t n_words = out_bytes / 4;
+    repack_f32_bits_kernel<true><<<grid_for(n_words, 256, sms), 256, 0, st>>>(src, n_words,
+                                                                            reinterpret_cast<uint32_t*>(dst), nullptr);
+    LAUNCHED();
+    if (!o_dev) CU(cudaMemcpyAsync(out_any, dst, out_bytes, cudaMemcpyDeviceToHost, st));
+    if (!x_dev || !o_dev) {
+        CU(cudaStreamSynchronize(st));
+        if (xin) cudaFree(xin);
+        if (xout) cudaFree(xout);
+    }
+    return VL_OK;
+}
+
+extern "C" int vl_synth_docs_i8(int device, void* cuda_stream, uint64_t seed, uint64_t first_row, uint64_t n, int dims,
+                                int8_t* out_dev) {
+    if (!out_dev || !is_device_ptr(out_dev)) return fail(VL_EINVAL, "out must be device memory");
+    if (dims < 8 || dims % 8 || dims > 1024) return fail(VL_EINVAL, "dims must be a multiple of 8, at most 1024");
+    int sms = 0;
+    TRY(check_device(device, &sms));
+    DeviceGuard g(device);
+    if (n == 0) return VL_OK;
+    synth_docs_kernel<<<grid_for(n * (uint64_t)(dims / 8), 256, sms), 256, 0, static_cast<cudaStream_t>(cuda_stream)>>>(
+        out_dev, dims, seed, first_row, n);
+    LAUNCHED();
+    return VL_OK;
+}
+
+// =============================== measurement ===============================
+extern "C" int vl_microbench(int device, int kind, int iters, double* ops_per_sec_out, double* ms_out) {
+    if (kind < 0 || kind > 4 || iters < 1) return fail(VL_EINVAL, "bad microbench arguments");
+    int sms = 0;
+    TRY(check_device(device, &sms));
+    DeviceGuard g(device);
+    uint32_t* out = nullptr;
+    CU(cudaMalloc(&out, 4));
+    cudaEvent_t e0, e1;
+    CU(cudaEventCreate(&e0));
+    CU(cudaEventCreate(&e1));
+    const int threads = 256, blocks = sms * 8;
+    auto run = [&](int it) {
+        switch (kind) {
+            case 0: microbench_kernel<0><<<blocks, threads>>>(it, 12345u, out); break;
+            case 1: microbench_kernel<1><<<blocks, threads>>>(it, 12345u, out); break;
+            case 2: microbench_kernel<2><<<blocks, threads>>>(it, 12345u, out); break;
+            case 3: microbench_kernel<3><<<blocks, threads>>>(it, 12345u, out); break;
+            default: microbench_kernel<4><<<blocks, threads>>>(it, 12345u, out); break;
+        }
+        g_launches.fetch_add(1);
+    };
+    run(std::max(1, iters / 10));  // warm-up
+    CU(cudaDeviceSynchronize());
+    float best = 1e30f;
+    for (int rep = 0; rep < 3; ++rep) {
+        CU(cudaEventRecord(e0));
+        run(iters);
+        CU(cudaEventRecord(e1));
+        CU(cudaEventSynchronize(e1));
+        float ms = 0;
+        CU(cudaEventElapsedTime(&ms, e0, e1));
+        best = std::min(best, ms);
+    }
+    CU(cudaGetLastError());
+    const double ops = (double)blocks * threads * (double)iters * kMbChains;  // primary op count (POPC for kind 4)
+    if (ops_per_sec_out) *ops_per_sec_out = ops / (best * 1e-3);
+    if (ms_out) *ms_out = best;
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(out);
+    return VL_OK;
+}
+
+extern "C" int vl_set_timing(vl_corpus* c, int enabled) {
+    if (!c) return fail(VL_EINVAL, "corpus is NULL");
+    c->timing = enabled != 0;
+    c->timed = false;
+    return VL_OK;
+}
+
+extern "C" int vl_last_timing(vl_corpus* c, float* total_ms, float* scan_ms) {
+    if (!c) return fail(VL_EINVAL, "corpus is NULL");
+    if (!c->timed) return fail(VL_EINVAL, "no timed call recorded (vl_set_timing first)");
+    DeviceGuard g(c->device);
+    CU(cudaEventSynchronize(c->ev2));
+    float t = 0, s = 0;
+    CU(cudaEventElapsedTime(&t, c->ev0, c->ev2));
+    CU(cudaEventElapsedTime(&s, c->ev0, c->ev1));
+    if (total_ms) *total_ms = t;
+    if (scan_ms) *scan_ms = s;
+    return VL_OK;
+}
+
+extern "C" int vl_set_tuning(vl_corpus* c, int row_splits, int stages) {
+    if (!c) return fail(VL_EINVAL, "corpus is NULL");
+    c->tune_splits = row_splits;
+    c->tune_stages = stages;
+    return VL_OK;
+}

@@ -1,0 +1,96 @@
+// Kernel 5: device-side repack of stored float32 rows into raw ubinary bytes, plus the
+// live-mask maintenance kernels (append / tombstone) and sign quantisation.
+//
+// Replaces the per-row struct.unpack_from("<64f") -> Python list -> np.array of the reference's
+// CTX load (vlite/ctx.py:116-119, vlite/main.py:50): the EMBEDDINGS payload is copied to the
+// device as-is and converted there.
+#pragma once
+#include "common.cuh"
+
+namespace vl {
+
+// float32 holding int8(u8)-128 in [-256,-1] (vlite/model.py:44) or a raw byte in [0,255]
+// -> u8.  One thread converts 4 values -> one 32-bit word of the row.
+__global__ void repack_f32_offset_kernel(const float* __restrict__ src, uint64_t n_words,
+                                         uint32_t* __restrict__ dst, int* __restrict__ err) {
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n_words;
+         i += (uint64_t)gridDim.x * blockDim.x) {
+        const float4 v = reinterpret_cast<const float4*>(src)[i];
+        const float f[4] = {v.x, v.y, v.z, v.w};
+        uint32_t out = 0;
+        bool bad = false;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float r = rintf(f[j]);
+            bad |= (r != f[j]) || (r < -256.f) || (r > 255.f);
+            const int iv = (int)r;
+            const uint32_t u = iv < 0 ? (uint32_t)((iv + 256) ^ 0x80) : (uint32_t)iv;
+            out |= (u & 0xFFu) << (8 * j);
+        }
+        if (bad) atomicOr(err, 1);
+        dst[i] = out;
+    }
+}
+
+// float32 0.0/1.0 (or any sign-quantisable value when SIGN) one per bit -> packbits MSB-first.
+// One thread converts 32 values -> one 32-bit word (4 bytes, byte j = values 8j..8j+7).
+template <bool SIGN>
+__global__ void repack_f32_bits_kernel(const float* __restrict__ src, uint64_t n_words,
+                                       uint32_t* __restrict__ dst, int* __restrict__ err) {
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n_words;
+         i += (uint64_t)gridDim.x * blockDim.x) {
+        const float4* s = reinterpret_cast<const float4*>(src) + i * 8;
+        uint32_t out = 0;
+        bool bad = false;
+#pragma unroll
+        for (int b = 0; b < 8; ++b) {
+            const float4 v = s[b];
+            const float f[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int bit_index = b * 4 + j;  // 0..31 within the word's 32 values
+                bool one;
+                if constexpr (SIGN) {
+                    one = f[j] > 0.f;  // vlite/model.py:41
+                } else {
+                    one = f[j] > 0.5f;
+                    bad |= (f[j] != 0.f) && (f[j] != 1.f);
+                }
+                // value v of byte (bit_index/8) is bit 7-(bit_index%8) (np.packbits, MSB first)
+                if (one) out |= 1u << (8 * (bit_index >> 3) + (7 - (bit_index & 7)));
+            }
+        }
+        if (bad) atomicOr(err, 1);
+        dst[i] = out;
+    }
+}
+
+// set live bits for rows [first, first+n)
+__global__ void live_set_range_kernel(uint32_t* __restrict__ live, uint64_t first, uint64_t n) {
+    const uint64_t w0 = first >> 5, w1 = (first + n + 31) >> 5;
+    for (uint64_t w = w0 + blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; w < w1;
+         w += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t lo = w << 5;
+        uint32_t bits = 0xFFFFFFFFu;
+        if (lo < first) bits &= 0xFFFFFFFFu << (first - lo);
+        if (lo + 32 > first + n) bits &= 0xFFFFFFFFu >> (lo + 32 - (first + n));
+        if (bits == 0xFFFFFFFFu)
+            live[w] = bits;
+        else
+            atomicOr(&live[w], bits);
+    }
+}
+
+// clear live bits for the listed rows; counts how many were live
+__global__ void live_clear_rows_kernel(uint32_t* __restrict__ live, const uint64_t* __restrict__ rows, uint64_t n,
+                                       uint64_t n_rows, unsigned long long* __restrict__ cleared) {
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t r = rows[i];
+        if (r >= n_rows) continue;
+        const uint32_t bit = 1u << (r & 31);
+        const uint32_t old = atomicAnd(&live[r >> 5], ~bit);
+        if (old & bit) atomicAdd(cleared, 1ull);
+    }
+}
+
+}  // namespace vl

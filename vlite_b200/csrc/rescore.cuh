@@ -1,0 +1,130 @@
+// Kernel 3: rescoring of the binary scan's candidates against int8 document embeddings.
+//
+// North-star piece (3).  The reference has no rescore (nearest code: the unused cos_sim,
+// vlite/utils.py:205-208); expected values are defined by oracle/search.py::rescore
+// ("parity unpinned").  Per query the C candidate rows are scattered 1 KB gathers, so the
+// kernel is gather-bandwidth bound, not a GEMM: one CTA per query, the query staged in
+// shared memory, one warp per candidate row with 128-bit coalesced loads, DP4A (int8 query,
+// exact int32) or FFMA (fp32 query, fp32 accumulate), then an in-CTA bitonic sort by
+// (score descending, row ascending) and the first k written out.
+#pragma once
+#include <math_constants.h>
+
+#include "common.cuh"
+
+namespace vl {
+
+constexpr int kRescoreThreads = 256;
+constexpr int kRescoreMaxCand = 2048;
+
+struct RescoreParams {
+    const int8_t* docs;        // n_docs x dims, LOCAL row index
+    const void* queries;       // Q x dims, float32 or int8
+    const uint64_t* cand;      // Q x n_cand GLOBAL rows, sentinel padded
+    float* out_scores;         // Q x k
+    uint64_t* out_rows;        // Q x k
+    uint64_t base_row;
+    uint64_t n_docs;
+    int dims, n_cand, n_sort, k;  // n_sort = next pow2 >= n_cand
+};
+
+template <bool QI8>
+__global__ void __launch_bounds__(kRescoreThreads) rescore_kernel(const RescoreParams p) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    const int q = blockIdx.x;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int dims = p.dims;
+    float* s_score = reinterpret_cast<float*>(smem);                       // n_sort
+    uint64_t* s_row = reinterpret_cast<uint64_t*>(s_score + p.n_sort);     // n_sort (8B aligned: n_sort even)
+    uint8_t* s_q = reinterpret_cast<uint8_t*>(s_row + p.n_sort);           // dims * (1 | 4)
+
+    const size_t qbytes = (size_t)dims * (QI8 ? 1 : 4);
+    {
+        const uint4* src = reinterpret_cast<const uint4*>(static_cast<const uint8_t*>(p.queries) + (size_t)q * qbytes);
+        uint4* dst = reinterpret_cast<uint4*>(s_q);
+        for (int i = threadIdx.x; i < (int)(qbytes / 16); i += kRescoreThreads) dst[i] = src[i];
+    }
+    for (int i = threadIdx.x; i < p.n_sort; i += kRescoreThreads) {
+        s_score[i] = -CUDART_INF_F;
+        s_row[i] = kSentinelRow;
+    }
+    __syncthreads();
+
+    const int chunks = dims / 16;  // 16 int8 per 128-bit load
+    for (int c = warp; c < p.n_cand; c += kRescoreThreads / 32) {
+        const uint64_t grow = p.cand[(size_t)q * p.n_cand + c];
+        if (grow == kSentinelRow) continue;
+        const uint64_t lrow = grow - p.base_row;
+        if (lrow >= p.n_docs) continue;  // not on this shard
+        const uint4* d = reinterpret_cast<const uint4*>(p.docs + lrow * (uint64_t)dims);
+        float facc = 0.f;
+        int iacc = 0;
+        for (int ch = lane; ch < chunks; ch += 32) {
+            const uint4 v = ldg128_stream(d + ch);
+            const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+            if constexpr (QI8) {
+                const uint4 qv = reinterpret_cast<const uint4*>(s_q)[ch];
+                iacc = __dp4a((int)w[0], (int)qv.x, iacc);
+                iacc = __dp4a((int)w[1], (int)qv.y, iacc);
+                iacc = __dp4a((int)w[2], (int)qv.z, iacc);
+                iacc = __dp4a((int)w[3], (int)qv.w, iacc);
+            } else {
+                const float4* qf = reinterpret_cast<const float4*>(s_q) + ch * 4;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float4 qq = qf[j];
+                    const int x = (int)w[j];
+                    facc = fmaf((float)(int8_t)(x & 0xFF), qq.x, facc);
+                    facc = fmaf((float)(int8_t)((x >> 8) & 0xFF), qq.y, facc);
+                    facc = fmaf((float)(int8_t)((x >> 16) & 0xFF), qq.z, facc);
+                    facc = fmaf((float)(int8_t)((x >> 24) & 0xFF), qq.w, facc);
+                }
+            }
+        }
+        if constexpr (QI8) {
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) iacc += __shfl_xor_sync(kFullMask, iacc, off);
+            facc = (float)iacc;
+        } else {
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) facc += __shfl_xor_sync(kFullMask, facc, off);
+        }
+        if (lane == 0) {
+            s_score[c] = facc;
+            s_row[c] = grow;
+        }
+    }
+    __syncthreads();
+
+    // bitonic sort, order: score descending, then row ascending (sentinels sink to the end)
+    auto before = [](float s1, uint64_t r1, float s2, uint64_t r2) {
+        return (s1 > s2) || (s1 == s2 && r1 < r2);
+    };
+    const int n = p.n_sort;
+    for (int size = 2; size <= n; size <<= 1) {
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            for (int i = threadIdx.x; i < n / 2; i += kRescoreThreads) {
+                const int lo = 2 * i - (i & (stride - 1));
+                const int hi = lo + stride;
+                const bool asc = ((lo & size) == 0);
+                const float s1 = s_score[lo], s2 = s_score[hi];
+                const uint64_t r1 = s_row[lo], r2 = s_row[hi];
+                const bool in_order = !before(s2, r2, s1, r1);  // lo already not after hi
+                if (asc != in_order) {
+                    s_score[lo] = s2;
+                    s_score[hi] = s1;
+                    s_row[lo] = r2;
+                    s_row[hi] = r1;
+                }
+            }
+            __syncthreads();
+        }
+    }
+    for (int i = threadIdx.x; i < p.k; i += kRescoreThreads) {
+        const bool ok = i < n && s_row[i] != kSentinelRow;
+        p.out_scores[(size_t)q * p.k + i] = ok ? s_score[i] : -CUDART_INF_F;
+        p.out_rows[(size_t)q * p.k + i] = ok ? s_row[i] : kSentinelRow;
+    }
+}
+
+}  // namespace vl

@@ -1,0 +1,327 @@
+// Kernel 1+2a: fused scan (XOR + POPC / DP4A) + metadata/tombstone mask + per-warp top-k.
+//
+// Replaces EmbeddingModel.search's  sum(q.int() ^ E.int(), dim=1) + topk
+// (reference vlite/model.py:82-85) for a batch of queries over the HBM-resident
+// packed corpus.
+//
+// Shape of the computation (M rows x Q queries x W/4 words, integer pipe, never
+// tensor cores):
+//   grid  = (query tiles, row splits).  A CTA owns QT = C*WQ queries (staged in
+//           shared memory once) and a contiguous range of 256-row corpus tiles.
+//   warps = 8 consumer warps + 1 producer warp.  The producer's elected lane
+//           streams tiles (rows + the tile's 32 B of live mask + 32 B of filter
+//           mask) global -> shared with cp.async.bulk (TMA, SASS UBLKCP) into a
+//           multi-stage mbarrier ring; consumers never touch global memory in
+//           the loop.  Consumer warp (wq, wr): query group wq (C queries in a
+//           register tile), row slice wr of every tile.
+//   lane  = one corpus row per lane (R rows per step), 128-bit LDS.  Lane l
+//           walks its row's 16 B chunks in the rotated order j ^ rot(l), which
+//           makes both the row reads (stride W) and the query reads bank-
+//           conflict free on the linear tile layout TMA 1-D copies produce.
+//   top-k = each (warp, query) keeps a sorted k-list in shared memory and its
+//           k-th best score in a register; rows are visited in ascending
+//           index order, so "score < threshold" + insert-after-equals IS the
+//           (score, row) tie-break.  A step whose 32*R*C scores all fail the
+//           threshold test costs one vote; insertions are warp-cooperative.
+//   out   = every (split, row slice) list goes to a partial buffer that the
+//           merge kernel (merge.cuh) reduces with the same (score, row) order.
+#pragma once
+#include "common.cuh"
+
+namespace vl {
+
+constexpr int kTileRows = 256;
+constexpr int kMaskWordsPerTile = kTileRows / 32;  // 8 words = 32 bytes
+constexpr int kConsumerWarps = 8;
+constexpr int kScanThreads = (kConsumerWarps + 1) * 32;
+constexpr int kWarpListMaxK = 128;
+
+struct ScanParams {
+    const uint8_t* rows;     // corpus, n_rows x W, 256-byte aligned
+    const uint32_t* live;    // live mask, padded to whole tiles, bits >= n_rows are 0
+    const uint32_t* filter;  // optional filter mask, same layout (or nullptr)
+    const uint8_t* queries;  // n_queries x W
+    uint32_t* part_scores;   // [n_lists][n_queries][k]
+    uint64_t* part_rows;
+    uint64_t base_row;  // global index of local row 0
+    uint32_t n_rows;
+    uint32_t n_tiles;
+    int n_queries;
+    int k;
+    int stages;
+    int evict_first;  // 1: corpus is read once -> stream it past L2
+    // optional per-query cursor (multi-pass large k): only rows whose key (score, local row) is
+    // strictly greater than (cur_score[q], cur_row[q]) are eligible
+    const uint32_t* cur_score;
+    const uint32_t* cur_row;
+};
+
+// Insert (s, idx) into the warp's sorted list (ascending score; an equal score goes after the
+// existing equals because rows arrive in ascending index order).  Returns the new threshold.
+__device__ __noinline__ uint32_t warp_list_insert(uint32_t* ls, uint32_t* li, int k, uint32_t s, uint32_t idx,
+                                                  int lane) {
+    int pos = 0;
+    for (int base = 0; base < k; base += 32) {
+        int e = base + lane;
+        bool le = (e < k) && (ls[e] <= s);
+        pos += __popc(__ballot_sync(kFullMask, le));
+    }
+    // entries [pos, k-1) move up one slot, highest chunk first; the last entry drops out
+    for (int top = k - 1; top > pos; top -= 32) {
+        int e = top - lane;
+        bool act = e > pos;
+        uint32_t a = 0, b = 0;
+        if (act) {
+            a = ls[e - 1];
+            b = li[e - 1];
+        }
+        __syncwarp();
+        if (act) {
+            ls[e] = a;
+            li[e] = b;
+        }
+        __syncwarp();
+    }
+    if (lane == 0) {
+        ls[pos] = s;
+        li[pos] = idx;
+    }
+    __syncwarp();
+    return ls[k - 1];
+}
+
+template <int W, int C, int WQ>
+struct ScanCfg {
+    static constexpr int WR = kConsumerWarps / WQ;
+    static constexpr int RPW = kTileRows / WR;            // rows of a tile one warp scores
+    static constexpr int R = RPW >= 128 ? 4 : RPW / 32;   // rows per lane per step
+    static constexpr int STEPS = RPW / (32 * R);
+    static constexpr int QT = C * WQ;                     // queries per CTA
+    static constexpr int CHUNKS = W / 16;
+    static constexpr int TILE_BYTES = kTileRows * W;
+    static constexpr int STAGE_BYTES = TILE_BYTES + 2 * kMaskWordsPerTile * 4;
+    static_assert(W == 32 || W == 64 || W == 128 || W == 256, "row width");
+    static_assert(WQ == 1 || WQ == 2 || WQ == 4 || WQ == 8, "warps along queries");
+    static size_t smem_bytes(int stages, int k) {
+        return (size_t)stages * STAGE_BYTES + (size_t)QT * W + (size_t)kConsumerWarps * C * k * 8 +
+               (size_t)QT * 8 + (size_t)stages * 16;
+    }
+};
+
+template <int W, int METRIC, int C, int WQ>
+__global__ void __launch_bounds__(kScanThreads) scan_topk_kernel(const ScanParams p) {
+    using Cfg = ScanCfg<W, C, WQ>;
+    constexpr int WR = Cfg::WR, RPW = Cfg::RPW, R = Cfg::R, STEPS = Cfg::STEPS, QT = Cfg::QT;
+    constexpr int CHUNKS = Cfg::CHUNKS, TILE_BYTES = Cfg::TILE_BYTES;
+
+    extern __shared__ __align__(128) uint8_t smem[];
+    const int stages = p.stages;
+    const int k = p.k;
+    uint8_t* s_tiles = smem;                                                        // stages x TILE_BYTES
+    uint32_t* s_masks = reinterpret_cast<uint32_t*>(smem + (size_t)stages * TILE_BYTES);  // stages x 16 words
+    uint8_t* s_queries = reinterpret_cast<uint8_t*>(s_masks + stages * 2 * kMaskWordsPerTile);
+    uint32_t* s_lscore = reinterpret_cast<uint32_t*>(s_queries + QT * W);           // [8][C][k]
+    uint32_t* s_lidx = s_lscore + kConsumerWarps * C * k;
+    uint32_t* s_cursor = s_lidx + kConsumerWarps * C * k;                            // [QT][2]
+    uint64_t* s_full = reinterpret_cast<uint64_t*>(s_cursor + QT * 2);
+    uint64_t* s_empty = s_full + stages;
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int qtile = blockIdx.x;
+    const int split = blockIdx.y;
+    const int n_splits = gridDim.y;
+    const uint32_t tile_begin = (uint32_t)(((uint64_t)p.n_tiles * split) / n_splits);
+    const uint32_t tile_end = (uint32_t)(((uint64_t)p.n_tiles * (split + 1)) / n_splits);
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < stages; ++s) {
+            mbar_init(&s_full[s], 1);
+            mbar_init(&s_empty[s], kConsumerWarps);
+        }
+        mbar_fence_init();
+    }
+    // stage this CTA's queries (zero-fill past n_queries)
+    {
+        const int q0 = qtile * QT;
+        const uint4* src = reinterpret_cast<const uint4*>(p.queries);
+        uint4* dst = reinterpret_cast<uint4*>(s_queries);
+        for (int i = threadIdx.x; i < QT * CHUNKS; i += kScanThreads) {
+            int q = q0 + i / CHUNKS;
+            uint4 v = make_uint4(0, 0, 0, 0);
+            if (q < p.n_queries) v = src[(size_t)q * CHUNKS + (i % CHUNKS)];
+            dst[i] = v;
+        }
+        if (p.cur_score != nullptr) {
+            for (int i = threadIdx.x; i < QT; i += kScanThreads) {
+                const bool in = q0 + i < p.n_queries;
+                s_cursor[2 * i] = in ? p.cur_score[q0 + i] : kSentinelScore;
+                s_cursor[2 * i + 1] = in ? p.cur_row[q0 + i] : 0xFFFFFFFFu;
+            }
+        }
+    }
+    __syncthreads();
+
+    if (warp == kConsumerWarps) {
+        // ---------------- producer: one elected lane drives the TMA ring ----------------
+        if (lane == 0) {
+            const uint64_t policy = p.evict_first ? l2_policy_evict_first() : l2_policy_evict_last();
+            uint32_t i = 0;
+            for (uint32_t t = tile_begin; t < tile_end; ++t, ++i) {
+                const int s = i % stages;
+                const uint32_t ph = (i / stages) & 1;
+                mbar_wait(&s_empty[s], ph ^ 1);
+                const uint32_t row0 = t * kTileRows;
+                const uint32_t rows_here = min((uint32_t)kTileRows, p.n_rows - row0);
+                const uint32_t mask_bytes = kMaskWordsPerTile * 4;
+                const uint32_t bytes = rows_here * W + mask_bytes + (p.filter ? mask_bytes : 0);
+                mbar_arrive_expect_tx(&s_full[s], bytes);
+                bulk_g2s_hint(s_tiles + (size_t)s * TILE_BYTES, p.rows + (uint64_t)row0 * W, rows_here * W,
+                              &s_full[s], policy);
+                uint32_t* m = s_masks + s * 2 * kMaskWordsPerTile;
+                bulk_g2s(m, p.live + (size_t)t * kMaskWordsPerTile, mask_bytes, &s_full[s]);
+                if (p.filter)
+                    bulk_g2s(m + kMaskWordsPerTile, p.filter + (size_t)t * kMaskWordsPerTile, mask_bytes,
+                             &s_full[s]);
+            }
+        }
+        return;
+    }
+
+    // -------------------------- consumers --------------------------
+    const int wq = warp % WQ;
+    const int wr = warp / WQ;
+    uint32_t* ls = s_lscore + (size_t)warp * C * k;
+    uint32_t* li = s_lidx + (size_t)warp * C * k;
+    for (int e = lane; e < C * k; e += 32) {
+        ls[e] = kSentinelScore;
+        li[e] = 0xFFFFFFFFu;
+    }
+    __syncwarp();
+
+    uint32_t thr[C];
+#pragma unroll
+    for (int c = 0; c < C; ++c) thr[c] = (qtile * QT + wq * C + c < p.n_queries) ? kSentinelScore : 0u;
+
+    // rotated chunk order: conflict-free 128-bit LDS on a linear (unswizzled) tile
+    constexpr int LANES_PER_128B = (W >= 128) ? 1 : 128 / W;
+    constexpr int ROT_MASK = (CHUNKS < 8 ? CHUNKS : 8) - 1;
+    const uint32_t rot16 = (uint32_t)(((lane / LANES_PER_128B) & ROT_MASK) * 16);
+    const uint32_t q_saddr = smem_u32(s_queries) + (uint32_t)(wq * C * W);
+    const uint32_t tiles_saddr = smem_u32(s_tiles);
+    const bool has_filter = p.filter != nullptr;
+    const bool has_cursor = p.cur_score != nullptr;
+
+    uint32_t i = 0;
+    for (uint32_t t = tile_begin; t < tile_end; ++t, ++i) {
+        const int s = i % stages;
+        const uint32_t ph = (i / stages) & 1;
+        mbar_wait(&s_full[s], ph);
+        const uint32_t* m = s_masks + s * 2 * kMaskWordsPerTile;
+
+#pragma unroll 1
+        for (int st = 0; st < STEPS; ++st) {
+            const int row_in_tile0 = wr * RPW + st * 32 * R;  // multiple of 32
+            bool valid[R];
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                uint32_t w = m[row_in_tile0 / 32 + r];
+                if (has_filter) w &= m[kMaskWordsPerTile + row_in_tile0 / 32 + r];
+                valid[r] = (w >> lane) & 1u;
+            }
+            uint32_t acc[R][C];
+#pragma unroll
+            for (int r = 0; r < R; ++r)
+#pragma unroll
+                for (int c = 0; c < C; ++c) acc[r][c] = 0;
+
+            const uint32_t row_saddr =
+                tiles_saddr + (uint32_t)s * TILE_BYTES + (uint32_t)(row_in_tile0 + lane) * W;
+            // bound the unrolled body to ~256 POPCs so the hot loop stays inside the 32 KB L1.5 I-cache
+            constexpr int UNROLL = (R * C >= 32) ? 2 : (R * C >= 16 ? 4 : CHUNKS);
+#pragma unroll UNROLL
+            for (int j = 0; j < CHUNKS; ++j) {
+                const uint32_t coff = ((uint32_t)(j * 16)) ^ rot16;
+                uint4 rv[R];
+#pragma unroll
+                for (int r = 0; r < R; ++r) rv[r] = lds128(row_saddr + (uint32_t)(r * 32 * W) + coff);
+#pragma unroll
+                for (int c = 0; c < C; ++c) {
+                    const uint4 qv = lds128(q_saddr + (uint32_t)(c * W) + coff);
+#pragma unroll
+                    for (int r = 0; r < R; ++r) acc[r][c] = score_chunk<METRIC>(rv[r], qv, acc[r][c]);
+                }
+            }
+
+            bool hit = false;
+#pragma unroll
+            for (int r = 0; r < R; ++r)
+#pragma unroll
+                for (int c = 0; c < C; ++c) hit |= valid[r] && (acc[r][c] < thr[c]);
+
+            if (__any_sync(kFullMask, hit)) {
+                const uint32_t row_base = t * kTileRows + (uint32_t)row_in_tile0;
+#pragma unroll
+                for (int c = 0; c < C; ++c) {
+#pragma unroll
+                    for (int r = 0; r < R; ++r) {
+                        unsigned mm = __ballot_sync(kFullMask, valid[r] && (acc[r][c] < thr[c]));
+                        while (mm) {
+                            const int src = __ffs(mm) - 1;
+                            mm &= mm - 1;
+                            const uint32_t sc = __shfl_sync(kFullMask, acc[r][c], src);
+                            if (sc < thr[c]) {
+                                const uint32_t idx = row_base + (uint32_t)(r * 32 + src);
+                                bool eligible = true;
+                                if (has_cursor) {
+                                    const uint32_t cs = s_cursor[2 * (wq * C + c)];
+                                    const uint32_t cr = s_cursor[2 * (wq * C + c) + 1];
+                                    eligible = (sc > cs) || (sc == cs && idx > cr);
+                                }
+                                if (eligible) thr[c] = warp_list_insert(ls + c * k, li + c * k, k, sc, idx, lane);
+                            }
+                        }
+                    }
+                }
+            }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&s_empty[s]);
+    }
+
+    // -------- write this warp's lists to the partial buffer --------
+    const int list_id = split * WR + wr;
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+        const int q = qtile * QT + wq * C + c;
+        if (q >= p.n_queries) continue;
+        const size_t o = ((size_t)list_id * p.n_queries + q) * k;
+        for (int e = lane; e < k; e += 32) {
+            const uint32_t idx = li[c * k + e];
+            p.part_scores[o + e] = ls[c * k + e];
+            p.part_rows[o + e] = (idx == 0xFFFFFFFFu) ? kSentinelRow : p.base_row + idx;
+        }
+    }
+}
+
+// ---- full score vector of one query (parity tests; not the search path) --------
+template <int METRIC>
+__global__ void scores_kernel(const uint8_t* __restrict__ rows, int w, const uint8_t* __restrict__ query,
+                              uint64_t first, uint64_t n, uint32_t* __restrict__ out) {
+    extern __shared__ uint32_t s_q[];
+    const int words = w / 4;
+    for (int i = threadIdx.x; i < words; i += blockDim.x) s_q[i] = reinterpret_cast<const uint32_t*>(query)[i];
+    __syncthreads();
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint4* r = reinterpret_cast<const uint4*>(rows + (first + i) * (uint64_t)w);
+        uint32_t acc = 0;
+        for (int j = 0; j < words / 4; ++j) {
+            uint4 v = ldg128_stream(r + j);
+            uint4 q = make_uint4(s_q[4 * j], s_q[4 * j + 1], s_q[4 * j + 2], s_q[4 * j + 3]);
+            acc = score_chunk<METRIC>(v, q, acc);
+        }
+        out[i] = acc;
+    }
+}
+
+}  // namespace vl
