@@ -14,7 +14,8 @@ import re
 import numpy as np
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG, "lib", "libvlite_b200.so")
+# VLITE_B200_LIB: load an experiment build instead of the shipped library (tuning only)
+LIB_PATH = os.environ.get("VLITE_B200_LIB") or os.path.join(_PKG, "lib", "libvlite_b200.so")
 HEADER_PATH = os.path.join(os.path.dirname(_PKG), "include", "vlite_b200.h")
 
 HAMMING, XORSUM = 0, 1

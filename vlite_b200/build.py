@@ -35,15 +35,17 @@ def is_stale() -> bool:
     return any(os.path.getmtime(f) > t for f in SOURCES + HEADERS if os.path.exists(f))
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    if not force and not is_stale():
+def build(force: bool = False, verbose: bool = False, out: str | None = None, extra_flags=()) -> str:
+    """out / extra_flags: experiment builds (e.g. -DVL_RMAX=2) next to the shipped library."""
+    if out is None and not force and not is_stale():
         return LIB_PATH
+    out = out or LIB_PATH
     os.makedirs(LIB_DIR, exist_ok=True)
     cmd = [
         _nvcc(), "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
         "--shared", "-Xcompiler", "-fPIC,-O3,-Wall",
-        "-o", LIB_PATH,
-    ] + SOURCES
+        "-o", out,
+    ] + list(extra_flags) + SOURCES
     if verbose:
         cmd.insert(1, "-Xptxas")
         cmd.insert(2, "-v")
@@ -52,7 +54,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         sys.stderr.write(res.stdout + res.stderr)
     if res.returncode != 0:
         raise RuntimeError("nvcc failed building libvlite_b200.so")
-    return LIB_PATH
+    return out
 
 
 if __name__ == "__main__":

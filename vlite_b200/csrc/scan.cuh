@@ -8,12 +8,12 @@
 // tensor cores):
 //   grid  = (query tiles, row splits).  A CTA owns QT = C*WQ queries (staged in
 //           shared memory once) and a contiguous range of 256-row corpus tiles.
-//   warps = 8 consumer warps + 1 producer warp.  The producer's elected lane
-//           streams tiles (rows + the tile's 32 B of live mask + 32 B of filter
-//           mask) global -> shared with cp.async.bulk (TMA, SASS UBLKCP) into a
-//           multi-stage mbarrier ring; consumers never touch global memory in
-//           the loop.  Consumer warp (wq, wr): query group wq (C queries in a
-//           register tile), row slice wr of every tile.
+//   warps = 8 per CTA, two CTAs per SM.  One elected thread streams tiles (rows +
+//           the tile's 32 B of live mask + 32 B of filter mask) global -> shared
+//           with cp.async.bulk (TMA, SASS UBLKCP) into a multi-stage mbarrier
+//           ring (full/empty barriers); no warp touches global memory in the
+//           loop.  Warp (wq, wr): query group wq (C queries in a register
+//           tile), row slice wr of every tile.
 //   lane  = one corpus row per lane (R rows per step), 128-bit LDS.  Lane l
 //           walks its row's 16 B chunks in the rotated order j ^ rot(l), which
 //           makes both the row reads (stride W) and the query reads bank-
@@ -32,8 +32,8 @@ namespace vl {
 
 constexpr int kTileRows = 256;
 constexpr int kMaskWordsPerTile = kTileRows / 32;  // 8 words = 32 bytes
-constexpr int kConsumerWarps = 8;
-constexpr int kScanThreads = (kConsumerWarps + 1) * 32;
+constexpr int kScanWarps = 8;
+constexpr int kScanThreads = kScanWarps * 32;
 constexpr int kWarpListMaxK = 128;
 
 struct ScanParams {
@@ -92,9 +92,12 @@ __device__ __noinline__ uint32_t warp_list_insert(uint32_t* ls, uint32_t* li, in
 
 template <int W, int C, int WQ>
 struct ScanCfg {
-    static constexpr int WR = kConsumerWarps / WQ;
+    static constexpr int WR = kScanWarps / WQ;
     static constexpr int RPW = kTileRows / WR;            // rows of a tile one warp scores
-    static constexpr int R = RPW >= 128 ? 4 : RPW / 32;   // rows per lane per step
+#ifndef VL_RMAX
+#define VL_RMAX 4
+#endif
+    static constexpr int R = RPW >= 32 * VL_RMAX ? VL_RMAX : RPW / 32;  // rows per lane per step
     static constexpr int STEPS = RPW / (32 * R);
     static constexpr int QT = C * WQ;                     // queries per CTA
     static constexpr int CHUNKS = W / 16;
@@ -103,16 +106,58 @@ struct ScanCfg {
     static_assert(W == 32 || W == 64 || W == 128 || W == 256, "row width");
     static_assert(WQ == 1 || WQ == 2 || WQ == 4 || WQ == 8, "warps along queries");
     static size_t smem_bytes(int stages, int k) {
-        return (size_t)stages * STAGE_BYTES + (size_t)QT * W + (size_t)kConsumerWarps * C * k * 8 +
-               (size_t)QT * 8 + (size_t)stages * 16;
+        return (size_t)stages * STAGE_BYTES + (size_t)QT * W + (size_t)kScanWarps * C * k * 8 +
+               (size_t)QT * 8 + (size_t)kScanWarps * C * 4 + (size_t)stages * 16;
     }
 };
 
+// 8 words (two 16 B chunks) of one (row, query) pair.
+//  HAMMING: carry-save adders (LOP3 0x96 = xor3, 0xE8 = majority) compress 7 of the 8 XOR words
+//  into ones/twos/fours words, so the pair costs 4 POPC (XU pipe, 16 lanes/clk/SM) + 16 LOP3
+//  (ALU pipe, 64 lanes/clk/SM) instead of 8 POPC + 8 LOP3: both integer pipes end up evenly
+//  loaded, twice the pair rate of the plain XOR+POPC loop.  The weighted adds go to IMAD (FMA pipe).
+//  XORSUM: one IDP4A per word (byte-value sum), no compression needed.
+__device__ __forceinline__ uint32_t xor3(uint32_t a, uint32_t b, uint32_t c) {
+    uint32_t d;
+    asm("lop3.b32 %0, %1, %2, %3, 0x96;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+__device__ __forceinline__ uint32_t maj3(uint32_t a, uint32_t b, uint32_t c) {
+    uint32_t d;
+    asm("lop3.b32 %0, %1, %2, %3, 0xE8;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+__device__ __forceinline__ uint32_t mad_u32(uint32_t a, uint32_t b, uint32_t c) {
+    uint32_t d;
+    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+template <int METRIC>
+__device__ __forceinline__ uint32_t score_chunk_pair(const uint4& ra, const uint4& rb, const uint4& qa,
+                                                     const uint4& qb, uint32_t acc) {
+    if constexpr (METRIC == kHamming) {
+        const uint32_t x0 = ra.x ^ qa.x, x1 = ra.y ^ qa.y, x2 = ra.z ^ qa.z, x3 = ra.w ^ qa.w;
+        const uint32_t x4 = rb.x ^ qb.x, x5 = rb.y ^ qb.y, x6 = rb.z ^ qb.z, x7 = rb.w ^ qb.w;
+        const uint32_t s1 = xor3(x0, x1, x2), c1 = maj3(x0, x1, x2);
+        const uint32_t s2 = xor3(x3, x4, x5), c2 = maj3(x3, x4, x5);
+        const uint32_t s3 = xor3(s1, s2, x6), c3 = maj3(s1, s2, x6);
+        const uint32_t tw = xor3(c1, c2, c3), fo = maj3(c1, c2, c3);
+        acc += __popc(s3) + __popc(x7);
+        acc = mad_u32(__popc(tw), 2u, acc);
+        acc = mad_u32(__popc(fo), 4u, acc);
+        return acc;
+    } else {
+        acc = score_chunk<METRIC>(ra, qa, acc);
+        return score_chunk<METRIC>(rb, qb, acc);
+    }
+}
+
 template <int W, int METRIC, int C, int WQ>
-__global__ void __launch_bounds__(kScanThreads) scan_topk_kernel(const ScanParams p) {
+__global__ void __launch_bounds__(kScanThreads, 2) scan_topk_kernel(const ScanParams p) {
     using Cfg = ScanCfg<W, C, WQ>;
     constexpr int WR = Cfg::WR, RPW = Cfg::RPW, R = Cfg::R, STEPS = Cfg::STEPS, QT = Cfg::QT;
     constexpr int CHUNKS = Cfg::CHUNKS, TILE_BYTES = Cfg::TILE_BYTES;
+    static_assert(CHUNKS % 2 == 0, "rows are scored two 16 B chunks at a time");
 
     extern __shared__ __align__(128) uint8_t smem[];
     const int stages = p.stages;
@@ -121,9 +166,10 @@ __global__ void __launch_bounds__(kScanThreads) scan_topk_kernel(const ScanParam
     uint32_t* s_masks = reinterpret_cast<uint32_t*>(smem + (size_t)stages * TILE_BYTES);  // stages x 16 words
     uint8_t* s_queries = reinterpret_cast<uint8_t*>(s_masks + stages * 2 * kMaskWordsPerTile);
     uint32_t* s_lscore = reinterpret_cast<uint32_t*>(s_queries + QT * W);           // [8][C][k]
-    uint32_t* s_lidx = s_lscore + kConsumerWarps * C * k;
-    uint32_t* s_cursor = s_lidx + kConsumerWarps * C * k;                            // [QT][2]
-    uint64_t* s_full = reinterpret_cast<uint64_t*>(s_cursor + QT * 2);
+    uint32_t* s_lidx = s_lscore + kScanWarps * C * k;
+    uint32_t* s_cursor = s_lidx + kScanWarps * C * k;                                // [QT][2]
+    uint32_t* s_thr = s_cursor + QT * 2;                                             // [8][C]
+    uint64_t* s_full = reinterpret_cast<uint64_t*>(s_thr + kScanWarps * C);
     uint64_t* s_empty = s_full + stages;
 
     const int warp = threadIdx.x >> 5;
@@ -133,11 +179,12 @@ __global__ void __launch_bounds__(kScanThreads) scan_topk_kernel(const ScanParam
     const int n_splits = gridDim.y;
     const uint32_t tile_begin = (uint32_t)(((uint64_t)p.n_tiles * split) / n_splits);
     const uint32_t tile_end = (uint32_t)(((uint64_t)p.n_tiles * (split + 1)) / n_splits);
+    const uint32_t my_tiles = tile_end - tile_begin;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < stages; ++s) {
             mbar_init(&s_full[s], 1);
-            mbar_init(&s_empty[s], kConsumerWarps);
+            mbar_init(&s_empty[s], kScanWarps);
         }
         mbar_fence_init();
     }
@@ -162,33 +209,28 @@ __global__ void __launch_bounds__(kScanThreads) scan_topk_kernel(const ScanParam
     }
     __syncthreads();
 
-    if (warp == kConsumerWarps) {
-        // ---------------- producer: one elected lane drives the TMA ring ----------------
-        if (lane == 0) {
-            const uint64_t policy = p.evict_first ? l2_policy_evict_first() : l2_policy_evict_last();
-            uint32_t i = 0;
-            for (uint32_t t = tile_begin; t < tile_end; ++t, ++i) {
-                const int s = i % stages;
-                const uint32_t ph = (i / stages) & 1;
-                mbar_wait(&s_empty[s], ph ^ 1);
-                const uint32_t row0 = t * kTileRows;
-                const uint32_t rows_here = min((uint32_t)kTileRows, p.n_rows - row0);
-                const uint32_t mask_bytes = kMaskWordsPerTile * 4;
-                const uint32_t bytes = rows_here * W + mask_bytes + (p.filter ? mask_bytes : 0);
-                mbar_arrive_expect_tx(&s_full[s], bytes);
-                bulk_g2s_hint(s_tiles + (size_t)s * TILE_BYTES, p.rows + (uint64_t)row0 * W, rows_here * W,
-                              &s_full[s], policy);
-                uint32_t* m = s_masks + s * 2 * kMaskWordsPerTile;
-                bulk_g2s(m, p.live + (size_t)t * kMaskWordsPerTile, mask_bytes, &s_full[s]);
-                if (p.filter)
-                    bulk_g2s(m + kMaskWordsPerTile, p.filter + (size_t)t * kMaskWordsPerTile, mask_bytes,
-                             &s_full[s]);
-            }
-        }
-        return;
+    // ---- TMA ring: one elected thread issues the bulk copies of tile `i` into stage i % stages ----
+    const uint64_t policy = p.evict_first ? l2_policy_evict_first() : l2_policy_evict_last();
+    auto issue_tile = [&](uint32_t i) {
+        const int s = i % stages;
+        const uint32_t t = tile_begin + i;
+        const uint32_t row0 = t * kTileRows;
+        const uint32_t rows_here = min((uint32_t)kTileRows, p.n_rows - row0);
+        const uint32_t mask_bytes = kMaskWordsPerTile * 4;
+        const uint32_t bytes = rows_here * W + mask_bytes + (p.filter ? mask_bytes : 0);
+        mbar_arrive_expect_tx(&s_full[s], bytes);
+        bulk_g2s_hint(s_tiles + (size_t)s * TILE_BYTES, p.rows + (uint64_t)row0 * W, rows_here * W, &s_full[s],
+                      policy);
+        uint32_t* m = s_masks + s * 2 * kMaskWordsPerTile;
+        bulk_g2s(m, p.live + (size_t)t * kMaskWordsPerTile, mask_bytes, &s_full[s]);
+        if (p.filter)
+            bulk_g2s(m + kMaskWordsPerTile, p.filter + (size_t)t * kMaskWordsPerTile, mask_bytes, &s_full[s]);
+    };
+    if (threadIdx.x == 0) {
+        const uint32_t pre = min((uint32_t)stages, my_tiles);
+        for (uint32_t i = 0; i < pre; ++i) issue_tile(i);
     }
 
-    // -------------------------- consumers --------------------------
     const int wq = warp % WQ;
     const int wr = warp / WQ;
     uint32_t* ls = s_lscore + (size_t)warp * C * k;
@@ -202,6 +244,8 @@ __global__ void __launch_bounds__(kScanThreads) scan_topk_kernel(const ScanParam
     uint32_t thr[C];
 #pragma unroll
     for (int c = 0; c < C; ++c) thr[c] = (qtile * QT + wq * C + c < p.n_queries) ? kSentinelScore : 0u;
+    if (lane < C) s_thr[warp * C + lane] = (qtile * QT + wq * C + lane < p.n_queries) ? kSentinelScore : 0u;
+    __syncwarp();
 
     // rotated chunk order: conflict-free 128-bit LDS on a linear (unswizzled) tile
     constexpr int LANES_PER_128B = (W >= 128) ? 1 : 128 / W;
@@ -212,11 +256,20 @@ __global__ void __launch_bounds__(kScanThreads) scan_topk_kernel(const ScanParam
     const bool has_filter = p.filter != nullptr;
     const bool has_cursor = p.cur_score != nullptr;
 
-    uint32_t i = 0;
-    for (uint32_t t = tile_begin; t < tile_end; ++t, ++i) {
+    for (uint32_t i = 0; i < my_tiles; ++i) {
+        const uint32_t t = tile_begin + i;
         const int s = i % stages;
-        const uint32_t ph = (i / stages) & 1;
-        mbar_wait(&s_full[s], ph);
+        // warp 0 refills the stage every warp released one tile ago (one tile of slack keeps it
+        // from waiting on the slowest warp)
+        if (warp == 0 && i >= 1) {
+            const uint32_t nxt = i - 1 + stages;
+            if (nxt < my_tiles) {
+                mbar_wait(&s_empty[(i - 1) % stages], ((i - 1) / stages) & 1);
+                if (lane == 0) issue_tile(nxt);
+                __syncwarp();
+            }
+        }
+        mbar_wait(&s_full[s], (i / stages) & 1);
         const uint32_t* m = s_masks + s * 2 * kMaskWordsPerTile;
 
 #pragma unroll 1
@@ -237,19 +290,25 @@ __global__ void __launch_bounds__(kScanThreads) scan_topk_kernel(const ScanParam
 
             const uint32_t row_saddr =
                 tiles_saddr + (uint32_t)s * TILE_BYTES + (uint32_t)(row_in_tile0 + lane) * W;
-            // bound the unrolled body to ~256 POPCs so the hot loop stays inside the 32 KB L1.5 I-cache
-            constexpr int UNROLL = (R * C >= 32) ? 2 : (R * C >= 16 ? 4 : CHUNKS);
+            // keep the unrolled body near 12 KB of SASS so the hot loop stays inside the I-cache
+            constexpr int UNROLL = (R * C >= 32) ? 1 : (R * C >= 16 ? 2 : CHUNKS / 2);
 #pragma unroll UNROLL
-            for (int j = 0; j < CHUNKS; ++j) {
-                const uint32_t coff = ((uint32_t)(j * 16)) ^ rot16;
-                uint4 rv[R];
+            for (int j = 0; j < CHUNKS; j += 2) {
+                const uint32_t coff_a = ((uint32_t)(j * 16)) ^ rot16;
+                const uint32_t coff_b = ((uint32_t)((j + 1) * 16)) ^ rot16;
+                uint4 ra[R], rb[R];
 #pragma unroll
-                for (int r = 0; r < R; ++r) rv[r] = lds128(row_saddr + (uint32_t)(r * 32 * W) + coff);
+                for (int r = 0; r < R; ++r) {
+                    ra[r] = lds128(row_saddr + (uint32_t)(r * 32 * W) + coff_a);
+                    rb[r] = lds128(row_saddr + (uint32_t)(r * 32 * W) + coff_b);
+                }
 #pragma unroll
                 for (int c = 0; c < C; ++c) {
-                    const uint4 qv = lds128(q_saddr + (uint32_t)(c * W) + coff);
+                    const uint4 qa = lds128(q_saddr + (uint32_t)(c * W) + coff_a);
+                    const uint4 qb = lds128(q_saddr + (uint32_t)(c * W) + coff_b);
 #pragma unroll
-                    for (int r = 0; r < R; ++r) acc[r][c] = score_chunk<METRIC>(rv[r], qv, acc[r][c]);
+                    for (int r = 0; r < R; ++r)
+                        acc[r][c] = score_chunk_pair<METRIC>(ra[r], rb[r], qa, qb, acc[r][c]);
                 }
             }
 
@@ -260,29 +319,48 @@ __global__ void __launch_bounds__(kScanThreads) scan_topk_kernel(const ScanParam
                 for (int c = 0; c < C; ++c) hit |= valid[r] && (acc[r][c] < thr[c]);
 
             if (__any_sync(kFullMask, hit)) {
+                // Rare path, kept small on purpose (a compact loop, not R*C unrolled copies) so it
+                // does not evict the hot loop from the instruction cache.  Bit b = c*R + r of `hm`
+                // marks a candidate; queries (c) are independent, rows ascend with (r, lane).
+                uint32_t hm = 0;
+#pragma unroll
+                for (int c = 0; c < C; ++c)
+#pragma unroll
+                    for (int r = 0; r < R; ++r)
+                        if (valid[r] && (acc[r][c] < thr[c])) hm |= 1u << (c * R + r);
+                uint32_t any = __reduce_or_sync(kFullMask, hm);
                 const uint32_t row_base = t * kTileRows + (uint32_t)row_in_tile0;
+                while (any) {
+                    const int b = __ffs(any) - 1;
+                    any &= any - 1;
+                    const int c = b / R, r = b % R;
+                    uint32_t v = 0;
 #pragma unroll
-                for (int c = 0; c < C; ++c) {
+                    for (int cc = 0; cc < C; ++cc)
 #pragma unroll
-                    for (int r = 0; r < R; ++r) {
-                        unsigned mm = __ballot_sync(kFullMask, valid[r] && (acc[r][c] < thr[c]));
-                        while (mm) {
-                            const int src = __ffs(mm) - 1;
-                            mm &= mm - 1;
-                            const uint32_t sc = __shfl_sync(kFullMask, acc[r][c], src);
-                            if (sc < thr[c]) {
-                                const uint32_t idx = row_base + (uint32_t)(r * 32 + src);
-                                bool eligible = true;
-                                if (has_cursor) {
-                                    const uint32_t cs = s_cursor[2 * (wq * C + c)];
-                                    const uint32_t cr = s_cursor[2 * (wq * C + c) + 1];
-                                    eligible = (sc > cs) || (sc == cs && idx > cr);
-                                }
-                                if (eligible) thr[c] = warp_list_insert(ls + c * k, li + c * k, k, sc, idx, lane);
+                        for (int rr = 0; rr < R; ++rr) v = (b == cc * R + rr) ? acc[rr][cc] : v;
+                    uint32_t tc = s_thr[warp * C + c];
+                    unsigned mm = __ballot_sync(kFullMask, (hm >> b) & 1u);
+                    while (mm) {
+                        const int src = __ffs(mm) - 1;
+                        mm &= mm - 1;
+                        const uint32_t sc = __shfl_sync(kFullMask, v, src);
+                        if (sc < tc) {
+                            const uint32_t idx = row_base + (uint32_t)(r * 32 + src);
+                            bool eligible = true;
+                            if (has_cursor) {
+                                const uint32_t cs = s_cursor[2 * (wq * C + c)];
+                                const uint32_t cr = s_cursor[2 * (wq * C + c) + 1];
+                                eligible = (sc > cs) || (sc == cs && idx > cr);
                             }
+                            if (eligible) tc = warp_list_insert(ls + c * k, li + c * k, k, sc, idx, lane);
                         }
                     }
+                    if (lane == 0) s_thr[warp * C + c] = tc;
+                    __syncwarp();
                 }
+#pragma unroll
+                for (int c = 0; c < C; ++c) thr[c] = s_thr[warp * C + c];
             }
         }
         __syncwarp();
