@@ -1,0 +1,384 @@
+#!/usr/bin/env python
+"""bench.py -- the retrieval hot path on N B200s of one node (contract in the task prompt).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+Workload (BASELINE.json configs[1]): a 500k x 128 B synthetic ubinary corpus per GPU shard,
+a batch of 1024 queries, top_k = 10, HAMMING.  A "step" = one vl_search over the shard (N > 1:
++ the all-gather of the per-shard top-k and the merge).  Row-sharded WEAK scaling: every rank
+holds its own 500k-row shard of an N x 500k corpus, all ranks scan all queries.
+
+``value``  queries/s in 500k-row-corpus equivalents (Q x total_rows / 500k per step), inputs
+           resident in HBM, CUDA events, max over ranks.  At N = 1 this is plain queries/s.
+``e2e``    same metric through the C ABI with HOST buffers (pinned queries in, results out).
+``roofline`` of the scan kernel as north_star defines it: the slower of corpus bytes at HBM
+           bandwidth and popcount work at the INT-pipe (POPC) peak; POPC peak measured live by
+           the library's micro-benchmark, HBM peak from MEASURED_PEAKS.json.
+``cpu_baseline`` the oracle's torch-op port of the reference's EmbeddingModel.search
+           (vlite/model.py:76-90) timed on this box's host cores on a bounded sample.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+ROWS_PER_GPU = 500_000
+WIDTH = 128
+N_QUERIES = 1024
+TOP_K = 10
+HBM_FALLBACK_GBS = 6650.0
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        d = json.load(open(path))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return HBM_FALLBACK_GBS, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                 "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except (ValueError, IndexError):
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def make_queries(n_rows_total: int, nq: int, width: int):
+    """Half clustered (true neighbours exist), half uniform (tie-heavy).  Same on every rank."""
+    from oracle import synth
+    qc, _ = synth.clustered_queries(1, 0, n_rows_total, nq // 2, width)
+    qu = synth.uniform_queries(1, nq - nq // 2, width)
+    return np.ascontiguousarray(np.concatenate([qc, qu]))
+
+
+# ------------------------------------------------------------------------------------------
+# reference arm / cpu_baseline: the oracle's torch-op port of EmbeddingModel.search on host cores
+# ------------------------------------------------------------------------------------------
+def time_reference(steps: int, warmup: int, budget_s: float = 150.0):
+    import torch
+    from oracle import ref_port, synth
+    rows = ROWS_PER_GPU
+    queries = make_queries(rows, 8, WIDTH)
+    # probe on 50k rows to size the per-step sample so that steps+warmup fit the budget
+    probe_n = 50_000
+    e = ref_port.corpus_as_reference_f32(synth.corpus_rows(0, 0, probe_n, WIDTH))
+    from oracle.search import to_ref_encoding
+    q_ref = to_ref_encoding(queries)
+    ref_port.search_port(q_ref[0], e, TOP_K)
+    t0 = time.perf_counter()
+    ref_port.search_port(q_ref[0], e, TOP_K)
+    per_row = (time.perf_counter() - t0) / probe_n
+    n_sample = rows
+    est = per_row * rows * (steps + warmup)
+    if est > budget_s:
+        n_sample = max(probe_n, int(rows * budget_s / est) // 1000 * 1000)
+    e = ref_port.corpus_as_reference_f32(synth.corpus_rows(0, 0, n_sample, WIDTH))
+    for i in range(warmup):
+        ref_port.search_port(q_ref[i % 8], e, TOP_K)
+    t0 = time.perf_counter()
+    for i in range(steps):
+        ref_port.search_port(q_ref[i % 8], e, TOP_K)     # one query per call, like main.py:116-117
+    dt = (time.perf_counter() - t0) / steps
+    qps = (1.0 / dt) * (n_sample / rows)                  # search cost is linear in N
+    sample = (f"{steps} sequential EmbeddingModel.search calls (1 query, k={TOP_K}) over "
+              f"{n_sample} of the {rows} x {WIDTH} B rows held as float32"
+              + ("" if n_sample == rows else "; q/s scaled linearly to the full corpus"))
+    return qps, dt * 1e3, torch.get_num_threads(), sample
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    qps, ms, cores, sample = time_reference(args.steps, args.warmup)
+    line = {
+        "impl": "reference", "metric": "queries_per_sec", "value": qps, "unit": "queries/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32 (via float32 storage)",
+        "data": "synthetic",
+        "config": workload_config(args.gpus),
+        "cpu_baseline": {"value": qps, "unit": "queries/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": qps, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(n_gpus: int):
+    return {
+        "workload": (f"BASELINE configs[1]: {ROWS_PER_GPU} x {WIDTH} B ubinary rows per GPU shard "
+                     f"({n_gpus} shard(s), row-sharded), batch of {N_QUERIES} queries, top_k={TOP_K}, HAMMING"),
+        "rows_per_gpu": ROWS_PER_GPU, "width_bytes": WIDTH, "queries": N_QUERIES, "top_k": TOP_K,
+        "metric_fn": "hamming", "parallelism": f"row-shard x{n_gpus}",
+        "l2": "corpus (64 MB) fits L2: a 256 MB buffer is overwritten between timed iterations (L2 flush)",
+    }
+
+
+# ------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from oracle import cscan, synth
+    from vlite_b200 import _capi
+    from vlite_b200.sharded import ShardedSearcher
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    _capi.load()
+    if _capi.device_count() < 1:
+        raise SystemExit("no sm_100 device: vlite_b200 has no CPU fallback")
+    hbm_peak, hbm_src = load_peaks()
+
+    rows, w, nq, k = ROWS_PER_GPU, WIDTH, N_QUERIES, TOP_K
+    total_rows = rows * world
+    corpus = _capi.Corpus(w, device=local_rank, capacity_rows=rows, base_row=rank * rows)
+    corpus.set_stream(torch.cuda.current_stream().cuda_stream)
+    corpus.fill_synthetic(0, 0, rows)
+    queries = make_queries(total_rows, nq, w)
+    dq = torch.from_numpy(queries).to(dev)
+    searcher = ShardedSearcher(corpus)
+
+    # ---- parity gate before any timing: device result vs the CPU oracle ----
+    out_s, out_r = searcher.search(dq, k, _capi.HAMMING)
+    torch.cuda.synchronize()
+    got_s = out_s.cpu().numpy().view(np.uint32)
+    got_r = out_r.cpu().numpy().view(np.uint64)
+    if rank == 0:
+        sub = np.r_[0:8, nq - 8:nq]
+        host_rows = np.concatenate([synth.corpus_rows(0, g * rows, rows, w) for g in range(world)])
+        es, er = cscan.search(queries[sub], host_rows, k, _capi.HAMMING)
+        if not (np.array_equal(got_s[sub], es) and np.array_equal(got_r[sub], er)):
+            print(json.dumps({"error": "parity gate failed: device top-k differs from the oracle"}), flush=True)
+            raise SystemExit(1)
+        del host_rows
+
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    ev0 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    ev1 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    corpus.set_timing(True)
+    for _ in range(args.warmup):
+        flush.zero_()
+        searcher.search(dq, k, _capi.HAMMING)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = _capi.launch_count()
+    scan_ms = []
+    barrier()
+    for i in range(args.steps):
+        flush.zero_()                              # L2 flush, outside the timed events
+        ev0[i].record()
+        searcher.search(dq, k, _capi.HAMMING)
+        ev1[i].record()
+        ev1[i].synchronize()
+        scan_ms.append(corpus.last_timing()[1])    # the scan kernel alone (library's own events)
+    barrier()
+    launches = _capi.launch_count() - launches0
+    step_ms = [a.elapsed_time(b) for a, b in zip(ev0, ev1)]
+    t_total = torch.tensor([sum(step_ms)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t_total, op=dist.ReduceOp.MAX)
+    ms_per_step = float(t_total.item()) / args.steps
+    value = nq * world / (ms_per_step * 1e-3)
+
+    # ---- e2e: host buffers through the C ABI (pinned queries in, host results out) ----
+    hq = torch.from_numpy(queries).pin_memory()
+    hs = torch.empty((nq, k), dtype=torch.int32).pin_memory()
+    hr = torch.empty((nq, k), dtype=torch.int64).pin_memory()
+    corpus.set_timing(False)
+
+    def e2e_step():
+        if world == 1:
+            corpus.search(hq, k, _capi.HAMMING, None, hs, hr)        # H2D + scan + merge + D2H inside
+        else:
+            dq2 = hq.to(dev, non_blocking=True)
+            s, r = searcher.search(dq2, k, _capi.HAMMING)
+            hs.copy_(s, non_blocking=True)
+            hr.copy_(r, non_blocking=True)
+            torch.cuda.synchronize()
+
+    for _ in range(max(1, args.warmup)):
+        flush.zero_()
+        e2e_step()
+    barrier()
+    e2e_t = 0.0
+    for _ in range(args.steps):
+        flush.zero_()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        e2e_step()
+        e2e_t += time.perf_counter() - t0
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    e2e_total = torch.tensor([e2e_t], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(e2e_total, op=dist.ReduceOp.MAX)
+    e2e_ms = float(e2e_total.item()) / args.steps * 1e3
+    e2e_value = nq * world / (e2e_ms * 1e-3)
+
+    # ---- roofline of the scan kernel ----
+    scan_avg_ms = float(np.mean(scan_ms))
+    popc_peak, _ = _capi.microbench(0, 8192, device=local_rank)           # lane-POPC/s, measured live
+    alg_bytes = rows * w + rows / 8 + nq * w + nq * k * 12
+    alg_popc = rows * nq * (w / 4)
+    t_hbm = alg_bytes / (hbm_peak * 1e9)
+    t_int = alg_popc / popc_peak
+    t_roof = max(t_hbm, t_int)
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic_cfg2.json")
+    if os.path.exists(tpath):
+        traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
+    roofline = {
+        "bound": "int_pipe" if t_int >= t_hbm else "hbm",
+        "achieved": alg_popc / (scan_avg_ms * 1e-3) / 1e12, "peak": popc_peak / 1e12, "unit": "TPOPC/s",
+        "frac": t_roof / (scan_avg_ms * 1e-3), "traffic": traffic,
+        "kernel": "scan_topk_kernel<128,HAMMING,8,8>", "kernel_ms": scan_avg_ms,
+        "algorithmic": {"bytes_per_launch": alg_bytes, "popc_per_launch": alg_popc,
+                        "per_unit": "W bytes and W/4 32-bit POPC per (query,row) pair; W=128"},
+        "peak_source": "POPC: vl_microbench live in this run; HBM: " + hbm_src,
+        "note": ("frac > 1 is expected: carry-save adders turn 32 algorithmic POPC per pair into 16 issued "
+                 "POPC + 64 LOP3, so the kernel beats the plain-POPC pipe bound"),
+        "hbm_view": {"achieved": rows * w / (scan_avg_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                     "frac": rows * w / (scan_avg_ms * 1e-3) / 1e9 / hbm_peak},
+    }
+
+    extra = {}
+    cpu_baseline = None
+    if world == 1:
+        # HBM-bound leg of the same kernel: 1 and 2 queries over a corpus far larger than L2
+        big = 32_000_000
+        with _capi.Corpus(w, device=local_rank, capacity_rows=big) as cb:
+            cb.set_stream(torch.cuda.current_stream().cuda_stream)
+            cb.fill_synthetic(0, 0, big)
+            cb.set_timing(True)
+            for q_small in (1, 2):
+                ds = torch.empty((q_small, k), dtype=torch.int32, device=dev)
+                dr = torch.empty((q_small, k), dtype=torch.int64, device=dev)
+                ts, tt = [], []
+                for i in range(6):
+                    cb.search(dq[:q_small], k, _capi.HAMMING, None, ds, dr)
+                    t_all, t_scan = cb.last_timing()
+                    if i >= 2:
+                        ts.append(t_scan)
+                        tt.append(t_all)
+                gbs = big * w / (float(np.mean(ts)) * 1e-3) / 1e9
+                extra[f"hbm_leg_q{q_small}"] = {
+                    "rows": big, "corpus_GB": big * w / 1e9, "scan_ms": float(np.mean(ts)),
+                    "total_ms": float(np.mean(tt)), "GBps": gbs, "hbm_frac": gbs / hbm_peak,
+                    "qps": q_small / (float(np.mean(tt)) * 1e-3)}
+        # the reference's LIVE score (XOR-sum of byte values, vlite/model.py:82) on the same workload
+        ds = torch.empty((nq, k), dtype=torch.int32, device=dev)
+        dr = torch.empty((nq, k), dtype=torch.int64, device=dev)
+        corpus.set_timing(True)
+        tt = []
+        for i in range(6):
+            flush.zero_()
+            corpus.search(dq, k, _capi.XORSUM, None, ds, dr)
+            if i >= 2:
+                tt.append(corpus.last_timing()[0])
+        extra["xorsum_same_workload"] = {"ms_per_step": float(np.mean(tt)), "qps": nq / (float(np.mean(tt)) * 1e-3)}
+        if rank == 0 and not args.no_cpu:
+            qps, ms, cores, sample = time_reference(6, 1, budget_s=40.0)
+            cpu_baseline = {"value": qps, "unit": "queries/s", "cores": cores, "kind": "port", "sample": sample}
+
+    if rank == 0:
+        line = {
+            "metric": "queries_per_sec", "value": value, "unit": "queries/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32 (XOR/POPC on packed bits)",
+            "data": "synthetic", "config": workload_config(world),
+            "e2e": {"value": e2e_value, "unit": "queries/s", "h2d_bytes_per_step": nq * w,
+                    "d2h_bytes_per_step": nq * k * 12, "ms_per_step": e2e_ms},
+            "gpu_launches": int(launches),
+            "roofline": roofline, "cpu_baseline": cpu_baseline, "clocks": clocks,
+            "scan_GBps_aggregate": rows * w * world / (scan_avg_ms * 1e-3) / 1e9,
+            "qps_over_whole_corpus": nq / (ms_per_step * 1e-3),
+            "value_definition": "Q x total_rows / 500k per step / time: queries/s in 500k-row-corpus equivalents",
+            "extra": extra,
+        }
+        print(json.dumps(line), flush=True)
+    corpus.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -134,9 +134,13 @@ int vl_scores(vl_corpus* c, const uint8_t* query_any, int metric, uint64_t first
               uint32_t* out_any);
 /* merge n_lists candidate lists (each Q x k_in, ascending (score,row), sentinel
  * padded) into Q x k_out: the step after the all-gather of per-shard top-k
- * (SURVEY.md section 8e).  All pointers device memory. */
+ * (SURVEY.md section 8e).  All pointers device memory.  List l starts at
+ * scores_dev + l*score_list_stride and rows_dev + l*row_list_stride (strides in
+ * ELEMENTS; 0 = dense, i.e. Q*k_in), so one all-gathered byte buffer holding
+ * every rank's [scores | rows] block can be merged in place. */
 int vl_merge_topk(int device, void* cuda_stream, const uint32_t* scores_dev, const uint64_t* rows_dev,
                   int n_lists, int n_queries, int k_in, int k_out,
+                  uint64_t score_list_stride, uint64_t row_list_stride,
                   uint32_t* out_score_dev, uint64_t* out_row_dev);
 
 /* ---- rescore (north-star piece 3; no reference implementation -- nearest

@@ -78,7 +78,8 @@ def load():
         "vl_synth_filter_mask": (c_int, [c_void_p, c_u64, c_u64, c_void_p]),
         "vl_search": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
         "vl_scores": (c_int, [c_void_p, c_void_p, c_int, c_u64, c_u64, c_void_p]),
-        "vl_merge_topk": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
+        "vl_merge_topk": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_u64, c_u64,
+                                  c_void_p, c_void_p]),
         "vl_rescore": (c_int, [c_void_p, c_void_p, c_u64, c_int, c_void_p, c_int, c_void_p, c_int, c_int, c_int,
                                c_void_p, c_void_p]),
         "vl_quantize_binary": (c_int, [c_int, c_void_p, c_void_p, c_u64, c_int, c_void_p]),
@@ -296,9 +297,12 @@ class Corpus:
 
 
 def merge_topk(scores_dev, rows_dev, n_lists: int, n_queries: int, k_in: int, k_out: int,
-               out_scores_dev, out_rows_dev, device: int = 0, stream: int | None = None):
+               out_scores_dev, out_rows_dev, device: int = 0, stream: int | None = None,
+               score_list_stride: int = 0, row_list_stride: int = 0):
+    """Merge n_lists device-resident candidate lists; strides in elements (0 = dense)."""
     check(load().vl_merge_topk(device, ctypes.c_void_p(stream or 0), ptr(scores_dev), ptr(rows_dev), n_lists,
-                               n_queries, k_in, k_out, ptr(out_scores_dev), ptr(out_rows_dev)))
+                               n_queries, k_in, k_out, score_list_stride, row_list_stride,
+                               ptr(out_scores_dev), ptr(out_rows_dev)))
 
 
 def quantize_binary(x, out=None, device: int = 0, stream: int | None = None):

@@ -745,7 +745,7 @@ extern "C" int vl_search(vl_corpus* c, const uint8_t* queries_any, int n_queries
             const unsigned mg = (unsigned)((n_queries + kMergeWarps - 1) / kMergeWarps);
             merge_topk_kernel<<<mg, kMergeWarps * 32, kMergeWarps * n_lists * sizeof(uint16_t), st>>>(
                 p.part_scores, p.part_rows, (int)n_lists, n_queries, k_pass, k_pass, o_s, o_r, k,
-                pass * kWarpListMaxK);
+                pass * kWarpListMaxK, (size_t)n_queries * k_pass, (size_t)n_queries * k_pass);
             LAUNCHED();
             if (pass + 1 < n_pass) {
                 cursor_update_kernel<<<(n_queries + 127) / 128, 128, 0, st>>>(
@@ -795,8 +795,8 @@ extern "C" int vl_scores(vl_corpus* c, const uint8_t* query_any, int metric, uin
 }
 
 extern "C" int vl_merge_topk(int device, void* cuda_stream, const uint32_t* scores_dev, const uint64_t* rows_dev,
-                             int n_lists, int n_queries, int k_in, int k_out, uint32_t* out_score_dev,
-                             uint64_t* out_row_dev) {
+                             int n_lists, int n_queries, int k_in, int k_out, uint64_t score_list_stride,
+                             uint64_t row_list_stride, uint32_t* out_score_dev, uint64_t* out_row_dev) {
     if (!scores_dev || !rows_dev || !out_score_dev || !out_row_dev) return fail(VL_EINVAL, "NULL argument");
     if (n_lists < 1 || n_queries < 1 || k_in < 1 || k_out < 1 || k_in > 65535)
         return fail(VL_EINVAL, "bad merge shape");
@@ -808,7 +808,9 @@ extern "C" int vl_merge_topk(int device, void* cuda_stream, const uint32_t* scor
         CU(cudaFuncSetAttribute(merge_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const unsigned mg = (unsigned)((n_queries + kMergeWarps - 1) / kMergeWarps);
     merge_topk_kernel<<<mg, kMergeWarps * 32, smem, static_cast<cudaStream_t>(cuda_stream)>>>(
-        scores_dev, rows_dev, n_lists, n_queries, k_in, k_out, out_score_dev, out_row_dev, k_out, 0);
+        scores_dev, rows_dev, n_lists, n_queries, k_in, k_out, out_score_dev, out_row_dev, k_out, 0,
+        score_list_stride ? (size_t)score_list_stride : (size_t)n_queries * k_in,
+        row_list_stride ? (size_t)row_list_stride : (size_t)n_queries * k_in);
     LAUNCHED();
     return VL_OK;
 }

@@ -22,7 +22,8 @@ __device__ __forceinline__ bool key_less(uint32_t s1, uint64_t r1, uint32_t s2, 
 __global__ void __launch_bounds__(kMergeWarps * 32)
 merge_topk_kernel(const uint32_t* __restrict__ scores, const uint64_t* __restrict__ rows, int n_lists,
                   int n_queries, int k_in, int k_out, uint32_t* __restrict__ out_scores,
-                  uint64_t* __restrict__ out_rows, int out_stride, int out_offset) {
+                  uint64_t* __restrict__ out_rows, int out_stride, int out_offset, size_t score_list_stride,
+                  size_t row_list_stride) {
     extern __shared__ uint16_t s_heads[];  // [kMergeWarps][n_lists]
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int q = blockIdx.x * kMergeWarps + warp;
@@ -38,9 +39,9 @@ merge_topk_kernel(const uint32_t* __restrict__ scores, const uint64_t* __restric
         for (int l = lane; l < n_lists; l += 32) {
             const int h = heads[l];
             if (h < k_in) {
-                const size_t idx = ((size_t)l * n_queries + q) * k_in + h;
-                const uint64_t r = rows[idx];
-                const uint32_t s = scores[idx];
+                const size_t idx = (size_t)q * k_in + h;
+                const uint64_t r = rows[(size_t)l * row_list_stride + idx];
+                const uint32_t s = scores[(size_t)l * score_list_stride + idx];
                 if (r != kSentinelRow && key_less(s, r, bs, br)) {
                     bs = s;
                     br = r;
