@@ -1,0 +1,230 @@
+"""-m gpu: the VLite / EmbeddingModel / CTX mirrors, driven like the reference's own call sites and
+checked against outputs the reference produced (tests/golden/collection_golden.json)."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from oracle import ctxfile as octx, search as osearch, synth
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def bits_embedder(queries_u8):
+    """A stand-in for the HF model whose sign pattern IS the given packed vectors."""
+    def f(texts):
+        n = len(texts)
+        return np.unpackbits(queries_u8[:n], axis=1).astype(np.float32) * 2 - 1
+    return f
+
+
+@pytest.fixture()
+def golden():
+    g = json.load(open(os.path.join(GOLD, "collection_golden.json")))
+    w = g["width"]
+    g["corpus"] = np.frombuffer(bytes.fromhex(g["corpus_u8_hex"]), dtype=np.uint8).reshape(-1, w)
+    g["queries"] = np.frombuffer(bytes.fromhex(g["queries_u8_hex"]), dtype=np.uint8).reshape(-1, w)
+    return g
+
+
+def _build(gpu, golden, tmp_path, **kw):
+    from vlite_b200 import VLite
+    v = VLite("golden", ctx_dir=str(tmp_path / "contexts"), embedder=bits_embedder(golden["queries"]), **kw)
+    enc = osearch.to_ref_encoding(golden["corpus"])
+    keys = [k for k in golden["keys"] if k != "odd_0"]     # the reference skips the odd-width row (main.py:143)
+    first = v._append_vectors(enc)
+    for i, key in enumerate(keys):
+        v._register(key, f"text {i}", dict(golden["metadata"][key]), first + i)
+    return v
+
+
+def test_rank_and_filter_matches_reference_outputs(gpu, golden, tmp_path):
+    v = _build(gpu, golden, tmp_path, filter_mode="reference")
+    for case in golden["rank_and_filter"]:
+        q = osearch.to_ref_encoding(golden["queries"][case["q"]])
+        got = v.rank_and_filter(q, case["top_k"], case["metadata"], case["mult"])
+        assert [c for c, _ in got] == case["ids"], case
+        assert [int(s) for _, s in got] == case["scores"], case      # includes main.py:165's mis-pairing
+    v.close()
+
+
+def test_prefilter_is_true_filtered_topk(gpu, golden, tmp_path):
+    v = _build(gpu, golden, tmp_path)                                  # default: filter inside the scan
+    keys = [k for k in golden["keys"] if k != "odd_0"]
+    for md in ({"tag": "b"}, {"tag": "c", "parity": 1}, {"tag": "zzz"}):
+        valid = np.array([all(golden["metadata"][k].get(a) == b for a, b in md.items()) for k in keys])
+        for qi in range(2):
+            got = v.rank_and_filter(osearch.to_ref_encoding(golden["queries"][qi]), 5, md)
+            es, er = osearch.search(golden["queries"][qi:qi + 1], golden["corpus"], 5, osearch.XORSUM, valid=valid)
+            keep = er[0] != osearch.SENTINEL_ROW
+            assert [c for c, _ in got] == [keys[int(r)] for r in er[0][keep]]
+            assert [int(s) for _, s in got] == [int(s) for s in es[0][keep]]
+    v.close()
+
+
+def test_retrieve_merges_all_queries_like_reference(gpu, golden, tmp_path):
+    v = _build(gpu, golden, tmp_path)
+    r = v.retrieve(["a", "b"], top_k=4, return_scores=True)          # two query rows -> ONE list
+    assert [[a, b, c, int(d)] for a, b, c, d in r] == golden["retrieve_scores"]
+    assert [[a, b, c] for a, b, c in v.retrieve(["a", "b"], top_k=3)] == golden["retrieve_plain"]
+    assert v.retrieve(None) is golden["retrieve_none"] and v.retrieve("") is None
+    per_query = v.retrieve_batch(["a", "b"], top_k=2, return_scores=True)
+    assert len(per_query) == 2 and per_query[1][0][0] == "doc5_2" and int(per_query[1][0][3]) == 64
+    v.close()
+
+
+def test_delete_prefix_semantics_and_persistence(gpu, golden, tmp_path):
+    v = _build(gpu, golden, tmp_path)
+    enc = osearch.to_ref_encoding(golden["corpus"])
+    v.set_batch(["x"], enc[:1])
+    extra_key = [k for k in v.index.keys()][-1]
+    assert extra_key.endswith("_0")
+    v.delete(extra_key[:-2])
+    for cid, row in (("doc1extra_0", 0), ("doc1_extra_0", 1)):
+        first = v._append_vectors(enc[row:row + 1])
+        v._register(cid, cid, {}, first)
+    before = v.count()
+    assert before == golden["delete"]["before"]     # (the golden run dropped its odd-width row before deleting)
+    assert v.delete("doc1") == golden["delete"]["deleted"]
+    assert ("doc1extra_0" in v.index) == golden["delete"]["doc1extra_0_survives"]
+    assert ("doc1_extra_0" in v.index) == golden["delete"]["doc1_extra_0_survives"]
+    assert v.delete(["nope", "nada"]) == golden["delete_missing"]
+    # deleted rows never come back from a search
+    got = v.rank_and_filter(osearch.to_ref_encoding(golden["corpus"][3]), 3)     # doc1_0 was row 3
+    assert all(not c.startswith("doc1_") for c, _ in got)
+    # delete() saved a CLEAN file: reload gives exactly the live collection
+    from vlite_b200 import VLite
+    v2 = VLite("golden", ctx_dir=str(tmp_path / "contexts"), embedder=bits_embedder(golden["queries"]))
+    assert v2.count() == v.count() and list(v2.index.keys()) == list(v.index.keys())
+    q = osearch.to_ref_encoding(golden["queries"][0])
+    assert v2.rank_and_filter(q, 5) == v.rank_and_filter(q, 5)
+    # and that file is what the reference's loader would accept (oracle restatement of ctx.py:85-139)
+    header, emb, contexts, metadata, _ = octx.read_ctx(str(tmp_path / "contexts" / "golden.ctx"))
+    assert header["embedding_size"] == 64 and len(emb) == len(contexts) == len(metadata) == v.count()
+    v.close()
+    v2.close()
+
+
+def test_errors_and_set_batch_like_reference(gpu, golden, tmp_path):
+    from vlite_b200 import VLite
+    v = VLite("empty", ctx_dir=str(tmp_path / "contexts"), embedder=bits_embedder(golden["queries"]))
+    with pytest.raises(ValueError, match=golden["empty_error"]):
+        v.rank_and_filter(osearch.to_ref_encoding(golden["queries"][0]), 3)
+    enc = osearch.to_ref_encoding(golden["corpus"])
+    with pytest.raises(ValueError) as e1:
+        v.set_batch(["a", "b"], enc[:1])
+    with pytest.raises(ValueError) as e2:
+        v.set_batch(["a"], enc[:1], [{}, {}])
+    assert [str(e1.value), str(e2.value)] == golden["set_batch_errors"]
+    v.set_batch(["t0", "t1", "t2"], enc[:3], [{"i": 0}, {"i": 1}, {"i": 2}])
+    assert v.count() == golden["set_batch_count"]
+    assert sorted({k.rsplit("_", 1)[1] for k in v.index}) == golden["set_batch_key_suffixes"]
+    assert os.path.exists(tmp_path / "contexts" / "empty.ctx")           # set_batch saves (main.py:271)
+    v.clear()
+    assert v.count() == 0 and not os.path.exists(tmp_path / "contexts" / "empty.ctx")
+    v.close()
+
+
+def test_add_get_update_dump(gpu, golden, tmp_path):
+    from vlite_b200 import VLite
+    qs = synth.uniform_queries(40, 8, 64)
+    v = VLite("api", ctx_dir=str(tmp_path / "contexts"), embedder=bits_embedder(qs))
+    res = v.add(["alpha", {"text": "beta", "metadata": {"lang": "el"}}], metadata={"src": "t"}, item_id="it")
+    assert len(res) == 1 and res[0][0] == "it" and res[0][1].shape == (2, 64) and res[0][2] == {"lang": "el", "src": "t"}
+    assert v.count() == 2 and list(v.index.keys()) == ["it_0", "it_1"]
+    np.testing.assert_array_equal(res[0][1], osearch.to_ref_encoding(qs[:2]))      # reference encoding out
+    assert res[0][1].min() >= -256 and res[0][1].max() <= -1
+    long = v.add("z" * 5000, need_chunks=True, item_id="long")                     # fast char chunks
+    assert v.count() == 2 + 3 and long[0][1].shape[0] == 3
+    assert v.get("it") == [("it", "alpha beta", {"src": "t", "lang": "el"})]
+    assert v.get(where={"lang": "el"}) == [("it", "beta", {"lang": "el", "src": "t"})]
+    assert v.update("it", metadata={"seen": 1}) is True and v.update("nope") is False
+    assert v.get("it")[0][2]["seen"] == 1
+    d = v.dump()
+    e = d["it_1"]
+    assert e["text"] == "beta" and e["metadata"]["lang"] == "el"
+    np.testing.assert_array_equal(e["binary_vector"], osearch.to_ref_encoding(qs[1]))
+    v.set("it", text="gamma")
+    assert v.get("it")[0][1] == "gamma gamma"
+    v.set("fresh", text="delta", metadata={"a": 1})
+    assert "fresh_0" in v.index
+    hits = v.retrieve("alpha", top_k=1, metadata={"a": 1})
+    assert hits[0][0] == "fresh_0"
+    v.close()
+
+
+def test_embedding_model_search_is_the_reference_seam(gpu):
+    from vlite_b200 import EmbeddingModel
+    g = np.load(os.path.join(GOLD, "search_golden.npz"))
+    m = EmbeddingModel(embedder=lambda t: None)
+    for name in ("u64", "u128", "dup128", "kbig64"):
+        corpus, queries, k = g[f"{name}_corpus_u8"], g[f"{name}_queries_u8"], int(g[f"{name}_k"])
+        e_f32 = osearch.to_ref_encoding(corpus).astype(np.float32)     # what main.py:146 hands to search
+        for qi, q in enumerate(queries):
+            idx, sc = m.search(osearch.to_ref_encoding(q), e_f32, k)
+            assert idx.dtype == np.int64 and sc.dtype == np.int64 and len(idx) == min(k, len(corpus))
+            ref_idx, ref_sc = g[f"{name}_q{qi}_idx"], g[f"{name}_q{qi}_scores"]
+            np.testing.assert_array_equal(sc, np.sort(ref_sc, kind="stable"))       # same scores
+            ci, cs = osearch.canonicalise_ties(ref_idx, ref_sc)
+            kth = sc[-1]
+            np.testing.assert_array_equal(idx[sc < kth], ci[cs < kth])               # same rows off the tie boundary
+            er, es = osearch.ref_search_port(osearch.to_ref_encoding(q), e_f32, k)   # canonical order: bit exact
+            np.testing.assert_array_equal(idx, er)
+            idx2, sc2 = m.search(q, corpus, k)                                       # raw bytes score the same
+            np.testing.assert_array_equal(sc2, sc)
+        bits_q = np.unpackbits(queries[0])[None, :]
+        bits_c = np.unpackbits(corpus, axis=1)
+        np.testing.assert_array_equal(m.hamming_distance(bits_q, bits_c), g[f"{name}_q0_hamming"])
+
+
+def test_quantize_binary_matches_packbits(gpu):
+    rng = np.random.default_rng(3)
+    x = rng.standard_normal((37, 512)).astype(np.float32)
+    x[0, :8] = 0.0                                                       # (x > 0): zero is a 0 bit
+    np.testing.assert_array_equal(gpu.quantize_binary(x), osearch.quantize_binary(x))
+    x2 = rng.standard_normal((5, 1024)).astype(np.float32)
+    np.testing.assert_array_equal(gpu.quantize_binary(x2), np.packbits(x2 > 0, axis=-1))
+
+
+def test_ctx_embeddings_stream_to_hbm(gpu, tmp_path):
+    w = 64
+    rows = synth.corpus_rows(50, 0, 3000, w)
+    p = str(tmp_path / "big.ctx")
+    octx.write_ctx(p, {"embedding_model": "m", "embedding_size": 64, "embedding_dtype": "float32", "context_length": 512},
+                   osearch.to_ref_encoding(rows).astype(np.float32), [f"c{i}" for i in range(3000)],
+                   {f"id{i}_0": {"i": i} for i in range(2990)})          # fewer keys than rows: surplus ignored
+    from vlite_b200 import VLite
+    v = VLite("big", ctx_dir=str(tmp_path))
+    assert v.count() == 2990
+    np.testing.assert_array_equal(v._corpus.read(), rows[:2990])
+    got = v.rank_and_filter(osearch.to_ref_encoding(rows[1234]), 1)
+    assert got == [("id1234_0", np.int64(0))]
+    v.close()
+    # legacy layout (tests/contexts/vlite-bench.ctx): 512 floats of 0.0/1.0 per row
+    f = json.load(open(os.path.join(GOLD, "fixture_facts.json")))
+    first8 = np.frombuffer(bytes.fromhex(f["legacy_first8_packed_hex"]), dtype=np.uint8).reshape(8, 64)
+    p2 = str(tmp_path / "legacy.ctx")
+    import struct
+    with open(p2, "wb") as fh:
+        hj = json.dumps(f["header"]).encode()
+        fh.write(b"CTXF" + struct.pack("<I", 1) + struct.pack("<II", 0, len(hj)) + hj)
+        data = np.unpackbits(first8, axis=1).astype("<f4").tobytes()
+        fh.write(struct.pack("<II", 1, len(data)) + data)
+        fh.write(struct.pack("<II", 2, 0))
+        mj = json.dumps({f"k{i}_0": {} for i in range(8)}).encode()
+        fh.write(struct.pack("<II", 3, len(mj)) + mj)
+    v = VLite("legacy", ctx_dir=str(tmp_path))
+    assert v.count() == 8 and v._corpus.width == 64
+    np.testing.assert_array_equal(v._corpus.read(), first8)
+    v.close()
+    # values outside the encoding are refused, loudly
+    with gpu.Corpus(64) as c:
+        bad = np.full((2, 64), 300.0, dtype=np.float32)
+        with pytest.raises(gpu.VliteB200Error) as ei:
+            c.append_f32(bad, gpu.SRC_F32_OFFSET)
+        assert ei.value.code == gpu.ERANGE and c.rows == 0
+        c.append_f32(osearch.to_ref_encoding(rows[:5]).astype(np.float32), gpu.SRC_F32_OFFSET)
+        c.append_f32(rows[5:9].astype(np.float32), gpu.SRC_F32_OFFSET)            # raw 0..255 also accepted
+        np.testing.assert_array_equal(c.read(), rows[:9])

@@ -1,0 +1,105 @@
+"""-m gpu: rescore kernel vs the oracle (float64 dot; "parity unpinned": the reference has no
+rescore) and the single-GPU emulation of the sharded merge."""
+import numpy as np
+import pytest
+
+from oracle import cscan, search as osearch, synth
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-5          # north_star: rescored float scores within 1e-5 relative
+
+
+def _docs(gpu, torch, n, dims, seed=7):
+    d = torch.empty((n, dims), dtype=torch.int8, device="cuda")
+    gpu.synth_docs_i8(seed, 0, n, dims, d)
+    torch.cuda.synchronize()
+    host = synth.doc_rows_i8(seed, 0, n, dims)
+    np.testing.assert_array_equal(d.cpu().numpy(), host)                # device generator == numpy generator
+    return d, host
+
+
+@pytest.mark.parametrize("qtype", ["f32", "i8"])
+@pytest.mark.parametrize("n_cand,k", [(100, 10), (1000, 10), (37, 37), (2048, 50)])
+def test_rescore_matches_oracle(gpu, qtype, n_cand, k):
+    torch = pytest.importorskip("torch")
+    n, dims, nq = 20000, 1024, 9
+    docs, host_docs = _docs(gpu, torch, n, dims)
+    rng = np.random.default_rng(5)
+    if qtype == "f32":
+        queries = rng.standard_normal((nq, dims)).astype(np.float32)
+    else:
+        queries = rng.integers(-128, 128, size=(nq, dims), dtype=np.int8)
+    cand = np.stack([rng.choice(n, size=n_cand, replace=False) for _ in range(nq)]).astype(np.uint64)
+    cand[0, -3:] = osearch.SENTINEL_ROW                                   # padded candidate lists
+    with gpu.Corpus(128) as c:
+        s, r = c.rescore(docs, n, dims, queries, cand, k)
+    es, er = osearch.rescore(queries, host_docs, cand, k)
+    if qtype == "i8":
+        np.testing.assert_array_equal(r, er)                             # int32 accumulate: exact
+        np.testing.assert_array_equal(s.astype(np.float64), es)
+    else:
+        # fp32 accumulate: 1e-5 relative to the magnitude of the dot's terms
+        scale = np.abs(host_docs[cand[cand != osearch.SENTINEL_ROW][:8].astype(np.int64)].astype(np.float64)).sum(1).mean()
+        np.testing.assert_allclose(s, es, rtol=RTOL, atol=RTOL * scale)
+        same = r == er
+        assert same.mean() > 0.99                                        # order may swap only on near-ties
+        for qi, pos in zip(*np.nonzero(~same)):
+            assert abs(es[qi, pos] - s[qi, pos]) <= RTOL * scale
+
+
+def test_binary_then_rescore_pipeline(gpu):
+    """config 3 in miniature: binary top-C on sign bits of the int8 docs, then int8 rescore to k."""
+    torch = pytest.importorskip("torch")
+    n, dims, nq, C, k = 30000, 1024, 6, 200, 10
+    docs, host_docs = _docs(gpu, torch, n, dims, seed=11)
+    ubin = osearch.quantize_binary(host_docs.astype(np.float32))
+    qf = host_docs[[5, 77, 4000, 12345, 29999, 0]].astype(np.float32) + np.random.default_rng(1).standard_normal((nq, dims)).astype(np.float32) * 20
+    qb = osearch.quantize_binary(qf)
+    with gpu.Corpus(128) as c:
+        # sign-quantise the int8 docs on the device and append (no host round trip of the corpus)
+        packed = gpu.quantize_binary(docs.float().contiguous())
+        np.testing.assert_array_equal(packed, ubin)
+        c.append(packed)
+        bs, br = c.search(qb, C, gpu.HAMMING)
+        es, er = cscan.search(qb, ubin, C, gpu.HAMMING)
+        np.testing.assert_array_equal(br, er)
+        s, r = c.rescore(docs, n, dims, qf, br, k)
+    os_, or_ = osearch.rescore(qf, host_docs, er, k)
+    np.testing.assert_array_equal(r, or_)
+    np.testing.assert_allclose(s, os_, rtol=RTOL)
+    np.testing.assert_array_equal(r[:, 0], [5, 77, 4000, 12345, 29999, 0])
+
+
+@pytest.mark.parametrize("shards", [2, 4, 8])
+def test_sharded_merge_single_gpu_emulation(gpu, shards):
+    """All shards on one GPU (the profiling guide's advice for fewer GPUs than ranks): per-shard
+    top-k into the all-gather layout [scores | rows] per rank, then the strided CUDA merge."""
+    torch = pytest.importorskip("torch")
+    from vlite_b200.sharded import ShardPlan
+    n, w, nq, k = 40001, 128, 33, 10
+    nq_even = nq + (nq * k) % 2
+    full = synth.corpus_rows(9, 0, n, w, period=700)
+    queries = synth.uniform_queries(10, nq_even, w)
+    plan = ShardPlan(n, shards)
+    nb = nq_even * k
+    block = torch.empty((shards, nb * 12), dtype=torch.uint8, device="cuda")
+    dq = torch.from_numpy(queries).cuda()
+    handles = []
+    for g in range(shards):
+        c = gpu.Corpus(w, base_row=plan.base_row(g))
+        c.fill_synthetic(9, 0, plan.shard_rows(g), 700)
+        ls = block[g, : nb * 4].view(torch.int32).view(nq_even, k)
+        lr = block[g, nb * 4:].view(torch.int64).view(nq_even, k)
+        c.search(dq, k, gpu.HAMMING, None, ls, lr)
+        handles.append(c)
+    out_s = torch.empty((nq_even, k), dtype=torch.int32, device="cuda")
+    out_r = torch.empty((nq_even, k), dtype=torch.int64, device="cuda")
+    base = block.data_ptr()
+    gpu.merge_topk(base, base + nb * 4, shards, nq_even, k, k, out_s, out_r,
+                   score_list_stride=nb * 3, row_list_stride=nb * 12 // 8)
+    torch.cuda.synchronize()
+    for c in handles:
+        c.close()
+    es, er = cscan.search(queries, full, k, gpu.HAMMING)
+    np.testing.assert_array_equal(out_s.cpu().numpy().view(np.uint32), es)
+    np.testing.assert_array_equal(out_r.cpu().numpy().view(np.uint64), er)

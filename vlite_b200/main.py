@@ -1,0 +1,449 @@
+"""``VLite`` -- host-side mirror of the reference's collection API (``vlite/main.py``) over a
+corpus that lives packed in HBM.
+
+Same method names, argument meaning, return shapes and error strings as the reference class
+(vlite/main.py:19-311); what changes is where the work happens:
+
+  reference                                                  here
+  ---------------------------------------------------------  -----------------------------------
+  index = dict of Python lists, rebuilt into an (N, W)        rows appended in place to a device
+  float32 array on EVERY query (main.py:143-146)              corpus (vl_corpus_append*); host keeps
+                                                              chunk_id <-> row, texts, metadata
+  EmbeddingModel.search per query (main.py:150)               one batched vl_search for all queries
+  metadata post-filter over top_k*4 candidates, scores        filter bitmask applied INSIDE the scan
+  mis-paired afterwards (main.py:159-165)                     (true filtered top-k); the reference's
+                                                              behaviour is kept as filter_mode="reference"
+  delete = dict delete + whole-file rewrite (main.py:190)     tombstone bit + whole-file rewrite
+  CTX load: struct.unpack per row into lists (ctx.py:116)     EMBEDDINGS payload streamed to HBM and
+                                                              repacked on the device (vl_corpus_load_file)
+
+Embedding generation (the Hugging Face forward pass) stays on the reference path; pass
+``embedder=`` to plug in any ``texts -> float array`` callable.  No telemetry is sent
+(the reference posts to PostHog on init/load/save, main.py:17-24).
+"""
+from __future__ import annotations
+
+import datetime
+import logging
+from uuid import uuid4
+
+import numpy as np
+
+from . import _capi
+from .ctx import Ctx, row_floats_for
+from .model import EmbeddingModel, from_reference_encoding, to_reference_encoding
+
+logger = logging.getLogger(__name__)
+
+METRICS = {"xorsum": _capi.XORSUM, "hamming": _capi.HAMMING}
+
+
+def chop_and_chunk(text, max_seq_length=512, fast=False):
+    """vlite/utils.py:25-48.  fast=True: slices of max_seq_length*4 characters.  The token-based
+    path needs tiktoken (ingest is out of scope for this build; it is used if importable)."""
+    if isinstance(text, str):
+        text = [text]
+    chunks = []
+    for t in text:
+        if fast:
+            size = max_seq_length * 4
+            chunks.extend([t[i:i + size] for i in range(0, len(t), size)])
+        else:
+            import tiktoken
+            enc = tiktoken.get_encoding("cl100k_base")
+            ids = enc.encode(t, disallowed_special=())
+            if len(ids) <= max_seq_length:
+                chunks.append(t)
+            else:
+                chunks.extend(enc.decode(ids[i:i + max_seq_length]) for i in range(0, len(ids), max_seq_length))
+    return chunks
+
+
+def _hashable(v):
+    try:
+        hash(v)
+        return True
+    except TypeError:
+        return False
+
+
+class _IndexView(dict):
+    """What ``VLite.index`` / ``dump()`` expose: chunk_id -> {'text', 'metadata', 'binary_vector'}
+    like the reference's dict (main.py:41), except that the vector is read back from the device
+    when asked for instead of being held as a Python list."""
+
+    def __init__(self, owner):
+        super().__init__()
+        self._owner = owner
+
+    def __getitem__(self, chunk_id):
+        return self._owner._entry(chunk_id)
+
+    def get(self, chunk_id, default=None):
+        return self._owner._entry(chunk_id) if chunk_id in self._owner._row_of else default
+
+    def __contains__(self, chunk_id):
+        return chunk_id in self._owner._row_of
+
+    def __iter__(self):
+        return iter(self._owner._row_of)
+
+    def __len__(self):
+        return len(self._owner._row_of)
+
+    def keys(self):
+        return self._owner._row_of.keys()
+
+    def values(self):
+        return (self._owner._entry(k) for k in self._owner._row_of)
+
+    def items(self):
+        return ((k, self._owner._entry(k)) for k in self._owner._row_of)
+
+    def __repr__(self):
+        return f"<VLite index: {len(self)} chunks on device>"
+
+
+class VLite:
+    def __init__(self, collection=None, device=None, model_name="mixedbread-ai/mxbai-embed-large-v1", *,
+                 embedder=None, metric="xorsum", width=None, filter_mode="prefilter", ctx_dir="contexts",
+                 gpu_index=0):
+        """collection / device / model_name: as vlite/main.py:20.  Keyword-only additions:
+        embedder (texts -> float array), metric ("xorsum" = the reference's live score,
+        "hamming" = true Hamming distance), width (bytes per row, default from the data: 64),
+        filter_mode ("prefilter" | "reference"), ctx_dir, gpu_index."""
+        if metric not in METRICS:
+            raise ValueError(f"metric must be one of {sorted(METRICS)}")
+        if filter_mode not in ("prefilter", "reference"):
+            raise ValueError("filter_mode must be 'prefilter' or 'reference'")
+        self.device = device or "cuda"
+        if collection is None:
+            collection = f"vlite_{datetime.datetime.now().strftime('%Y%m%d_%H%M%S')}"
+        self.collection = f"{collection}"
+        self.metric = METRICS[metric]
+        self.filter_mode = filter_mode
+        self.gpu_index = gpu_index
+        self.model = EmbeddingModel(model_name, device=self.device, embedder=embedder, gpu_index=gpu_index)
+        self.ctx = Ctx(ctx_dir)
+        self._width = width
+        self._corpus = None
+        self._row_of = {}          # chunk_id -> row (None: no stored vector)
+        self._ids = []             # row -> chunk_id (None once deleted)
+        self._texts = {}           # chunk_id -> text
+        self._metas = {}           # chunk_id -> metadata dict
+        self._extra = {}           # chunk_id -> {'vector': ...} written by update() (main.py:180)
+        self._postings = {}        # (key, value) -> list of rows, for filter masks
+        self.index = _IndexView(self)
+        self._load_collection()
+
+    # ------------------------------------------------------------------ internals
+    def _ensure_corpus(self, width: int):
+        if self._corpus is None:
+            self._width = self._width or width
+            self._corpus = _capi.Corpus(self._width, device=self.gpu_index)
+        return self._corpus
+
+    def _entry(self, chunk_id):
+        row = self._row_of[chunk_id]
+        if row is None:
+            vec = np.zeros(self.model.dimension)                         # main.py:50
+        else:
+            vec = to_reference_encoding(self._corpus.read(row, 1)[0])
+        e = {"text": self._texts[chunk_id], "metadata": self._metas[chunk_id], "binary_vector": vec}
+        e.update(self._extra.get(chunk_id, {}))
+        return e
+
+    def _post(self, chunk_id, row):
+        for kv in self._metas[chunk_id].items():
+            if _hashable(kv[1]):
+                self._postings.setdefault(kv, []).append(row)
+
+    def _register(self, chunk_id, text, metadata, row):
+        old = self._row_of.get(chunk_id)
+        if old is not None:                                              # dict overwrite (main.py:91)
+            self._corpus.tombstone([old])
+            self._ids[old] = None
+        self._row_of[chunk_id] = row
+        self._texts[chunk_id] = text
+        self._metas[chunk_id] = metadata
+        self._extra.pop(chunk_id, None)
+        if row is not None:
+            while len(self._ids) <= row:
+                self._ids.append(None)
+            self._ids[row] = chunk_id
+            self._post(chunk_id, row)
+
+    def _append_vectors(self, vectors) -> int:
+        """vectors: (n, W) in the reference encoding or raw bytes.  Returns the first row."""
+        u8 = from_reference_encoding(np.asarray(vectors))
+        u8 = np.ascontiguousarray(np.atleast_2d(u8))
+        return self._ensure_corpus(u8.shape[1]).append(u8)
+
+    def _load_collection(self):
+        """vlite/main.py:42-53: index keyed by metadata.keys() order; embeddings[idx] and
+        contexts[idx] are positional; surplus rows in the file are ignored."""
+        cf = self.ctx.read(self.collection)
+        cf.load(materialise=False)
+        keys = list(cf.metadata.keys())
+        if not keys:
+            return
+        floats = row_floats_for(cf.header)
+        n_emb = cf.n_embeddings
+        n_take = min(len(keys), n_emb)
+        if n_take:
+            kind = _capi.SRC_F32_BITS if floats == 512 else _capi.SRC_F32_OFFSET
+            width = floats // 8 if floats == 512 else floats
+            off, length = cf.embeddings_section
+            c = self._ensure_corpus(width)
+            first, n = c.load_file(cf.file_path, off, length, kind, max_rows=n_take)
+            assert n == n_take
+        else:
+            first = 0
+        for idx, chunk_id in enumerate(keys):
+            text = cf.contexts[idx] if idx < len(cf.contexts) else ""
+            row = first + idx if idx < n_take else None
+            self._register(chunk_id, text, cf.metadata.get(chunk_id, {}), row)
+
+    def _filter_rows(self, metadata: dict):
+        """Rows whose metadata satisfies all(md.get(k) == v) (main.py:162)."""
+        items = list(metadata.items())
+        if all(_hashable(v) for _, v in items):
+            lists = [self._postings.get(kv, []) for kv in items]
+            seed = min(lists, key=len)
+            rows = [r for r in seed if self._ids[r] is not None
+                    and all(self._metas[self._ids[r]].get(k) == v for k, v in items)]
+        else:
+            rows = [r for cid, r in self._row_of.items() if r is not None
+                    and all(self._metas[cid].get(k) == v for k, v in items)]
+        return np.unique(np.asarray(rows, dtype=np.int64))
+
+    def _filter_mask(self, metadata: dict):
+        n = self._corpus.rows
+        bits = np.zeros((n + 31) // 32 * 32, dtype=bool)
+        bits[self._filter_rows(metadata)] = True
+        return np.packbits(bits.reshape(-1, 32), axis=1, bitorder="little").view(np.uint32).reshape(-1)
+
+    def _search(self, queries_u8, k, mask=None):
+        if self._corpus is None or self._corpus.live_rows == 0 or queries_u8.shape[1] != self._corpus.width:
+            raise ValueError("No valid binary vectors found for comparison.")     # main.py:149
+        k = max(1, min(int(k), _capi.MAX_K))
+        scores, rows = self._corpus.search(queries_u8, k, self.metric, mask)
+        return scores, rows
+
+    # ------------------------------------------------------------------ API
+    def add(self, data, metadata=None, item_id=None, need_chunks=False, fast=True):
+        """vlite/main.py:61-104 -- including its quirks: one item_id is generated and reused for
+        every item of the call, chunk ids run ``{item_id}_{n}`` over all chunks, the return value is
+        a one-element list ``[(item_id, encoded_vectors, last_metadata)]``, and nothing is saved."""
+        data = [data] if not isinstance(data, list) else data
+        all_chunks, all_metadata = [], []
+        item_metadata = {}
+        for item in data:
+            if isinstance(item, dict):
+                text_content = item["text"]
+                item_metadata = item.get("metadata", {})
+            else:
+                text_content = item
+                item_metadata = {}
+            if item_id is None:
+                item_id = str(uuid4())
+            item_metadata.update(metadata or {})
+            chunks = chop_and_chunk(text_content, fast=fast) if need_chunks else [text_content]
+            all_chunks.extend(chunks)
+            all_metadata.extend([item_metadata] * len(chunks))
+        encoded = self.model.embed(all_chunks, precision="binary")
+        if len(all_chunks):
+            first = self._append_vectors(encoded)
+            for idx, (chunk, md) in enumerate(zip(all_chunks, all_metadata)):
+                self._register(f"{item_id}_{idx}", chunk, md, first + idx)
+        return [(item_id, encoded, all_metadata[-1] if all_metadata else item_metadata)]
+
+    def retrieve(self, text=None, top_k=5, metadata=None, return_scores=False, top_k_multiplier=4):
+        """vlite/main.py:108-128: every query row is ranked, ALL results are merged, sorted by
+        score and cut to top_k -- a list of Q texts yields ONE list.  Falsy text returns None."""
+        if not text:
+            return None
+        queries = self.model.embed(text, precision="binary")
+        results = []
+        for chunk_results in self._rank_batch(np.atleast_2d(queries), top_k, metadata, top_k_multiplier):
+            results.extend(chunk_results)
+        results.sort(key=lambda x: x[1])                 # stable, by score only (main.py:120)
+        results = results[:top_k]
+        if return_scores:
+            return [(cid, self._texts[cid], self._metas[cid], score) for cid, score in results]
+        return [(cid, self._texts[cid], self._metas[cid]) for cid, _ in results]
+
+    def retrieve_batch(self, texts, top_k=5, metadata=None, return_scores=False, top_k_multiplier=4):
+        """One result list PER query (the reference merges them, main.py:116-121).  One batched scan."""
+        queries = self.model.embed(texts, precision="binary")
+        out = []
+        for chunk_results in self._rank_batch(np.atleast_2d(queries), top_k, metadata, top_k_multiplier):
+            if return_scores:
+                out.append([(cid, self._texts[cid], self._metas[cid], s) for cid, s in chunk_results])
+            else:
+                out.append([(cid, self._texts[cid], self._metas[cid]) for cid, _ in chunk_results])
+        return out
+
+    def _rank_batch(self, queries, top_k, metadata, top_k_multiplier):
+        q = from_reference_encoding(queries)
+        if metadata and self.filter_mode == "reference":
+            scores, rows = self._search(q, top_k * top_k_multiplier)           # main.py:134-137
+            out = []
+            for s_row, r_row in zip(scores, rows):
+                ids = [self._ids[int(r)] for r in r_row if r != _capi.SENTINEL_ROW]
+                kept = [cid for cid in ids
+                        if all(self._metas[cid].get(k) == v for k, v in metadata.items())][:top_k]
+                # main.py:165 pairs the surviving ids with the FIRST len(ids) scores
+                out.append(list(zip(kept, [np.int64(s) for s in s_row[:len(kept)]])))
+            return out
+        mask = self._filter_mask(metadata) if metadata else None
+        scores, rows = self._search(q, top_k, mask)
+        out = []
+        for s_row, r_row in zip(scores, rows):
+            keep = r_row != _capi.SENTINEL_ROW
+            out.append([(self._ids[int(r)], np.int64(s)) for s, r in zip(s_row[keep], r_row[keep])])
+        return out
+
+    def rank_and_filter(self, query_binary_vector, top_k, metadata=None, top_k_multiplier=4):
+        """vlite/main.py:130-168 for ONE query vector: list of (chunk_id, score)."""
+        q = np.array(query_binary_vector).reshape(1, -1)
+        return self._rank_batch(q, top_k, metadata, top_k_multiplier)[0]
+
+    def update(self, id, text=None, metadata=None, vector=None):
+        """vlite/main.py:170-188 (the vector is stored under 'vector' and not searched, as there)."""
+        chunk_ids = [cid for cid in self._row_of if cid.startswith(f"{id}_")]
+        if not chunk_ids:
+            return False
+        for cid in chunk_ids:
+            if text is not None:
+                self._texts[cid] = text
+            if metadata is not None:
+                self._metas[cid].update(metadata)
+                row = self._row_of[cid]
+                if row is not None:
+                    for kv in metadata.items():
+                        if _hashable(kv[1]):
+                            self._postings.setdefault(kv, []).append(row)
+            if vector is not None:
+                self._extra.setdefault(cid, {})["vector"] = vector
+        self.save()
+        return True
+
+    def delete(self, ids):
+        """vlite/main.py:190-205: prefix match on ``{id}_``; returns the number of chunks removed."""
+        if isinstance(ids, str):
+            ids = [ids]
+        deleted, dead_rows = 0, []
+        for id in ids:
+            for cid in [c for c in self._row_of if c.startswith(f"{id}_")]:
+                row = self._row_of.pop(cid)
+                self._texts.pop(cid, None)
+                self._metas.pop(cid, None)
+                self._extra.pop(cid, None)
+                if row is not None:
+                    dead_rows.append(row)
+                    self._ids[row] = None
+                deleted += 1
+        if dead_rows:
+            self._corpus.tombstone(dead_rows)
+        if deleted > 0:
+            self.save()
+        return deleted
+
+    def get(self, ids=None, where=None):
+        """vlite/main.py:207-231."""
+        items = []
+        if ids is not None:
+            if isinstance(ids, str):
+                ids = [ids]
+            for id in ids:
+                chunks, md = [], {}
+                for cid in self._row_of:
+                    if cid.startswith(f"{id}_"):
+                        chunks.append(self._texts[cid])
+                        md.update(self._metas[cid])
+                if chunks:
+                    items.append((id, " ".join(chunks), md))
+        else:
+            for cid in self._row_of:
+                items.append((cid.split("_")[0], self._texts[cid], self._metas[cid]))
+        if where is not None:
+            items = [it for it in items if all(it[2].get(k) == v for k, v in where.items())]
+        return items
+
+    def set(self, id, text=None, metadata=None, vector=None):
+        """vlite/main.py:233-240."""
+        if any(cid.startswith(f"{id}_") for cid in self._row_of):
+            self.update(id, text, metadata, vector)
+        else:
+            self.add(text, metadata=metadata, item_id=id)
+
+    def set_batch(self, texts, embeddings, metadatas=None):
+        """vlite/main.py:243-274: precomputed embeddings, one fresh uuid per row, then save()."""
+        if not isinstance(texts, list):
+            texts = [texts]
+        if metadatas is None:
+            metadatas = [{}] * len(texts)
+        elif not isinstance(metadatas, list):
+            metadatas = [metadatas]
+        if len(texts) != len(embeddings):
+            raise ValueError("The number of texts and embeddings must be the same.")
+        if len(texts) != len(metadatas):
+            raise ValueError("The number of texts and metadatas must be the same.")
+        if len(texts):
+            first = self._append_vectors(np.asarray(embeddings))
+            for i, (text, md) in enumerate(zip(texts, metadatas)):
+                self._register(f"{uuid4()}_0", text, md, first + i)
+        self.save()
+
+    def count(self):
+        return len(self._row_of)
+
+    def save(self):
+        """vlite/main.py:280-294, written CLEAN: one row per live key in key order (the reference's
+        context manager loads the old file first and appends the whole collection to it again,
+        vlite/ctx.py:157-162; a reference reader loads a clean file identically)."""
+        cf = self.ctx.create(self.collection)
+        width = self._width or 64
+        cf.set_header(embedding_model="mixedbread-ai/mxbai-embed-large-v1", embedding_size=width,
+                      embedding_dtype=self.model.embedding_dtype, context_length=self.model.context_length)
+        keys = list(self._row_of.keys())
+        rows = [self._row_of[k] for k in keys]
+        if keys and any(r is None for r in rows):
+            raise ValueError("cannot save: some chunks have no stored vector")
+        if keys:
+            all_rows = self._corpus.read()                                   # one D2H copy
+            cf.set_embeddings_array(to_reference_encoding(all_rows[np.asarray(rows)]).astype(np.float32))
+        for k in keys:
+            cf.add_context(self._texts[k])
+            cf.add_metadata(k, self._metas[k])
+        cf.save()
+
+    def clear(self):
+        """vlite/main.py:296-300."""
+        if self._corpus is not None:
+            self._corpus.clear()
+        self._row_of.clear()
+        self._ids.clear()
+        self._texts.clear()
+        self._metas.clear()
+        self._extra.clear()
+        self._postings.clear()
+        self.ctx.delete(self.collection)
+
+    def info(self):
+        print("[VLite.info] Collection Information:")
+        print(f"[VLite.info] Items: {self.count()}")
+        print(f"[VLite.info] Collection file: {self.collection}")
+        print(f"[VLite.info] Embedding model: {self.model}")
+
+    def __repr__(self):
+        return f"VLite(collection={self.collection}, device={self.device}, model={self.model})"
+
+    def dump(self):
+        return self.index
+
+    def close(self):
+        if self._corpus is not None:
+            self._corpus.close()
+            self._corpus = None
