@@ -100,19 +100,39 @@ bool is_device_ptr(const void* p) {
     return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
 }
 
+// cudaGetDeviceProperties costs milliseconds per call: query each device once per process
+struct DevInfo {
+    std::atomic<int> state{0};  // 0 unknown, 1 ok, -1 unusable
+    int major = 0, minor = 0, sms = 0;
+};
+DevInfo g_dev[64];
+std::atomic<int> g_ndev{-1};
+
 int check_device(int device, int* sms_out) {
-    int n = 0;
-    if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) {
-        cudaGetLastError();
-        return fail(VL_ENODEV, "no CUDA device visible; vlite_b200 has no CPU fallback");
+    int n = g_ndev.load();
+    if (n < 0) {
+        if (cudaGetDeviceCount(&n) != cudaSuccess) {
+            cudaGetLastError();
+            n = 0;
+        }
+        if (n > 0) g_ndev.store(n);
     }
-    if (device < 0 || device >= n) return fail(VL_EINVAL, "device %d out of range (0..%d)", device, n - 1);
-    cudaDeviceProp prop;
-    CU(cudaGetDeviceProperties(&prop, device));
-    if (prop.major != 10)
-        return fail(VL_ENODEV, "device %d is sm_%d%d; vlite_b200 is built for sm_100a (B200) only", device,
-                    prop.major, prop.minor);
-    if (sms_out) *sms_out = prop.multiProcessorCount;
+    if (n == 0) return fail(VL_ENODEV, "no CUDA device visible; vlite_b200 has no CPU fallback");
+    if (device < 0 || device >= n || device >= 64)
+        return fail(VL_EINVAL, "device %d out of range (0..%d)", device, n - 1);
+    DevInfo& d = g_dev[device];
+    if (d.state.load() == 0) {
+        cudaDeviceProp prop;
+        CU(cudaGetDeviceProperties(&prop, device));
+        d.major = prop.major;
+        d.minor = prop.minor;
+        d.sms = prop.multiProcessorCount;
+        d.state.store(prop.major == 10 ? 1 : -1);
+    }
+    if (d.state.load() < 0)
+        return fail(VL_ENODEV, "device %d is sm_%d%d; vlite_b200 is built for sm_100a (B200) only", device, d.major,
+                    d.minor);
+    if (sms_out) *sms_out = d.sms;
     return VL_OK;
 }
 
