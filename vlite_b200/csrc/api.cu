@@ -376,6 +376,44 @@ int stage_filter(vl_corpus* c, const uint32_t* filter_any, const uint32_t** out_
     return VL_OK;
 }
 
+// Multi-level merge: <= kMergeGroup lists per warp per level.  tmp_* must hold
+// merge_tmp_lists(n_lists) lists of n_queries x k_out entries (unused when n_lists <= kMergeGroup).
+size_t merge_tmp_lists(size_t n_lists) {
+    size_t total = 0;
+    while (n_lists > (size_t)kMergeGroup) {
+        n_lists = (n_lists + kMergeGroup - 1) / kMergeGroup;
+        total += n_lists;
+    }
+    return total;
+}
+
+int merge_levels(cudaStream_t st, const uint32_t* in_s, const uint64_t* in_r, size_t n_lists, size_t s_stride,
+                 size_t r_stride, int n_queries, int k_in, int k_out, uint32_t* out_s, uint64_t* out_r,
+                 int out_stride, int out_offset, uint32_t* tmp_s, uint64_t* tmp_r) {
+    const unsigned gx = (unsigned)((n_queries + kMergeWarps - 1) / kMergeWarps);
+    const size_t dense = (size_t)n_queries * k_out;
+    while (true) {
+        const size_t groups = (n_lists + kMergeGroup - 1) / kMergeGroup;
+        if (groups <= 1) {
+            merge_topk_kernel<<<dim3(gx, 1), kMergeWarps * 32, 0, st>>>(in_s, in_r, (int)n_lists, n_queries, k_in, k_out,
+                                                                      out_s, out_r, out_stride, out_offset, s_stride,
+                                                                      r_stride, 0);
+            LAUNCHED();
+            return VL_OK;
+        }
+        merge_topk_kernel<<<dim3(gx, (unsigned)groups), kMergeWarps * 32, 0, st>>>(
+            in_s, in_r, (int)n_lists, n_queries, k_in, k_out, tmp_s, tmp_r, k_out, 0, s_stride, r_stride, dense);
+        LAUNCHED();
+        in_s = tmp_s;
+        in_r = tmp_r;
+        tmp_s += groups * dense;
+        tmp_r += groups * dense;
+        n_lists = groups;
+        k_in = k_out;
+        s_stride = r_stride = dense;
+    }
+}
+
 }  // namespace
 
 // =============================== library ===============================
@@ -738,6 +776,7 @@ extern "C" int vl_search(vl_corpus* c, const uint8_t* queries_any, int n_queries
         p.n_rows = (uint32_t)c->count;
         p.n_tiles = (uint32_t)((c->count + kTileRows - 1) / kTileRows);
         p.n_queries = n_queries;
+        p.one = 1u;
         const int n_pass = (k + kWarpListMaxK - 1) / kWarpListMaxK;
         uint32_t *cur_s = nullptr, *cur_r = nullptr;
         if (n_pass > 1) {
@@ -753,7 +792,7 @@ extern "C" int vl_search(vl_corpus* c, const uint8_t* queries_any, int n_queries
             ScanPlan plan{};
             TRY(launch_scan(c, p, n_queries, k_pass, metric, &plan, /*dry=*/true));
             const size_t n_lists = (size_t)plan.S * plan.WR;
-            const size_t n_part = n_lists * (size_t)n_queries * k_pass;
+            const size_t n_part = (n_lists + merge_tmp_lists(n_lists)) * (size_t)n_queries * k_pass;
             TRY(c->part_s.ensure(n_part * 4));
             TRY(c->part_r.ensure(n_part * 8));
             p.part_scores = static_cast<uint32_t*>(c->part_s.p);
@@ -762,11 +801,10 @@ extern "C" int vl_search(vl_corpus* c, const uint8_t* queries_any, int n_queries
             p.evict_first = (plan.T == 1 && n_pass == 1 && c->count * (uint64_t)c->w > (96ull << 20)) ? 1 : 0;
             TRY(launch_scan(c, p, n_queries, k_pass, metric, nullptr, /*dry=*/false));
             if (c->timing && pass == 0) CU(cudaEventRecord(c->ev1, st));
-            const unsigned mg = (unsigned)((n_queries + kMergeWarps - 1) / kMergeWarps);
-            merge_topk_kernel<<<mg, kMergeWarps * 32, kMergeWarps * n_lists * sizeof(uint16_t), st>>>(
-                p.part_scores, p.part_rows, (int)n_lists, n_queries, k_pass, k_pass, o_s, o_r, k,
-                pass * kWarpListMaxK, (size_t)n_queries * k_pass, (size_t)n_queries * k_pass);
-            LAUNCHED();
+            const size_t dense = (size_t)n_queries * k_pass;
+            TRY(merge_levels(st, p.part_scores, p.part_rows, n_lists, dense, dense, n_queries, k_pass, k_pass, o_s,
+                             o_r, k, pass * kWarpListMaxK, p.part_scores + n_lists * dense,
+                             p.part_rows + n_lists * dense));
             if (pass + 1 < n_pass) {
                 cursor_update_kernel<<<(n_queries + 127) / 128, 128, 0, st>>>(
                     o_s, o_r, n_queries, k, pass * kWarpListMaxK + k_pass - 1, c->base_row, cur_s, cur_r);
@@ -822,17 +860,21 @@ extern "C" int vl_merge_topk(int device, void* cuda_stream, const uint32_t* scor
         return fail(VL_EINVAL, "bad merge shape");
     TRY(check_device(device, nullptr));
     DeviceGuard g(device);
-    const size_t smem = (size_t)kMergeWarps * n_lists * sizeof(uint16_t);
-    if (smem > 200 * 1024) return fail(VL_EINVAL, "too many lists (%d)", n_lists);
-    if (smem > 48 * 1024)
-        CU(cudaFuncSetAttribute(merge_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const unsigned mg = (unsigned)((n_queries + kMergeWarps - 1) / kMergeWarps);
-    merge_topk_kernel<<<mg, kMergeWarps * 32, smem, static_cast<cudaStream_t>(cuda_stream)>>>(
-        scores_dev, rows_dev, n_lists, n_queries, k_in, k_out, out_score_dev, out_row_dev, k_out, 0,
-        score_list_stride ? (size_t)score_list_stride : (size_t)n_queries * k_in,
-        row_list_stride ? (size_t)row_list_stride : (size_t)n_queries * k_in);
-    LAUNCHED();
-    return VL_OK;
+    cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+    const size_t ss = score_list_stride ? (size_t)score_list_stride : (size_t)n_queries * k_in;
+    const size_t rs = row_list_stride ? (size_t)row_list_stride : (size_t)n_queries * k_in;
+    const size_t tmp_lists = merge_tmp_lists((size_t)n_lists);
+    uint32_t* tmp_s = nullptr;
+    uint64_t* tmp_r = nullptr;
+    if (tmp_lists) {  // only beyond 128 lists; stream-ordered scratch
+        const size_t n = tmp_lists * (size_t)n_queries * k_out;
+        CU(cudaMallocAsync(reinterpret_cast<void**>(&tmp_r), n * 12, st));
+        tmp_s = reinterpret_cast<uint32_t*>(tmp_r + n);
+    }
+    int rc = merge_levels(st, scores_dev, rows_dev, (size_t)n_lists, ss, rs, n_queries, k_in, k_out, out_score_dev,
+                          out_row_dev, k_out, 0, tmp_s, tmp_r);
+    if (tmp_r) cudaFreeAsync(tmp_r, st);
+    return rc;
 }
 
 // =============================== rescore ===============================

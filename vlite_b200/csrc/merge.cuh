@@ -5,68 +5,93 @@
 // Output: per query the k_out smallest by (score, global row) -- the canonical order that
 // stands in for the reference's torch.topk (vlite/model.py:85).
 //
-// One warp per query: lane l owns lists l, l+32, ...; every round each lane offers the best head
-// among its lists, a shuffle min-reduction on the 96-bit key (score, row) picks the winner, the
-// winning lane advances that list's head.  No atomics, so the result is deterministic.
+// One warp merges up to 128 lists of one query: list heads live in registers (4 per lane), every
+// round the lane's best head enters a shuffle min-reduction on the 96-bit key (score, row), the
+// owning lane advances that list with one load.  More than 128 lists (Q <= 8 produces one list
+// per warp of every CTA: up to 2368) are merged level by level: group g of a level writes its
+// k_out winners as list g of the next level.  No atomics, so the result is deterministic.
 #pragma once
 #include "common.cuh"
 
 namespace vl {
 
 constexpr int kMergeWarps = 4;
+constexpr int kMergeListsPerLane = 4;
+constexpr int kMergeGroup = 32 * kMergeListsPerLane;  // lists one warp merges per level
 
 __device__ __forceinline__ bool key_less(uint32_t s1, uint64_t r1, uint32_t s2, uint64_t r2) {
     return (s1 < s2) || (s1 == s2 && r1 < r2);
 }
 
+// grid = (ceil(Q / kMergeWarps), n_groups)
 __global__ void __launch_bounds__(kMergeWarps * 32)
 merge_topk_kernel(const uint32_t* __restrict__ scores, const uint64_t* __restrict__ rows, int n_lists,
                   int n_queries, int k_in, int k_out, uint32_t* __restrict__ out_scores,
                   uint64_t* __restrict__ out_rows, int out_stride, int out_offset, size_t score_list_stride,
-                  size_t row_list_stride) {
-    extern __shared__ uint16_t s_heads[];  // [kMergeWarps][n_lists]
+                  size_t row_list_stride, size_t out_group_stride) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int q = blockIdx.x * kMergeWarps + warp;
     if (q >= n_queries) return;
-    uint16_t* heads = s_heads + (size_t)warp * n_lists;
-    for (int l = lane; l < n_lists; l += 32) heads[l] = 0;
-    __syncwarp();
+    const int group = blockIdx.y;
+    const int list0 = group * kMergeGroup;
 
-    for (int o = 0; o < k_out; ++o) {
-        uint32_t bs = kSentinelScore;
-        uint64_t br = kSentinelRow;
-        int bl = -1;
-        for (int l = lane; l < n_lists; l += 32) {
-            const int h = heads[l];
-            if (h < k_in) {
-                const size_t idx = (size_t)q * k_in + h;
-                const uint64_t r = rows[(size_t)l * row_list_stride + idx];
-                const uint32_t s = scores[(size_t)l * score_list_stride + idx];
-                if (r != kSentinelRow && key_less(s, r, bs, br)) {
-                    bs = s;
-                    br = r;
-                    bl = l;
-                }
-            }
+    uint32_t cs[kMergeListsPerLane];
+    uint64_t cr[kMergeListsPerLane];
+    int hd[kMergeListsPerLane];
+    auto load = [&](int j) {
+        const int l = list0 + j * 32 + lane;
+        cs[j] = kSentinelScore;
+        cr[j] = kSentinelRow;
+        if (l < n_lists && hd[j] < k_in) {
+            const size_t idx = (size_t)q * k_in + hd[j];
+            cr[j] = rows[(size_t)l * row_list_stride + idx];
+            cs[j] = scores[(size_t)l * score_list_stride + idx];
+            if (cr[j] == kSentinelRow) cs[j] = kSentinelScore;
         }
+    };
+#pragma unroll
+    for (int j = 0; j < kMergeListsPerLane; ++j) {
+        hd[j] = 0;
+        load(j);
+    }
+    uint32_t* os = out_scores + (size_t)group * out_group_stride + (size_t)q * out_stride + out_offset;
+    uint64_t* orow = out_rows + (size_t)group * out_group_stride + (size_t)q * out_stride + out_offset;
+    for (int o = 0; o < k_out; ++o) {
+        uint32_t bs = cs[0];
+        uint64_t br = cr[0];
+        int bj = 0;
+#pragma unroll
+        for (int j = 1; j < kMergeListsPerLane; ++j)
+            if (key_less(cs[j], cr[j], bs, br)) {
+                bs = cs[j];
+                br = cr[j];
+                bj = j;
+            }
+        int bl = lane;
 #pragma unroll
         for (int off = 16; off > 0; off >>= 1) {
-            const uint32_t os = __shfl_xor_sync(kFullMask, bs, off);
-            const uint64_t orow = __shfl_xor_sync(kFullMask, br, off);
-            const int ol = __shfl_xor_sync(kFullMask, bl, off);
-            if (key_less(os, orow, bs, br)) {
-                bs = os;
-                br = orow;
-                bl = ol;
+            const uint32_t s2 = __shfl_xor_sync(kFullMask, bs, off);
+            const uint64_t r2 = __shfl_xor_sync(kFullMask, br, off);
+            const int l2 = __shfl_xor_sync(kFullMask, bl, off);
+            if (key_less(s2, r2, bs, br) || (s2 == bs && r2 == br && l2 < bl)) {
+                bs = s2;
+                br = r2;
+                bl = l2;
             }
         }
-        // all lanes now agree on (bs, br, bl); rows are unique so there is exactly one owner
-        if (bl >= 0 && (bl & 31) == lane) heads[bl] += 1;
-        if (lane == 0) {
-            out_scores[(size_t)q * out_stride + out_offset + o] = bs;
-            out_rows[(size_t)q * out_stride + out_offset + o] = br;
+        // (bs, br, bl) now agree on every lane; rows are unique, so a real key has one owner
+        if (bl == lane && br != kSentinelRow) {
+#pragma unroll
+            for (int j = 0; j < kMergeListsPerLane; ++j)
+                if (j == bj) {
+                    hd[j] += 1;
+                    load(j);
+                }
         }
-        __syncwarp();
+        if (lane == 0) {
+            os[o] = bs;
+            orow[o] = br;
+        }
     }
 }
 

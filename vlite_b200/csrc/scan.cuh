@@ -54,6 +54,7 @@ struct ScanParams {
     // strictly greater than (cur_score[q], cur_row[q]) are eligible
     const uint32_t* cur_score;
     const uint32_t* cur_row;
+    uint32_t one;  // == 1, opaque to ptxas: keeps "acc += popc" on IMAD (FMA pipe) instead of IADD3 (ALU pipe)
 };
 
 // Insert (s, idx) into the warp's sorted list (ascending score; an equal score goes after the
@@ -134,7 +135,7 @@ __device__ __forceinline__ uint32_t mad_u32(uint32_t a, uint32_t b, uint32_t c) 
 }
 template <int METRIC>
 __device__ __forceinline__ uint32_t score_chunk_pair(const uint4& ra, const uint4& rb, const uint4& qa,
-                                                     const uint4& qb, uint32_t acc) {
+                                                     const uint4& qb, uint32_t acc, uint32_t one) {
     if constexpr (METRIC == kHamming) {
         const uint32_t x0 = ra.x ^ qa.x, x1 = ra.y ^ qa.y, x2 = ra.z ^ qa.z, x3 = ra.w ^ qa.w;
         const uint32_t x4 = rb.x ^ qb.x, x5 = rb.y ^ qb.y, x6 = rb.z ^ qb.z, x7 = rb.w ^ qb.w;
@@ -142,7 +143,9 @@ __device__ __forceinline__ uint32_t score_chunk_pair(const uint4& ra, const uint
         const uint32_t s2 = xor3(x3, x4, x5), c2 = maj3(x3, x4, x5);
         const uint32_t s3 = xor3(s1, s2, x6), c3 = maj3(s1, s2, x6);
         const uint32_t tw = xor3(c1, c2, c3), fo = maj3(c1, c2, c3);
-        acc += __popc(s3) + __popc(x7);
+        // all four weighted adds as IMAD: the FMA pipe idles while the ALU pipe (LOP3) is the bound
+        acc = mad_u32(__popc(s3), one, acc);
+        acc = mad_u32(__popc(x7), one, acc);
         acc = mad_u32(__popc(tw), 2u, acc);
         acc = mad_u32(__popc(fo), 4u, acc);
         return acc;
@@ -255,6 +258,7 @@ __global__ void __launch_bounds__(kScanThreads, 2) scan_topk_kernel(const ScanPa
     const uint32_t tiles_saddr = smem_u32(s_tiles);
     const bool has_filter = p.filter != nullptr;
     const bool has_cursor = p.cur_score != nullptr;
+    const uint32_t one = p.one;
 
     for (uint32_t i = 0; i < my_tiles; ++i) {
         const uint32_t t = tile_begin + i;
@@ -308,7 +312,7 @@ __global__ void __launch_bounds__(kScanThreads, 2) scan_topk_kernel(const ScanPa
                     const uint4 qb = lds128(q_saddr + (uint32_t)(c * W) + coff_b);
 #pragma unroll
                     for (int r = 0; r < R; ++r)
-                        acc[r][c] = score_chunk_pair<METRIC>(ra[r], rb[r], qa, qb, acc[r][c]);
+                        acc[r][c] = score_chunk_pair<METRIC>(ra[r], rb[r], qa, qb, acc[r][c], one);
                 }
             }
 
