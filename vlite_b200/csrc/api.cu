@@ -301,7 +301,9 @@ int launch_scan_cfg(vl_corpus* c, ScanParams& p, int n_queries, int k, ScanPlan*
             s = std::min(s, max_splits);
             const long ctas = s * T;
             const double eff = (double)ctas / ((double)((ctas + slots - 1) / slots) * slots);
-            if (eff > best_eff + 0.02) {
+            // an extra wave re-pays per-CTA prologue, list write-out and merge work: take it only
+            // for a clear gain in SM fill (measured: 1 wave of 288 CTAs beats 2 full waves of 592)
+            if (eff > best_eff + 0.08) {
                 best_eff = eff;
                 S = s;
             }
@@ -779,9 +781,10 @@ extern "C" int vl_search(vl_corpus* c, const uint8_t* queries_any, int n_queries
         p.one = 1u;
         const int n_pass = (k + kWarpListMaxK - 1) / kWarpListMaxK;
         uint32_t *cur_s = nullptr, *cur_r = nullptr;
+        TRY(c->cand_buf.ensure((size_t)n_queries * 12));
+        p.tau = static_cast<uint32_t*>(c->cand_buf.p);
         if (n_pass > 1) {
-            TRY(c->cand_buf.ensure((size_t)n_queries * 8));
-            cur_s = static_cast<uint32_t*>(c->cand_buf.p);
+            cur_s = p.tau + n_queries;
             cur_r = cur_s + n_queries;
         }
         for (int pass = 0; pass < n_pass; ++pass) {
@@ -799,6 +802,7 @@ extern "C" int vl_search(vl_corpus* c, const uint8_t* queries_any, int n_queries
             p.part_rows = static_cast<uint64_t*>(c->part_r.p);
             // corpus read once and far larger than L2 -> stream it; otherwise let L2 keep it
             p.evict_first = (plan.T == 1 && n_pass == 1 && c->count * (uint64_t)c->w > (96ull << 20)) ? 1 : 0;
+            CU(cudaMemsetAsync(p.tau, 0xFF, (size_t)n_queries * 4, st));
             TRY(launch_scan(c, p, n_queries, k_pass, metric, nullptr, /*dry=*/false));
             if (c->timing && pass == 0) CU(cudaEventRecord(c->ev1, st));
             const size_t dense = (size_t)n_queries * k_pass;

@@ -54,6 +54,10 @@ struct ScanParams {
     // strictly greater than (cur_score[q], cur_row[q]) are eligible
     const uint32_t* cur_score;
     const uint32_t* cur_row;
+    // per-query upper bound on the final k-th best score, shared by every CTA (init 0xFFFFFFFF).
+    // A full list publishes its k-th score with atomicMin; rows scoring above the bound cannot be
+    // in the final top-k, so dropping them early changes no result (only prunes insert work).
+    uint32_t* tau;
     uint32_t one;  // == 1, opaque to ptxas: keeps "acc += popc" on IMAD (FMA pipe) instead of IADD3 (ALU pipe)
 };
 
@@ -260,6 +264,13 @@ __global__ void __launch_bounds__(kScanThreads, 2) scan_topk_kernel(const ScanPa
     const bool has_cursor = p.cur_score != nullptr;
     const uint32_t one = p.one;
 
+    // Q <= 2 is HBM-bound with idle integer pipes: pruning buys nothing there, skip the traffic
+    constexpr bool USE_TAU = QT > 2;
+    const bool tau_mine = USE_TAU && lane < C && (qtile * QT + wq * C + lane) < p.n_queries;
+    const uint32_t* tau_ptr = p.tau + (qtile * QT + wq * C + (tau_mine ? lane : 0));
+    uint32_t tau_pref = kSentinelScore;
+    bool dirty = false;
+
     for (uint32_t i = 0; i < my_tiles; ++i) {
         const uint32_t t = tile_begin + i;
         const int s = i % stages;
@@ -272,6 +283,14 @@ __global__ void __launch_bounds__(kScanThreads, 2) scan_topk_kernel(const ScanPa
                 if (lane == 0) issue_tile(nxt);
                 __syncwarp();
             }
+        }
+        // refresh the effective thresholds: min(own k-th best, device-wide bound + 1).  The bound
+        // was fetched one tile ago, so the L2 round trip hides behind that tile's work.
+        if constexpr (USE_TAU) {
+            const uint32_t g = (tau_pref == kSentinelScore) ? tau_pref : tau_pref + 1;
+#pragma unroll
+            for (int c = 0; c < C; ++c) thr[c] = min(thr[c], __shfl_sync(kFullMask, g, c));
+            if (tau_mine) tau_pref = __ldcg(tau_ptr);
         }
         mbar_wait(&s_full[s], (i / stages) & 1);
         const uint32_t* m = s_masks + s * 2 * kMaskWordsPerTile;
@@ -363,12 +382,22 @@ __global__ void __launch_bounds__(kScanThreads, 2) scan_topk_kernel(const ScanPa
                     if (lane == 0) s_thr[warp * C + c] = tc;
                     __syncwarp();
                 }
+                dirty = true;
 #pragma unroll
-                for (int c = 0; c < C; ++c) thr[c] = s_thr[warp * C + c];
+                for (int c = 0; c < C; ++c) thr[c] = min(thr[c], s_thr[warp * C + c]);
             }
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(&s_empty[s]);
+        // publish improved k-th scores at most once per tile, and only when they beat the bound
+        // this warp last saw (one hot address per query: keep the atomics rare)
+        if (dirty) {
+            dirty = false;
+            if (tau_mine) {
+                const uint32_t mine = s_thr[warp * C + lane];
+                if (mine < tau_pref) atomicMin(const_cast<uint32_t*>(tau_ptr), mine);
+            }
+        }
     }
 
     // -------- write this warp's lists to the partial buffer --------
