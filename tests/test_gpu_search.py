@@ -71,6 +71,30 @@ def test_large_k_multipass(gpu, k):
         _check(c, corpus, queries, k, HAMMING)
 
 
+@pytest.mark.parametrize("k", [300, 1000, 2048])
+@pytest.mark.parametrize("period", [0, 700])
+def test_large_k_sampled_path_and_fallback(gpu, k, period):
+    """k > 256 on a corpus larger than the candidate buffer: sampled threshold + collect + select.
+    period=700 makes every score value shared by ~290 rows, so buffers overflow and the exact
+    multi-pass fallback must answer -- the result is the same either way."""
+    n = 200_000
+    corpus = synth.corpus_rows(31, 0, n, 128, period)
+    queries = synth.uniform_queries(32, 6, 128)
+    queries[0] = corpus[777]
+    valid = synth.filter_valid(2, 0, n, 0.5)
+    with gpu.Corpus(128) as c:
+        c.append(corpus)
+        _check(c, corpus, queries, k, HAMMING)
+        _check(c, corpus, queries[:2], k, XORSUM)
+        _check(c, corpus, queries[:3], k, HAMMING, synth.pack_mask(valid))
+        fast = c.search(queries, k, HAMMING)
+        c.set_tuning(stages=-1)                     # force the multi-pass cursor path
+        slow = c.search(queries, k, HAMMING)
+        c.set_tuning()
+    np.testing.assert_array_equal(fast[0], slow[0])
+    np.testing.assert_array_equal(fast[1], slow[1])
+
+
 def test_duplicates_tie_break(gpu):
     # distribution D: every score value is shared by n/period rows
     n, period = 30000, 97

@@ -14,6 +14,7 @@
 #include <vector>
 
 #include "../../include/vlite_b200.h"
+#include "largek.cuh"
 #include "merge.cuh"
 #include "repack.cuh"
 #include "rescore.cuh"
@@ -155,7 +156,8 @@ struct vl_corpus {
     uint64_t count = 0;
     uint64_t live_count = 0;
     uint64_t base_row = 0;
-    DevBuf q_buf, filt_buf, part_s, part_r, out_s, out_r, stage[2], rows_buf, cand_buf, misc;
+    DevBuf q_buf, filt_buf, part_s, part_r, out_s, out_r, stage[2], rows_buf, cand_buf, misc, lk_keys, lk_misc;
+    int force_multipass = 0;  // tuning/testing: disable the sampled large-k path
     void* pinned[2] = {nullptr, nullptr};
     size_t pinned_bytes = 0;
     cudaEvent_t stage_ev[2] = {nullptr, nullptr};
@@ -416,6 +418,112 @@ int merge_levels(cudaStream_t st, const uint32_t* in_s, const uint64_t* in_r, si
     }
 }
 
+// k <= 128: one scan + merge.  Larger k: ceil(k/128) passes, each returning the next 128 keys after
+// a per-query cursor (exact and deterministic for any tie pattern).  `p` arrives with the corpus,
+// queries and masks filled in.
+int search_lists(vl_corpus* c, ScanParams p, int n_queries, int k, int metric, uint32_t* o_s, uint64_t* o_r,
+                 int out_stride = 0) {
+    cudaStream_t st = c->stream;
+    if (out_stride == 0) out_stride = k;
+    const int n_pass = (k + kWarpListMaxK - 1) / kWarpListMaxK;
+    TRY(c->cand_buf.ensure((size_t)n_queries * 12));
+    p.tau = static_cast<uint32_t*>(c->cand_buf.p);
+    uint32_t* cur_s = p.tau + n_queries;
+    uint32_t* cur_r = cur_s + n_queries;
+    for (int pass = 0; pass < n_pass; ++pass) {
+        const int k_pass = std::min(kWarpListMaxK, k - pass * kWarpListMaxK);
+        p.k = k_pass;
+        p.cur_score = pass ? cur_s : nullptr;
+        p.cur_row = pass ? cur_r : nullptr;
+        ScanPlan plan{};
+        TRY(launch_scan(c, p, n_queries, k_pass, metric, &plan, /*dry=*/true));
+        const size_t n_lists = (size_t)plan.S * plan.WR;
+        const size_t dense = (size_t)n_queries * k_pass;
+        const size_t n_part = (n_lists + merge_tmp_lists(n_lists)) * dense;
+        TRY(c->part_s.ensure(n_part * 4));
+        TRY(c->part_r.ensure(n_part * 8));
+        p.part_scores = static_cast<uint32_t*>(c->part_s.p);
+        p.part_rows = static_cast<uint64_t*>(c->part_r.p);
+        // corpus read once and far larger than L2 -> stream it; otherwise let L2 keep it
+        p.evict_first = (plan.T == 1 && n_pass == 1 && p.tile_stride == 1 &&
+                         c->count * (uint64_t)c->w > (96ull << 20)) ? 1 : 0;
+        CU(cudaMemsetAsync(p.tau, 0xFF, (size_t)n_queries * 4, st));
+        TRY(launch_scan(c, p, n_queries, k_pass, metric, nullptr, /*dry=*/false));
+        if (c->timing && pass == 0 && p.tile_stride == 1) CU(cudaEventRecord(c->ev1, st));
+        TRY(merge_levels(st, p.part_scores, p.part_rows, n_lists, dense, dense, n_queries, k_pass, k_pass, o_s, o_r,
+                         out_stride, pass * kWarpListMaxK, p.part_scores + n_lists * dense,
+                         p.part_rows + n_lists * dense));
+        if (pass + 1 < n_pass) {
+            cursor_update_kernel<<<(n_queries + 127) / 128, 128, 0, st>>>(
+                o_s, o_r, n_queries, out_stride, pass * kWarpListMaxK + k_pass - 1, c->base_row, cur_s, cur_r);
+            LAUNCHED();
+        }
+    }
+    return VL_OK;
+}
+
+// k > 256: sampled threshold + collect + select (largek.cuh).  *done = false asks the caller to run
+// the exact multi-pass path instead (tiny corpus, or a buffer overflowed / came up short).
+int search_large_k(vl_corpus* c, ScanParams p, int n_queries, int k, int metric, uint32_t* o_s, uint64_t* o_r,
+                   bool* done) {
+    *done = false;
+    cudaStream_t st = c->stream;
+    uint32_t cap = 8192;
+    while (cap < 6u * (uint32_t)k) cap <<= 1;                       // expected ~3k candidates per query
+    const size_t key_bytes = (size_t)n_queries * cap * 8;
+    if (key_bytes > (8ull << 30)) return VL_OK;                      // would need > 8 GB of scratch
+    const uint32_t stride = std::max<uint32_t>(1, (3u * (uint32_t)k) / kLargeKSample);
+    const uint32_t visited = (p.n_tiles + stride - 1) / stride;
+    TRY(c->lk_keys.ensure(key_bytes));
+    TRY(c->lk_misc.ensure((size_t)n_queries * (4 + 4 + kLargeKSample * 12) + 64));
+    uint32_t* thr = static_cast<uint32_t*>(c->lk_misc.p);
+    uint32_t* cnt = thr + n_queries;
+    uint64_t* smp_r = reinterpret_cast<uint64_t*>(cnt + n_queries);  // 8*Q bytes in: 8-byte aligned
+    uint32_t* smp_s = reinterpret_cast<uint32_t*>(smp_r + (size_t)n_queries * kLargeKSample);
+    int* flags = c->d_err;
+    if (c->count <= cap) {
+        // the whole shard fits a buffer: no sampling, collect every eligible row
+        CU(cudaMemsetAsync(thr, 0xFF, (size_t)n_queries * 4, st));
+    } else {
+        ScanParams ps = p;
+        ps.tile_stride = stride;
+        ps.n_tiles = visited;
+        TRY(search_lists(c, ps, n_queries, kLargeKSample, metric, smp_s, smp_r));
+        extract_thr_kernel<<<(n_queries + 127) / 128, 128, 0, st>>>(smp_s, smp_r, n_queries, kLargeKSample, thr);
+        LAUNCHED();
+    }
+    CU(cudaMemsetAsync(cnt, 0, (size_t)n_queries * 4, st));
+    ScanParams pc = p;
+    pc.k = 1;
+    pc.collect_thr = thr;
+    pc.collect_keys = static_cast<unsigned long long*>(c->lk_keys.p);
+    pc.collect_count = cnt;
+    pc.collect_cap = cap;
+    TRY(c->cand_buf.ensure((size_t)n_queries * 12));
+    pc.tau = static_cast<uint32_t*>(c->cand_buf.p);
+    TRY(c->part_s.ensure(4096));
+    TRY(c->part_r.ensure(4096));
+    pc.part_scores = static_cast<uint32_t*>(c->part_s.p);
+    pc.part_rows = static_cast<uint64_t*>(c->part_r.p);
+    pc.evict_first = 0;
+    TRY(launch_scan(c, pc, n_queries, 1, metric, nullptr, /*dry=*/false));
+    if (c->timing) CU(cudaEventRecord(c->ev1, st));
+    const size_t smem = (size_t)cap * 8;
+    CU(cudaFuncSetAttribute(collect_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    collect_select_kernel<<<n_queries, kSelectThreads, smem, st>>>(pc.collect_keys, cnt, thr, cap, k, c->base_row, o_s,
+                                                                o_r, flags);
+    LAUNCHED();
+    int h = 0;
+    CU(cudaMemcpyAsync(&h, flags, sizeof h, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    if (h) {
+        CU(cudaMemsetAsync(flags, 0, sizeof(int), st));
+        return VL_OK;  // overflow / shortfall: let the exact multi-pass path answer
+    }
+    *done = true;
+    return VL_OK;
+}
+
 }  // namespace
 
 // =============================== library ===============================
@@ -476,7 +584,7 @@ extern "C" int vl_corpus_destroy(vl_corpus* c) {
     if (c->rows) cudaFree(c->rows);
     if (c->live) cudaFree(c->live);
     for (DevBuf* b : {&c->q_buf, &c->filt_buf, &c->part_s, &c->part_r, &c->out_s, &c->out_r, &c->stage[0],
-                      &c->stage[1], &c->rows_buf, &c->cand_buf, &c->misc})
+                      &c->stage[1], &c->rows_buf, &c->cand_buf, &c->misc, &c->lk_keys, &c->lk_misc})
         b->release();
     for (int i = 0; i < 2; ++i) {
         if (c->pinned[i]) cudaFreeHost(c->pinned[i]);
@@ -766,56 +874,23 @@ extern "C" int vl_search(vl_corpus* c, const uint8_t* queries_any, int n_queries
     }
 
     if (c->timing) CU(cudaEventRecord(c->ev0, st));
-    {
-        // k <= 128: one scan + merge.  Larger k: ceil(k/128) passes, each returning the next 128
-        // keys after a per-query cursor (exact and deterministic for any tie pattern).
-        ScanParams p{};
-        p.rows = c->rows;
-        p.live = c->live;
-        p.filter = filt;
-        p.queries = q_ptr;
-        p.base_row = c->base_row;
-        p.n_rows = (uint32_t)c->count;
-        p.n_tiles = (uint32_t)((c->count + kTileRows - 1) / kTileRows);
-        p.n_queries = n_queries;
-        p.one = 1u;
-        const int n_pass = (k + kWarpListMaxK - 1) / kWarpListMaxK;
-        uint32_t *cur_s = nullptr, *cur_r = nullptr;
-        TRY(c->cand_buf.ensure((size_t)n_queries * 12));
-        p.tau = static_cast<uint32_t*>(c->cand_buf.p);
-        if (n_pass > 1) {
-            cur_s = p.tau + n_queries;
-            cur_r = cur_s + n_queries;
-        }
-        for (int pass = 0; pass < n_pass; ++pass) {
-            const int k_pass = std::min(kWarpListMaxK, k - pass * kWarpListMaxK);
-            p.k = k_pass;
-            p.cur_score = pass ? cur_s : nullptr;
-            p.cur_row = pass ? cur_r : nullptr;
-            ScanPlan plan{};
-            TRY(launch_scan(c, p, n_queries, k_pass, metric, &plan, /*dry=*/true));
-            const size_t n_lists = (size_t)plan.S * plan.WR;
-            const size_t n_part = (n_lists + merge_tmp_lists(n_lists)) * (size_t)n_queries * k_pass;
-            TRY(c->part_s.ensure(n_part * 4));
-            TRY(c->part_r.ensure(n_part * 8));
-            p.part_scores = static_cast<uint32_t*>(c->part_s.p);
-            p.part_rows = static_cast<uint64_t*>(c->part_r.p);
-            // corpus read once and far larger than L2 -> stream it; otherwise let L2 keep it
-            p.evict_first = (plan.T == 1 && n_pass == 1 && c->count * (uint64_t)c->w > (96ull << 20)) ? 1 : 0;
-            CU(cudaMemsetAsync(p.tau, 0xFF, (size_t)n_queries * 4, st));
-            TRY(launch_scan(c, p, n_queries, k_pass, metric, nullptr, /*dry=*/false));
-            if (c->timing && pass == 0) CU(cudaEventRecord(c->ev1, st));
-            const size_t dense = (size_t)n_queries * k_pass;
-            TRY(merge_levels(st, p.part_scores, p.part_rows, n_lists, dense, dense, n_queries, k_pass, k_pass, o_s,
-                             o_r, k, pass * kWarpListMaxK, p.part_scores + n_lists * dense,
-                             p.part_rows + n_lists * dense));
-            if (pass + 1 < n_pass) {
-                cursor_update_kernel<<<(n_queries + 127) / 128, 128, 0, st>>>(
-                    o_s, o_r, n_queries, k, pass * kWarpListMaxK + k_pass - 1, c->base_row, cur_s, cur_r);
-                LAUNCHED();
-            }
-        }
+    ScanParams p{};
+    p.rows = c->rows;
+    p.live = c->live;
+    p.filter = filt;
+    p.queries = q_ptr;
+    p.base_row = c->base_row;
+    p.n_rows = (uint32_t)c->count;
+    p.n_tiles = (uint32_t)((c->count + kTileRows - 1) / kTileRows);
+    p.n_queries = n_queries;
+    p.tile_stride = 1;
+    p.one = 1u;
+    bool done = false;
+    if (k > 2 * kWarpListMaxK && !c->force_multipass) {
+        int rc = search_large_k(c, p, n_queries, k, metric, o_s, o_r, &done);
+        if (rc != VL_OK) return rc;
     }
+    if (!done) TRY(search_lists(c, p, n_queries, k, metric, o_s, o_r));
     if (c->timing) {
         CU(cudaEventRecord(c->ev2, st));
         c->timed = true;
@@ -1073,6 +1148,8 @@ extern "C" int vl_last_timing(vl_corpus* c, float* total_ms, float* scan_ms) {
 
 extern "C" int vl_set_tuning(vl_corpus* c, int row_splits, int stages) {
     if (!c) return fail(VL_EINVAL, "corpus is NULL");
+    c->force_multipass = stages < 0 ? 1 : 0;  // stages = -1: force the exact multi-pass path for large k
+    if (stages < 0) stages = 0;
     c->tune_splits = row_splits;
     c->tune_stages = stages;
     return VL_OK;

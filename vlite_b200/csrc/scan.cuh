@@ -58,6 +58,15 @@ struct ScanParams {
     // A full list publishes its k-th score with atomicMin; rows scoring above the bound cannot be
     // in the final top-k, so dropping them early changes no result (only prunes insert work).
     uint32_t* tau;
+    // tile sampling (large-k threshold estimate): the kernel visits tiles 0, stride, 2*stride, ...
+    // n_tiles counts the VISITED tiles; 1 = every tile
+    uint32_t tile_stride;
+    // collect mode (large k): instead of keeping k-lists, every eligible row with score <= fixed
+    // per-query threshold collect_thr[q] is appended to collect_keys[q][..] (score << 32 | local row)
+    const uint32_t* collect_thr;
+    unsigned long long* collect_keys;
+    uint32_t* collect_count;
+    uint32_t collect_cap;
     uint32_t one;  // == 1, opaque to ptxas: keeps "acc += popc" on IMAD (FMA pipe) instead of IADD3 (ALU pipe)
 };
 
@@ -220,7 +229,7 @@ __global__ void __launch_bounds__(kScanThreads, 2) scan_topk_kernel(const ScanPa
     const uint64_t policy = p.evict_first ? l2_policy_evict_first() : l2_policy_evict_last();
     auto issue_tile = [&](uint32_t i) {
         const int s = i % stages;
-        const uint32_t t = tile_begin + i;
+        const uint32_t t = (tile_begin + i) * p.tile_stride;
         const uint32_t row0 = t * kTileRows;
         const uint32_t rows_here = min((uint32_t)kTileRows, p.n_rows - row0);
         const uint32_t mask_bytes = kMaskWordsPerTile * 4;
@@ -253,6 +262,20 @@ __global__ void __launch_bounds__(kScanThreads, 2) scan_topk_kernel(const ScanPa
     for (int c = 0; c < C; ++c) thr[c] = (qtile * QT + wq * C + c < p.n_queries) ? kSentinelScore : 0u;
     if (lane < C) s_thr[warp * C + lane] = (qtile * QT + wq * C + lane < p.n_queries) ? kSentinelScore : 0u;
     __syncwarp();
+    const bool collect = p.collect_thr != nullptr;
+    if (collect) {
+        // fixed thresholds: "score <= thr" is tested as "score < thr + 1" (thr + 1 saturates)
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+            const int qg = qtile * QT + wq * C + c;
+            uint32_t v = 0;
+            if (qg < p.n_queries) {
+                v = p.collect_thr[qg];
+                v = (v == kSentinelScore) ? v : v + 1;
+            }
+            thr[c] = v;
+        }
+    }
 
     // rotated chunk order: conflict-free 128-bit LDS on a linear (unswizzled) tile
     constexpr int LANES_PER_128B = (W >= 128) ? 1 : 128 / W;
@@ -266,13 +289,13 @@ __global__ void __launch_bounds__(kScanThreads, 2) scan_topk_kernel(const ScanPa
 
     // Q <= 2 is HBM-bound with idle integer pipes: pruning buys nothing there, skip the traffic
     constexpr bool USE_TAU = QT > 2;
-    const bool tau_mine = USE_TAU && lane < C && (qtile * QT + wq * C + lane) < p.n_queries;
+    const bool tau_mine = USE_TAU && p.collect_thr == nullptr && lane < C && (qtile * QT + wq * C + lane) < p.n_queries;
     const uint32_t* tau_ptr = p.tau + (qtile * QT + wq * C + (tau_mine ? lane : 0));
     uint32_t tau_pref = kSentinelScore;
     bool dirty = false;
 
     for (uint32_t i = 0; i < my_tiles; ++i) {
-        const uint32_t t = tile_begin + i;
+        const uint32_t t = (tile_begin + i) * p.tile_stride;
         const int s = i % stages;
         // warp 0 refills the stage every warp released one tile ago (one tile of slack keeps it
         // from waiting on the slowest warp)
@@ -362,8 +385,30 @@ __global__ void __launch_bounds__(kScanThreads, 2) scan_topk_kernel(const ScanPa
                     for (int cc = 0; cc < C; ++cc)
 #pragma unroll
                         for (int rr = 0; rr < R; ++rr) v = (b == cc * R + rr) ? acc[rr][cc] : v;
-                    uint32_t tc = s_thr[warp * C + c];
                     unsigned mm = __ballot_sync(kFullMask, (hm >> b) & 1u);
+                    if (collect) {
+                        // append every flagged row: one atomicAdd per (warp, query, row group)
+                        const int qg = qtile * QT + wq * C + c;
+                        bool mine = (mm >> lane) & 1u;
+                        const uint32_t idx = row_base + (uint32_t)(r * 32 + lane);
+                        if (mine && has_cursor) {
+                            const uint32_t cs = s_cursor[2 * (wq * C + c)];
+                            const uint32_t cr = s_cursor[2 * (wq * C + c) + 1];
+                            mine = (v > cs) || (v == cs && idx > cr);
+                        }
+                        const unsigned sel = __ballot_sync(kFullMask, mine);
+                        if (sel) {
+                            uint32_t base = 0;
+                            if (lane == __ffs(sel) - 1) base = atomicAdd(p.collect_count + qg, (uint32_t)__popc(sel));
+                            base = __shfl_sync(kFullMask, base, __ffs(sel) - 1);
+                            const uint32_t slot = base + (uint32_t)__popc(sel & ((1u << lane) - 1));
+                            if (mine && slot < p.collect_cap)
+                                p.collect_keys[(size_t)qg * p.collect_cap + slot] =
+                                    ((unsigned long long)v << 32) | idx;
+                        }
+                        continue;
+                    }
+                    uint32_t tc = s_thr[warp * C + c];
                     while (mm) {
                         const int src = __ffs(mm) - 1;
                         mm &= mm - 1;
@@ -382,9 +427,11 @@ __global__ void __launch_bounds__(kScanThreads, 2) scan_topk_kernel(const ScanPa
                     if (lane == 0) s_thr[warp * C + c] = tc;
                     __syncwarp();
                 }
-                dirty = true;
+                if (!collect) {
+                    dirty = true;
 #pragma unroll
-                for (int c = 0; c < C; ++c) thr[c] = min(thr[c], s_thr[warp * C + c]);
+                    for (int c = 0; c < C; ++c) thr[c] = min(thr[c], s_thr[warp * C + c]);
+                }
             }
         }
         __syncwarp();
@@ -401,6 +448,7 @@ __global__ void __launch_bounds__(kScanThreads, 2) scan_topk_kernel(const ScanPa
     }
 
     // -------- write this warp's lists to the partial buffer --------
+    if (collect) return;
     const int list_id = split * WR + wr;
 #pragma unroll
     for (int c = 0; c < C; ++c) {
