@@ -94,6 +94,10 @@ int vl_corpus_append_f32(vl_corpus* c, const float* vals_any, uint64_t n, int sr
 int vl_corpus_load_file(vl_corpus* c, const char* path, uint64_t byte_off, uint64_t byte_len,
                         int src_kind, uint64_t max_rows, uint64_t* first_row_out,
                         uint64_t* n_rows_out);
+/* append n rows whose bits are the signs (x > 0, MSB-first like np.packbits) of an int8 document
+ * store already on the device: docs_i8_dev is n x (8*W) int8, 16 B aligned.  Keeps the binary
+ * corpus and the rescore documents consistent without a host round trip (config 3). */
+int vl_corpus_append_sign_i8(vl_corpus* c, const int8_t* docs_i8_dev, uint64_t n, uint64_t* first_row_out);
 /* overwrite one existing row (VLite.update with a new vector) */
 int vl_corpus_set_row(vl_corpus* c, uint64_t row, const uint8_t* row_any);
 /* delete = clear the row's bit in the live mask (replaces `del self.index[id]`,

@@ -66,6 +66,7 @@ def load():
         "vl_corpus_append": (c_int, [c_void_p, c_void_p, c_u64, P(c_u64)]),
         "vl_corpus_append_f32": (c_int, [c_void_p, c_void_p, c_u64, c_int, P(c_u64)]),
         "vl_corpus_load_file": (c_int, [c_void_p, ctypes.c_char_p, c_u64, c_u64, c_int, c_u64, P(c_u64), P(c_u64)]),
+        "vl_corpus_append_sign_i8": (c_int, [c_void_p, c_void_p, c_u64, P(c_u64)]),
         "vl_corpus_set_row": (c_int, [c_void_p, c_u64, c_void_p]),
         "vl_corpus_tombstone": (c_int, [c_void_p, c_void_p, c_u64]),
         "vl_corpus_clear": (c_int, [c_void_p]),
@@ -199,6 +200,12 @@ class Corpus:
             vals = np.ascontiguousarray(vals, dtype=np.float32)
         first = ctypes.c_uint64()
         check(self._L.vl_corpus_append_f32(self._h, ptr(vals) if n else None, n, kind, ctypes.byref(first)))
+        return first.value
+
+    def append_sign_i8(self, docs_i8_dev, n: int) -> int:
+        """Append the sign bits of n device-resident int8 document rows (n x 8*W int8)."""
+        first = ctypes.c_uint64()
+        check(self._L.vl_corpus_append_sign_i8(self._h, ptr(docs_i8_dev), n, ctypes.byref(first)))
         return first.value
 
     def load_file(self, path: str, byte_off: int, byte_len: int, kind: int, max_rows: int = 0):

@@ -732,6 +732,22 @@ extern "C" int vl_corpus_load_file(vl_corpus* c, const char* path, uint64_t byte
     return VL_OK;
 }
 
+extern "C" int vl_corpus_append_sign_i8(vl_corpus* c, const int8_t* docs_i8_dev, uint64_t n, uint64_t* first_row_out) {
+    if (!c) return fail(VL_EINVAL, "corpus is NULL");
+    if (n && (!docs_i8_dev || !is_device_ptr(docs_i8_dev))) return fail(VL_EINVAL, "docs must be device memory");
+    if (reinterpret_cast<uintptr_t>(docs_i8_dev) & 15) return fail(VL_EINVAL, "docs must be 16 B aligned");
+    DeviceGuard g(c->device);
+    const uint64_t first = c->count;
+    if (first_row_out) *first_row_out = first;
+    if (n == 0) return VL_OK;
+    TRY(ensure_capacity(c, first + n));
+    const uint64_t n_words = n * (uint64_t)c->w / 4;
+    sign_i8_kernel<<<grid_for(n_words, 256, c->sms), 256, 0, c->stream>>>(
+        docs_i8_dev, n_words, reinterpret_cast<uint32_t*>(c->rows + first * (uint64_t)c->w));
+    LAUNCHED();
+    return mark_appended(c, first, n);
+}
+
 extern "C" int vl_corpus_set_row(vl_corpus* c, uint64_t row, const uint8_t* row_any) {
     if (!c || !row_any) return fail(VL_EINVAL, "NULL argument");
     if (row >= c->count) return fail(VL_EINVAL, "row %llu out of range", (unsigned long long)row);

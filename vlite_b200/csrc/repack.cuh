@@ -65,6 +65,30 @@ __global__ void repack_f32_bits_kernel(const float* __restrict__ src, uint64_t n
     }
 }
 
+// int8 embeddings -> sign bits packed MSB-first (the binary twin of an int8 document store):
+// one thread turns 32 int8 values into one 32-bit word of the row.
+__global__ void sign_i8_kernel(const int8_t* __restrict__ src, uint64_t n_words, uint32_t* __restrict__ dst) {
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n_words;
+         i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint4* s = reinterpret_cast<const uint4*>(src) + i * 2;
+        uint32_t out = 0;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const uint4 v = s[h];
+            const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+#pragma unroll
+                for (int b = 0; b < 4; ++b) {
+                    const int idx = h * 16 + j * 4 + b;            // 0..31 within the word's 32 values
+                    const int8_t x = (int8_t)((w[j] >> (8 * b)) & 0xFF);
+                    if (x > 0) out |= 1u << (8 * (idx >> 3) + (7 - (idx & 7)));
+                }
+        }
+        dst[i] = out;
+    }
+}
+
 // set live bits for rows [first, first+n)
 __global__ void live_set_range_kernel(uint32_t* __restrict__ live, uint64_t first, uint64_t n) {
     const uint64_t w0 = first >> 5, w1 = (first + n + 31) >> 5;

@@ -124,6 +124,8 @@ class VLite:
         self.filter_mode = filter_mode
         self.gpu_index = gpu_index
         self.model = EmbeddingModel(model_name, device=self.device, embedder=embedder, gpu_index=gpu_index)
+        if width:
+            self.model.binary_dims = width * 8      # e.g. width=128: keep all 1024 dims (no MRL cut)
         self.ctx = Ctx(ctx_dir)
         self._width = width
         self._corpus = None
