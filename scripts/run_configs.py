@@ -23,7 +23,7 @@ from vlite_b200 import _capi  # noqa: E402
 
 HBM = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"] if os.path.exists(
     os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6650.0
-OUT = os.path.join(ROOT, "gpurun_out", "configs.jsonl")
+OUT = os.path.join(ROOT, "gpurun_out", f"configs_{os.getpid()}_{int(time.time())}.jsonl")  # one file per run: gpurun merges by file name
 
 
 def emit(rec):
