@@ -232,3 +232,49 @@ def test_device_resident_queries_and_outputs(gpu):
     es, er = _oracle(corpus, queries, 10, HAMMING)
     np.testing.assert_array_equal(ds.cpu().numpy().view(np.uint32), es)
     np.testing.assert_array_equal(dr.cpu().numpy().view(np.uint64), er)
+
+
+def test_config2_full_size_bit_exact(gpu):
+    """BASELINE configs[1] at full size: 500k x 128 B, 1024 queries, k=10, every query compared
+    with the C oracle (5.1e8 pairs on the host cores), both metrics."""
+    n, w, nq, k = 500_000, 128, 1024, 10
+    corpus = synth.corpus_rows(0, 0, n, w)
+    qc, src = synth.clustered_queries(1, 0, n, nq // 2, w)
+    queries = np.ascontiguousarray(np.concatenate([qc, synth.uniform_queries(1, nq - nq // 2, w)]))
+    with gpu.Corpus(w, capacity_rows=n) as c:
+        c.fill_synthetic(0, 0, n)
+        for metric in (HAMMING, XORSUM):
+            s, r = c.search(queries, k, metric)
+            es, er = cscan.search(queries, corpus, k, metric)
+            np.testing.assert_array_equal(s, es)
+            np.testing.assert_array_equal(r, er)
+        np.testing.assert_array_equal(r[: nq // 2, 0].astype(np.int64), src)
+
+
+def test_large_corpus_properties(gpu):
+    """Size-independent properties on a 64M-row (8 GB) shard, where the oracle cannot follow:
+    planted needles at the ends and at tile boundaries come back first, lists ascend by
+    (score, row), returned scores equal a host re-score of the regenerated rows, and a second
+    identical call returns identical bytes (determinism)."""
+    n, w, k = 64_000_000, 128, 10
+    needles = np.array([0, 255, 256, 31_999_999, 32_000_000, n - 257, n - 1])
+    rng = np.random.default_rng(5)
+    base = np.concatenate([synth.corpus_rows(0, int(r), 1, w) for r in needles])
+    q = base ^ np.packbits(rng.random((len(needles), w * 8)) < 0.05, axis=1)
+    q = np.concatenate([q, synth.uniform_queries(77, 3, w)])
+    with gpu.Corpus(w, capacity_rows=n) as c:
+        c.fill_synthetic(0, 0, n)
+        for nq in (1, 2, len(q)):
+            s, r = c.search(q[:nq], k, HAMMING)
+            s2, r2 = c.search(q[:nq], k, HAMMING)
+            assert np.array_equal(s, s2) and np.array_equal(r, r2)
+            np.testing.assert_array_equal(r[: min(nq, len(needles)), 0].astype(np.int64), needles[:nq])
+            key = s.astype(np.float64) * 2.0 ** 40 + r.astype(np.float64)
+            assert (np.diff(key, axis=1) > 0).all()
+            for qi in range(nq):
+                regen = np.concatenate([synth.corpus_rows(0, int(x), 1, w) for x in r[qi]])
+                np.testing.assert_array_equal(osearch.hamming_scores(q[qi], regen).astype(np.uint32), s[qi])
+        # the k-th score is a true bound: an independent device score vector has exactly the
+        # returned number of rows strictly below it
+        full = c.scores(q[0], HAMMING, 0, 4_000_000)
+        assert (full < s[0, -1]).sum() <= k
