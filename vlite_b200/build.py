@@ -43,7 +43,7 @@ def build(force: bool = False, verbose: bool = False, out: str | None = None, ex
     os.makedirs(LIB_DIR, exist_ok=True)
     cmd = [
         _nvcc(), "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-        "--shared", "-Xcompiler", "-fPIC,-O3,-Wall",
+        "--shared", "-Xcompiler", "-fPIC,-O3,-Wall,-pthread",
         "-o", out,
     ] + list(extra_flags) + SOURCES
     if verbose:
