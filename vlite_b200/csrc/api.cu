@@ -265,6 +265,35 @@ int check_err_flag(vl_corpus* c, const char* what) {
     return VL_OK;
 }
 
+// ---- TMA tensor map of the corpus: 2-D uint8 tensor {W, rows}, box {W, 256 rows}, hardware swizzle
+// matching the row width (128 B or 64 B) so that one-row-per-lane 128-bit LDS is conflict-free ----
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+int make_corpus_tmap(const vl_corpus* c, CUtensorMap* out) {
+    static std::atomic<EncodeTiledFn> cached{nullptr};
+    EncodeTiledFn fn = cached.load();
+    if (!fn) {
+        void* sym = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        CU(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres));
+        if (qres != cudaDriverEntryPointSuccess || !sym)
+            return fail(VL_ECUDA, "the CUDA driver does not export cuTensorMapEncodeTiled");
+        fn = reinterpret_cast<EncodeTiledFn>(sym);
+        cached.store(fn);
+    }
+    const cuuint64_t dims[2] = {(cuuint64_t)c->w, (cuuint64_t)c->count};
+    const cuuint64_t strides[1] = {(cuuint64_t)c->w};
+    const cuuint32_t box[2] = {(cuuint32_t)c->w, (cuuint32_t)kTileRows};
+    const cuuint32_t estr[2] = {1, 1};
+    const CUtensorMapSwizzle sw = c->w == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
+    CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, c->rows, dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(VL_ECUDA, "cuTensorMapEncodeTiled failed (CUresult %d)", (int)r);
+    return VL_OK;
+}
+
 // ---- scan dispatch -------------------------------------------------------------
 struct ScanPlan {
     int C, WQ, WR, QT, T, S, stages, occ;
@@ -318,8 +347,10 @@ int launch_scan_cfg(vl_corpus* c, ScanParams& p, int n_queries, int k, ScanPlan*
     if (plan_out) *plan_out = ScanPlan{C, WQ, Cfg::WR, Cfg::QT, T, (int)S, stages, occ, smem};
     if (dry) return VL_OK;
     p.stages = stages;
+    CUtensorMap tmap;
+    TRY(make_corpus_tmap(c, &tmap));
     dim3 grid((unsigned)T, (unsigned)S);
-    kern<<<grid, kScanThreads, smem, c->stream>>>(p);
+    kern<<<grid, kScanThreads, smem, c->stream>>>(tmap, p);
     LAUNCHED();
     return VL_OK;
 }

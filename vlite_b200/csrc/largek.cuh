@@ -30,7 +30,7 @@ __global__ void __launch_bounds__(kSelectThreads)
 collect_select_kernel(const unsigned long long* __restrict__ keys, const uint32_t* __restrict__ count,
                       const uint32_t* __restrict__ thr, uint32_t cap, int k, uint64_t base_row,
                       uint32_t* __restrict__ out_scores, uint64_t* __restrict__ out_rows, int* __restrict__ flags) {
-    extern __shared__ __align__(128) uint8_t smem[];
+    extern __shared__ __align__(1024) uint8_t smem[];
     unsigned long long* s_keys = reinterpret_cast<unsigned long long*>(smem);
     const int q = blockIdx.x;
     const uint32_t n = count[q];

@@ -37,7 +37,7 @@ merge_topk_kernel(const uint32_t* __restrict__ scores, const uint64_t* __restric
 
     uint32_t cs[kMergeListsPerLane];
     uint64_t cr[kMergeListsPerLane];
-    int hd[kMergeListsPerLane];
+    int hd[kMergeListsPerLane] = {};
     auto load = [&](int j) {
         const int l = list0 + j * 32 + lane;
         cs[j] = kSentinelScore;

@@ -30,7 +30,7 @@ struct RescoreParams {
 
 template <bool QI8>
 __global__ void __launch_bounds__(kRescoreThreads) rescore_kernel(const RescoreParams p) {
-    extern __shared__ __align__(128) uint8_t smem[];
+    extern __shared__ __align__(1024) uint8_t smem[];
     const int q = blockIdx.x;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int dims = p.dims;

@@ -169,13 +169,14 @@ __device__ __forceinline__ uint32_t score_chunk_pair(const uint4& ra, const uint
 }
 
 template <int W, int METRIC, int C, int WQ>
-__global__ void __launch_bounds__(kScanThreads, 2) scan_topk_kernel(const ScanParams p) {
+__global__ void __launch_bounds__(kScanThreads, 2)
+scan_topk_kernel(const __grid_constant__ CUtensorMap tmap, const ScanParams p) {
     using Cfg = ScanCfg<W, C, WQ>;
     constexpr int WR = Cfg::WR, RPW = Cfg::RPW, R = Cfg::R, STEPS = Cfg::STEPS, QT = Cfg::QT;
     constexpr int CHUNKS = Cfg::CHUNKS, TILE_BYTES = Cfg::TILE_BYTES;
     static_assert(CHUNKS % 2 == 0, "rows are scored two 16 B chunks at a time");
 
-    extern __shared__ __align__(128) uint8_t smem[];
+    extern __shared__ __align__(1024) uint8_t smem[];  // swizzled TMA tiles want 1024 B alignment
     const int stages = p.stages;
     const int k = p.k;
     uint8_t* s_tiles = smem;                                                        // stages x TILE_BYTES
@@ -198,6 +199,7 @@ __global__ void __launch_bounds__(kScanThreads, 2) scan_topk_kernel(const ScanPa
     const uint32_t my_tiles = tile_end - tile_begin;
 
     if (threadIdx.x == 0) {
+        tma_prefetch_desc(&tmap);
         for (int s = 0; s < stages; ++s) {
             mbar_init(&s_full[s], 1);
             mbar_init(&s_empty[s], kScanWarps);
@@ -231,12 +233,11 @@ __global__ void __launch_bounds__(kScanThreads, 2) scan_topk_kernel(const ScanPa
         const int s = i % stages;
         const uint32_t t = (tile_begin + i) * p.tile_stride;
         const uint32_t row0 = t * kTileRows;
-        const uint32_t rows_here = min((uint32_t)kTileRows, p.n_rows - row0);
         const uint32_t mask_bytes = kMaskWordsPerTile * 4;
-        const uint32_t bytes = rows_here * W + mask_bytes + (p.filter ? mask_bytes : 0);
-        mbar_arrive_expect_tx(&s_full[s], bytes);
-        bulk_g2s_hint(s_tiles + (size_t)s * TILE_BYTES, p.rows + (uint64_t)row0 * W, rows_here * W, &s_full[s],
-                      policy);
+        // the tile arrives hardware-swizzled (16 B chunk index ^= row bits): rows past n_rows are
+        // zero-filled by the TMA unit and the whole box is always counted
+        mbar_arrive_expect_tx(&s_full[s], TILE_BYTES + mask_bytes + (p.filter ? mask_bytes : 0));
+        tma_load_2d(s_tiles + (size_t)s * TILE_BYTES, &tmap, 0, (int)row0, &s_full[s], policy);
         uint32_t* m = s_masks + s * 2 * kMaskWordsPerTile;
         bulk_g2s(m, p.live + (size_t)t * kMaskWordsPerTile, mask_bytes, &s_full[s]);
         if (p.filter)
@@ -277,7 +278,9 @@ __global__ void __launch_bounds__(kScanThreads, 2) scan_topk_kernel(const ScanPa
         }
     }
 
-    // rotated chunk order: conflict-free 128-bit LDS on a linear (unswizzled) tile
+    // TMA wrote the tile with the 128 B (W=128) / 64 B (W=64) swizzle: logical chunk j of row r sits
+    // at physical chunk j ^ rot(r), rot = r & 7 (resp. (r >> 1) & 3).  Lane l owns row l (mod 32), so
+    // its physical offset is (j * 16) ^ rot16 -- one row per lane at stride W, conflict-free 128-bit LDS
     constexpr int LANES_PER_128B = (W >= 128) ? 1 : 128 / W;
     constexpr int ROT_MASK = (CHUNKS < 8 ? CHUNKS : 8) - 1;
     const uint32_t rot16 = (uint32_t)(((lane / LANES_PER_128B) & ROT_MASK) * 16);
@@ -350,8 +353,9 @@ __global__ void __launch_bounds__(kScanThreads, 2) scan_topk_kernel(const ScanPa
                 }
 #pragma unroll
                 for (int c = 0; c < C; ++c) {
-                    const uint4 qa = lds128(q_saddr + (uint32_t)(c * W) + coff_a);
-                    const uint4 qb = lds128(q_saddr + (uint32_t)(c * W) + coff_b);
+                    // every lane scores the same LOGICAL chunk: the query read is a broadcast
+                    const uint4 qa = lds128(q_saddr + (uint32_t)(c * W + j * 16));
+                    const uint4 qb = lds128(q_saddr + (uint32_t)(c * W + (j + 1) * 16));
 #pragma unroll
                     for (int r = 0; r < R; ++r)
                         acc[r][c] = score_chunk_pair<METRIC>(ra[r], rb[r], qa, qb, acc[r][c], one);
