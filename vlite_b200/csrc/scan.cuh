@@ -35,6 +35,7 @@ constexpr int kMaskWordsPerTile = kTileRows / 32;  // 8 words = 32 bytes
 constexpr int kScanWarps = 8;
 constexpr int kScanThreads = kScanWarps * 32;
 constexpr int kWarpListMaxK = 128;
+constexpr uint32_t kMaskedBias = 0x40000000u;
 
 struct ScanParams {
     const uint8_t* rows;     // corpus, n_rows x W, 256-byte aligned
@@ -331,11 +332,13 @@ scan_topk_kernel(const __grid_constant__ CUtensorMap tmap, const ScanParams p) {
                 if (has_filter) w &= m[kMaskWordsPerTile + row_in_tile0 / 32 + r];
                 valid[r] = (w >> lane) & 1u;
             }
+            // masked rows start from a bias no real score reaches (max 255 * W), so the hot
+            // threshold test below needs no per-row predicate
             uint32_t acc[R][C];
 #pragma unroll
             for (int r = 0; r < R; ++r)
 #pragma unroll
-                for (int c = 0; c < C; ++c) acc[r][c] = 0;
+                for (int c = 0; c < C; ++c) acc[r][c] = valid[r] ? 0u : kMaskedBias;
 
             const uint32_t row_saddr =
                 tiles_saddr + (uint32_t)s * TILE_BYTES + (uint32_t)(row_in_tile0 + lane) * W;
@@ -364,9 +367,12 @@ scan_topk_kernel(const __grid_constant__ CUtensorMap tmap, const ScanParams p) {
 
             bool hit = false;
 #pragma unroll
-            for (int r = 0; r < R; ++r)
+            for (int c = 0; c < C; ++c) {
+                uint32_t best = acc[0][c];
 #pragma unroll
-                for (int c = 0; c < C; ++c) hit |= valid[r] && (acc[r][c] < thr[c]);
+                for (int r = 1; r < R; ++r) best = min(best, acc[r][c]);
+                hit |= best < thr[c];
+            }
 
             if (__any_sync(kFullMask, hit)) {
                 // Rare path, kept small on purpose (a compact loop, not R*C unrolled copies) so it
