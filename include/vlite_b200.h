@@ -78,9 +78,11 @@ int vl_corpus_create(int device, int width_bytes, uint64_t capacity_rows, vl_cor
 int vl_corpus_destroy(vl_corpus* c);
 /* stream: a cudaStream_t (as void*); NULL = the legacy default stream */
 int vl_corpus_set_stream(vl_corpus* c, void* cuda_stream);
+/* back at least capacity_rows rows with physical memory now (exact, e.g. a 16 GB shard) */
 int vl_corpus_reserve(vl_corpus* c, uint64_t capacity_rows);
-/* append n rows of raw ubinary bytes in place (capacity doubles when full);
- * *first_row_out = local index of the first appended row */
+/* append n rows of raw ubinary bytes IN PLACE: the shard lives in a virtual address range
+ * reserved once; when it fills, more physical HBM is mapped behind it (no copy, the base pointer
+ * never moves).  *first_row_out = local index of the first appended row */
 int vl_corpus_append(vl_corpus* c, const uint8_t* rows_any, uint64_t n, uint64_t* first_row_out);
 /* append n rows given as float32 in one of the VL_SRC_F32_* encodings; the
  * f32 -> ubinary repack runs on the device.  replaces the row-by-row
@@ -110,8 +112,7 @@ int vl_corpus_width(const vl_corpus* c);
 int vl_corpus_set_base_row(vl_corpus* c, uint64_t base_row);
 /* copy rows [first, first+n) back to the host (CTX save, tests) */
 int vl_corpus_read(vl_corpus* c, uint64_t first, uint64_t n, uint8_t* out_host);
-/* device address of row 0 and of the live mask (borrowed; valid until the next
- * append that grows the corpus) */
+/* device address of row 0 and of the live mask (borrowed; stable for the life of the handle) */
 int vl_corpus_device_ptrs(vl_corpus* c, void** rows_dev, void** live_mask_dev);
 /* fill rows [first, first+n) on the device with the counter-based synthetic
  * generator of oracle/synth.py (period = 0: all rows distinct); rows past the

@@ -216,7 +216,7 @@ def cfg5(args):
         emit({"config": 5, "part": "streaming_add", "batch_rows": batch, "batches": 8,
               "append_ms_per_batch": add_ms, "append_GBps_steady": batch * w / (np.median(add_ms[3:]) * 1e-3) / 1e9,
               "query_ms_after_each_batch_q64": q_ms,
-              "note": "append = H2D from pinned memory + live-mask kernel; batches that double capacity include the D2D copy"})
+              "note": "append = H2D from pinned memory + live-mask kernel; growth maps more physical memory behind the reserved range (no copy)"})
     # ---- CTX EMBEDDINGS section streamed to HBM (W=64 rows stored as 64 float32 = 256 B/row) ----
     from oracle import ctxfile as octx
     n_ctx = args.ctx_rows

@@ -228,3 +228,29 @@ def test_ctx_embeddings_stream_to_hbm(gpu, tmp_path):
         c.append_f32(osearch.to_ref_encoding(rows[:5]).astype(np.float32), gpu.SRC_F32_OFFSET)
         c.append_f32(rows[5:9].astype(np.float32), gpu.SRC_F32_OFFSET)            # raw 0..255 also accepted
         np.testing.assert_array_equal(c.read(), rows[:9])
+
+
+def test_large_collection_splits_into_v1_part_files(gpu, golden, tmp_path):
+    """CTXF v1's u32 section length caps a file at 4 GiB of rows; bigger collections are written as
+    several complete v1 files.  Exercised here with a tiny per-file cap."""
+    from vlite_b200 import VLite
+    v = _build(gpu, golden, tmp_path)
+    v.max_rows_per_file = 50
+    v.save()
+    d = tmp_path / "contexts"
+    names = sorted(p.name for p in d.iterdir())
+    assert names == ["golden.ctx", "golden.part1.ctx", "golden.part2.ctx"]
+    header, emb, contexts, metadata, _ = octx.read_ctx(str(d / "golden.part1.ctx"))   # each part is plain CTXF v1
+    assert header["parts"] == 3 and header["part"] == 1 and len(emb) == len(contexts) == len(metadata) == 50
+    v2 = VLite("golden", ctx_dir=str(d), embedder=bits_embedder(golden["queries"]))
+    assert v2.count() == v.count() == 120 and list(v2.index.keys()) == list(v.index.keys())
+    q = osearch.to_ref_encoding(golden["queries"][1])
+    assert v2.rank_and_filter(q, 7) == v.rank_and_filter(q, 7)
+    np.testing.assert_array_equal(v2._corpus.read(), v._corpus.read())
+    v2.max_rows_per_file = 100
+    v2.save()                                               # fewer parts now: the stale part file goes away
+    assert sorted(p.name for p in d.iterdir()) == ["golden.ctx", "golden.part1.ctx"]
+    v2.clear()
+    assert list(d.iterdir()) == []
+    v.close()
+    v2.close()

@@ -10,6 +10,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <mutex>
 #include <string>
 #include <thread>
 #include <vector>
@@ -146,14 +147,132 @@ inline unsigned grid_for(uint64_t items, int threads, int sms) {
 
 }  // namespace
 
+// ---- append-in-place storage: a virtual address range reserved once, physical HBM mapped behind
+// it chunk by chunk (CUDA virtual memory management).  Growing a shard never copies a byte and never
+// moves the base pointer, so a 100 GB corpus can keep appending without a 2x transient.  The driver
+// entry points come from cudaGetDriverEntryPoint: the library does not link libcuda. ----
+struct VmmApi {
+    CUresult (*reserve)(CUdeviceptr*, size_t, size_t, CUdeviceptr, unsigned long long) = nullptr;
+    CUresult (*release_va)(CUdeviceptr, size_t) = nullptr;
+    CUresult (*create)(CUmemGenericAllocationHandle*, size_t, const CUmemAllocationProp*, unsigned long long) = nullptr;
+    CUresult (*release)(CUmemGenericAllocationHandle) = nullptr;
+    CUresult (*map)(CUdeviceptr, size_t, size_t, CUmemGenericAllocationHandle, unsigned long long) = nullptr;
+    CUresult (*unmap)(CUdeviceptr, size_t) = nullptr;
+    CUresult (*set_access)(CUdeviceptr, size_t, const CUmemAccessDesc*, size_t) = nullptr;
+    CUresult (*granularity)(size_t*, const CUmemAllocationProp*, CUmemAllocationGranularity_flags) = nullptr;
+    bool ok = false;
+};
+
+int vmm_api(const VmmApi** out) {
+    static VmmApi api;
+    static std::atomic<int> state{0};
+    if (state.load() == 0) {
+        static std::mutex mu;
+        std::lock_guard<std::mutex> lock(mu);
+        if (state.load() == 0) {
+            auto get = [](const char* name, void** fn) {
+                cudaDriverEntryPointQueryResult q;
+                return cudaGetDriverEntryPoint(name, fn, cudaEnableDefault, &q) == cudaSuccess &&
+                       q == cudaDriverEntryPointSuccess && *fn != nullptr;
+            };
+            api.ok = get("cuMemAddressReserve", reinterpret_cast<void**>(&api.reserve)) &&
+                     get("cuMemAddressFree", reinterpret_cast<void**>(&api.release_va)) &&
+                     get("cuMemCreate", reinterpret_cast<void**>(&api.create)) &&
+                     get("cuMemRelease", reinterpret_cast<void**>(&api.release)) &&
+                     get("cuMemMap", reinterpret_cast<void**>(&api.map)) &&
+                     get("cuMemUnmap", reinterpret_cast<void**>(&api.unmap)) &&
+                     get("cuMemSetAccess", reinterpret_cast<void**>(&api.set_access)) &&
+                     get("cuMemGetAllocationGranularity", reinterpret_cast<void**>(&api.granularity));
+            cudaGetLastError();
+            state.store(1);
+        }
+    }
+    if (!api.ok) return fail(VL_ECUDA, "the CUDA driver does not export the virtual memory management API");
+    *out = &api;
+    return VL_OK;
+}
+
+struct VmmArena {
+    CUdeviceptr base = 0;
+    size_t reserved = 0, mapped = 0, gran = 0;
+    int device = 0;
+    std::vector<std::pair<CUmemGenericAllocationHandle, size_t>> chunks;
+
+    CUmemAllocationProp prop() const {
+        CUmemAllocationProp p{};
+        p.type = CU_MEM_ALLOCATION_TYPE_PINNED;
+        p.location.type = CU_MEM_LOCATION_TYPE_DEVICE;
+        p.location.id = device;
+        return p;
+    }
+    int init(int dev, size_t reserve_bytes) {
+        const VmmApi* a;
+        TRY(vmm_api(&a));
+        device = dev;
+        CUmemAllocationProp p = prop();
+        if (a->granularity(&gran, &p, CU_MEM_ALLOC_GRANULARITY_RECOMMENDED) != CUDA_SUCCESS || gran == 0)
+            return fail(VL_ECUDA, "cuMemGetAllocationGranularity failed");
+        reserved = (reserve_bytes + gran - 1) / gran * gran;
+        CUresult r = a->reserve(&base, reserved, gran, 0, 0);
+        if (r != CUDA_SUCCESS) return fail(VL_ENOMEM, "cuMemAddressReserve(%zu) failed (CUresult %d)", reserved, (int)r);
+        return VL_OK;
+    }
+    // map physical memory until at least `need` bytes are backed
+    int grow(size_t need) {
+        if (need <= mapped) return VL_OK;
+        if (need > reserved) return fail(VL_ENOMEM, "corpus exceeds the reserved address range (%zu > %zu)", need, reserved);
+        const VmmApi* a;
+        TRY(vmm_api(&a));
+        const size_t add = (need - mapped + gran - 1) / gran * gran;
+        CUmemAllocationProp p = prop();
+        CUmemGenericAllocationHandle h;
+        CUresult r = a->create(&h, add, &p, 0);
+        if (r != CUDA_SUCCESS) return fail(VL_ENOMEM, "cuMemCreate(%zu) failed (CUresult %d): out of device memory", add, (int)r);
+        r = a->map(base + mapped, add, 0, h, 0);
+        if (r != CUDA_SUCCESS) {
+            a->release(h);
+            return fail(VL_ECUDA, "cuMemMap failed (CUresult %d)", (int)r);
+        }
+        CUmemAccessDesc acc{};
+        acc.location.type = CU_MEM_LOCATION_TYPE_DEVICE;
+        acc.location.id = device;
+        acc.flags = CU_MEM_ACCESS_FLAGS_PROT_READWRITE;
+        r = a->set_access(base + mapped, add, &acc, 1);
+        if (r != CUDA_SUCCESS) {
+            a->unmap(base + mapped, add);
+            a->release(h);
+            return fail(VL_ECUDA, "cuMemSetAccess failed (CUresult %d)", (int)r);
+        }
+        chunks.emplace_back(h, add);
+        mapped += add;
+        return VL_OK;
+    }
+    void destroy() {
+        const VmmApi* a;
+        if (vmm_api(&a) != VL_OK) return;
+        size_t off = 0;
+        for (auto& ch : chunks) {
+            a->unmap(base + off, ch.second);
+            a->release(ch.first);
+            off += ch.second;
+        }
+        chunks.clear();
+        if (base) a->release_va(base, reserved);
+        base = 0;
+        reserved = mapped = 0;
+    }
+};
+
 struct vl_corpus {
     int device = 0;
     int w = 0;
     int sms = 148;
     cudaStream_t stream = nullptr;
-    uint8_t* rows = nullptr;
-    uint32_t* live = nullptr;
-    uint64_t capacity = 0;  // rows, multiple of kTileRows
+    VmmArena rows_arena, live_arena;
+    uint8_t* rows = nullptr;   // = rows_arena.base: never moves
+    uint32_t* live = nullptr;  // = live_arena.base
+    size_t live_zeroed = 0;    // bytes of the live mask initialised so far
+    uint64_t capacity = 0;  // rows backed by physical memory, multiple of kTileRows
     uint64_t count = 0;
     uint64_t live_count = 0;
     uint64_t base_row = 0;
@@ -175,44 +294,32 @@ namespace {
 
 using namespace vl;
 
-// reallocate rows + live mask to exactly `cap_rows` (rounded up to whole tiles), keeping contents
+// back at least `cap_rows` rows (rounded up to whole tiles) with physical memory -- no copy, no move
 int grow_to(vl_corpus* c, uint64_t cap_rows) {
     if (cap_rows > 0xFFFFFF00ull) return fail(VL_EINVAL, "a corpus shard holds at most 2^32-256 rows");
     const uint64_t cap = (cap_rows + kTileRows - 1) / kTileRows * kTileRows;
-    uint8_t* nrows = nullptr;
-    uint32_t* nlive = nullptr;
-    cudaError_t e = cudaMalloc(&nrows, cap * (uint64_t)c->w);
-    if (e != cudaSuccess) {
-        cudaGetLastError();
-        return fail(VL_ENOMEM, "cudaMalloc of %llu rows x %d B failed: %s", (unsigned long long)cap, c->w,
-                    cudaGetErrorString(e));
+    if (cap <= c->capacity) return VL_OK;
+    TRY(c->rows_arena.grow(cap * (uint64_t)c->w));
+    TRY(c->live_arena.grow(cap / 8));
+    if (c->live_arena.mapped > c->live_zeroed) {  // fresh mask bytes start dead
+        CU(cudaMemsetAsync(reinterpret_cast<uint8_t*>(c->live) + c->live_zeroed, 0,
+                           c->live_arena.mapped - c->live_zeroed, c->stream));
+        c->live_zeroed = c->live_arena.mapped;
     }
-    e = cudaMalloc(&nlive, cap / 8);
-    if (e != cudaSuccess) {
-        cudaGetLastError();
-        cudaFree(nrows);
-        return fail(VL_ENOMEM, "cudaMalloc of live mask failed: %s", cudaGetErrorString(e));
-    }
-    CU(cudaMemsetAsync(nlive, 0, cap / 8, c->stream));
-    if (c->count) {
-        CU(cudaMemcpyAsync(nrows, c->rows, c->count * (uint64_t)c->w, cudaMemcpyDeviceToDevice, c->stream));
-        CU(cudaMemcpyAsync(nlive, c->live, c->capacity / 8, cudaMemcpyDeviceToDevice, c->stream));
-    }
-    CU(cudaStreamSynchronize(c->stream));
-    if (c->rows) cudaFree(c->rows);
-    if (c->live) cudaFree(c->live);
-    c->rows = nrows;
-    c->live = nlive;
-    c->capacity = cap;
+    // everything that is mapped is usable capacity (whole tiles only)
+    const uint64_t by_rows = c->rows_arena.mapped / (uint64_t)c->w;
+    const uint64_t by_live = (uint64_t)c->live_arena.mapped * 8;
+    c->capacity = std::min<uint64_t>(std::min(by_rows, by_live), 0xFFFFFF00ull) / kTileRows * kTileRows;
     return VL_OK;
 }
 
-// append-in-place growth: capacity doubles; if the doubled size does not fit, take exactly `need`
+// append-in-place growth: map at least 1/2 of the current size (64 MB minimum) so that a stream of
+// small appends costs O(log) driver calls; nothing is copied either way
 int ensure_capacity(vl_corpus* c, uint64_t need_rows) {
     if (need_rows <= c->capacity) return VL_OK;
-    const uint64_t doubled = std::max<uint64_t>(std::max<uint64_t>(need_rows, c->capacity * 2), 4096);
-    int rc = grow_to(c, doubled);
-    if (rc == VL_ENOMEM && doubled > need_rows) rc = grow_to(c, need_rows);
+    const uint64_t step_rows = std::max<uint64_t>(c->capacity / 2, (64ull << 20) / c->w);
+    int rc = grow_to(c, std::max(need_rows, c->capacity + step_rows));
+    if (rc == VL_ENOMEM) rc = grow_to(c, need_rows);
     return rc;
 }
 
@@ -603,7 +710,15 @@ extern "C" int vl_corpus_create(int device, int width_bytes, uint64_t capacity_r
     cudaEventCreate(&c->ev1);
     cudaEventCreate(&c->ev2);
     for (int i = 0; i < 2; ++i) cudaEventCreateWithFlags(&c->stage_ev[i], cudaEventDisableTiming);
-    int rc = ensure_capacity(c, std::max<uint64_t>(capacity_rows, 1));
+    size_t free_b = 0, total_b = 0;
+    if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) return bail(fail(VL_ECUDA, "cudaMemGetInfo failed"));
+    // address space is free: reserve room for a shard as large as the whole device
+    int rc = c->rows_arena.init(device, total_b);
+    if (rc == VL_OK) rc = c->live_arena.init(device, total_b / ((size_t)width_bytes * 8) + (1 << 21));
+    if (rc != VL_OK) return bail(rc);
+    c->rows = reinterpret_cast<uint8_t*>(c->rows_arena.base);
+    c->live = reinterpret_cast<uint32_t*>(c->live_arena.base);
+    rc = capacity_rows ? grow_to(c, capacity_rows) : VL_OK;   // exact reservation; 0 = map on first append
     if (rc != VL_OK) return bail(rc);
     *out = c;
     return VL_OK;
@@ -613,8 +728,8 @@ extern "C" int vl_corpus_destroy(vl_corpus* c) {
     if (!c) return VL_OK;
     DeviceGuard g(c->device);
     cudaStreamSynchronize(c->stream);
-    if (c->rows) cudaFree(c->rows);
-    if (c->live) cudaFree(c->live);
+    c->rows_arena.destroy();
+    c->live_arena.destroy();
     for (DevBuf* b : {&c->q_buf, &c->filt_buf, &c->part_s, &c->part_r, &c->out_s, &c->out_r, &c->stage[0],
                       &c->stage[1], &c->rows_buf, &c->cand_buf, &c->misc, &c->lk_keys, &c->lk_misc})
         b->release();
@@ -830,7 +945,7 @@ extern "C" int vl_corpus_tombstone(vl_corpus* c, const uint64_t* rows_host, uint
 extern "C" int vl_corpus_clear(vl_corpus* c) {
     if (!c) return fail(VL_EINVAL, "corpus is NULL");
     DeviceGuard g(c->device);
-    CU(cudaMemsetAsync(c->live, 0, c->capacity / 8, c->stream));
+    if (c->capacity) CU(cudaMemsetAsync(c->live, 0, c->capacity / 8, c->stream));
     CU(cudaStreamSynchronize(c->stream));
     c->count = 0;
     c->live_count = 0;

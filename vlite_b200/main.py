@@ -25,6 +25,7 @@ from __future__ import annotations
 
 import datetime
 import logging
+import os
 from uuid import uuid4
 
 import numpy as np
@@ -127,6 +128,7 @@ class VLite:
         if width:
             self.model.binary_dims = width * 8      # e.g. width=128: keep all 1024 dims (no MRL cut)
         self.ctx = Ctx(ctx_dir)
+        self.max_rows_per_file = 1 << 24       # CTXF v1: u32 section length => 4 GiB of float32 rows
         self._width = width
         self._corpus = None
         self._row_of = {}          # chunk_id -> row (None: no stored vector)
@@ -183,9 +185,21 @@ class VLite:
 
     def _load_collection(self):
         """vlite/main.py:42-53: index keyed by metadata.keys() order; embeddings[idx] and
-        contexts[idx] are positional; surplus rows in the file are ignored."""
-        cf = self.ctx.read(self.collection)
-        cf.load(materialise=False)
+        contexts[idx] are positional; surplus rows in the file are ignored.  A collection that was
+        split over several files by ``save`` (header key "parts") is read back part by part."""
+        parts, i = 1, 0
+        while i < parts:
+            cf = self.ctx.read(self._part_name(i))
+            cf.load(materialise=False)
+            if i == 0:
+                parts = int(cf.header.get("parts", 1)) if isinstance(cf.header, dict) else 1
+            self._load_part(cf)
+            i += 1
+
+    def _part_name(self, i: int) -> str:
+        return self.collection if i == 0 else f"{self.collection}.part{i}"
+
+    def _load_part(self, cf):
         keys = list(cf.metadata.keys())
         if not keys:
             return
@@ -404,22 +418,39 @@ class VLite:
     def save(self):
         """vlite/main.py:280-294, written CLEAN: one row per live key in key order (the reference's
         context manager loads the old file first and appends the whole collection to it again,
-        vlite/ctx.py:157-162; a reference reader loads a clean file identically)."""
-        cf = self.ctx.create(self.collection)
+        vlite/ctx.py:157-162; a reference reader loads a clean file identically).
+
+        CTXF v1 frames a section with a u32 length, i.e. at most 4 GiB of float32 rows per file
+        (16.7M rows of 64 floats).  A larger collection is written as several v1 files --
+        ``<name>.ctx`` plus ``<name>.partN.ctx`` -- each a complete, reference-readable CTX file
+        for its slice of the keys; the first header carries ``"parts": n``."""
         width = self._width or 64
-        cf.set_header(embedding_model="mixedbread-ai/mxbai-embed-large-v1", embedding_size=width,
-                      embedding_dtype=self.model.embedding_dtype, context_length=self.model.context_length)
         keys = list(self._row_of.keys())
         rows = [self._row_of[k] for k in keys]
         if keys and any(r is None for r in rows):
             raise ValueError("cannot save: some chunks have no stored vector")
-        if keys:
-            all_rows = self._corpus.read()                                   # one D2H copy
-            cf.set_embeddings_array(to_reference_encoding(all_rows[np.asarray(rows)]).astype(np.float32))
-        for k in keys:
-            cf.add_context(self._texts[k])
-            cf.add_metadata(k, self._metas[k])
-        cf.save()
+        per_file = max(1, min(self.max_rows_per_file, ((1 << 32) - 1) // (width * 4)))
+        n_parts = max(1, -(-len(keys) // per_file))
+        all_rows = self._corpus.read() if keys else None                     # one D2H copy
+        for part in range(n_parts):
+            cf = self.ctx.create(self._part_name(part))
+            cf.set_header(embedding_model="mixedbread-ai/mxbai-embed-large-v1", embedding_size=width,
+                          embedding_dtype=self.model.embedding_dtype, context_length=self.model.context_length)
+            if n_parts > 1:
+                cf.header["parts"] = n_parts
+                cf.header["part"] = part
+            lo, hi = part * per_file, min(len(keys), (part + 1) * per_file)
+            if hi > lo:
+                sel = np.asarray(rows[lo:hi])
+                cf.set_embeddings_array(to_reference_encoding(all_rows[sel]).astype(np.float32))
+            for k in keys[lo:hi]:
+                cf.add_context(self._texts[k])
+                cf.add_metadata(k, self._metas[k])
+            cf.save()
+        stale = n_parts                                                      # parts left by a bigger past save
+        while os.path.exists(self.ctx.get(self._part_name(stale))):
+            self.ctx.delete(self._part_name(stale))
+            stale += 1
 
     def clear(self):
         """vlite/main.py:296-300."""
@@ -431,7 +462,10 @@ class VLite:
         self._metas.clear()
         self._extra.clear()
         self._postings.clear()
-        self.ctx.delete(self.collection)
+        i = 0
+        while i == 0 or os.path.exists(self.ctx.get(self._part_name(i))):
+            self.ctx.delete(self._part_name(i))
+            i += 1
 
     def info(self):
         print("[VLite.info] Collection Information:")
