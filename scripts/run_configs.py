@@ -262,7 +262,10 @@ def cfg4(args):
     c.fill_synthetic(0, 0, rows)
     s = ShardedSearcher(c)
     # needles: clustered queries whose sources sit at shard boundaries and at rows 0, total-1
-    needle_rows = [0, total - 1] + [plan.base_row(g) for g in range(1, world)] + [plan.base_row(g) - 1 for g in range(1, world)]
+    # (the same rows for every world size -- boundaries of an 8-way split -- so that the result
+    # digest can be compared across 2/4/8 GPUs: the output must not depend on the shard count)
+    ref_plan = ShardPlan(total, 8)
+    needle_rows = [0, total - 1] + [ref_plan.base_row(g) for g in range(1, 8)] + [ref_plan.base_row(g) - 1 for g in range(1, 8)]
     rng = np.random.default_rng(11)
     digest = {}
     for nq in (1, 2, 64, 1024):
