@@ -1,0 +1,75 @@
+"""-m gpu: error behaviour of the C ABI (negative code + vl_last_error, no crash, no silent fallback)."""
+import ctypes
+
+import numpy as np
+import pytest
+
+from oracle import synth
+
+pytestmark = pytest.mark.gpu
+
+
+def test_argument_errors(gpu):
+    corpus = synth.corpus_rows(1, 0, 100, 128)
+    q = synth.uniform_queries(2, 2, 128)
+    with gpu.Corpus(128) as c:
+        c.append(corpus)
+        for bad_k in (0, -1, gpu.MAX_K + 1):
+            with pytest.raises(gpu.VliteB200Error) as ei:
+                c.search(q, bad_k)
+            assert ei.value.code == gpu.EINVAL
+        with pytest.raises(gpu.VliteB200Error):
+            c.search(q, 5, metric=7)
+        with pytest.raises(ValueError):
+            c.search(synth.uniform_queries(2, 2, 64), 5)            # wrong width
+        with pytest.raises(ValueError):
+            c.append(synth.corpus_rows(1, 0, 3, 64))
+        with pytest.raises(ValueError):
+            c.search(q, 5, filter_mask=np.zeros(1, np.uint32))       # mask shorter than the corpus
+        with pytest.raises(gpu.VliteB200Error):
+            c.read(50, 100)
+        with pytest.raises(gpu.VliteB200Error):
+            c.set_row(100, corpus[0])
+        with pytest.raises(gpu.VliteB200Error):
+            c.last_timing()                                           # nothing timed yet
+        # still healthy after all of that
+        s, r = c.search(corpus[7:8], 1)
+        assert int(r[0, 0]) == 7 and int(s[0, 0]) == 0
+    with pytest.raises(gpu.VliteB200Error) as ei:
+        gpu.Corpus(96)
+    assert ei.value.code == gpu.EINVAL
+    with pytest.raises(gpu.VliteB200Error):
+        gpu.Corpus(128, device=99)
+
+
+def test_set_row_reserve_clear_and_out_of_range_tombstones(gpu):
+    corpus = synth.corpus_rows(3, 0, 600, 64)
+    with gpu.Corpus(64) as c:
+        c.reserve(10_000)
+        rows_ptr, live_ptr = c.device_ptrs()
+        c.append(corpus)
+        c.reserve(5_000_000)                                          # growth maps memory: pointers do not move
+        assert c.device_ptrs() == (rows_ptr, live_ptr)
+        np.testing.assert_array_equal(c.read(), corpus)
+        c.set_row(5, corpus[9])
+        s, r = c.search(corpus[9:10], 2, gpu.HAMMING)
+        assert list(r[0]) == [5, 9] and list(s[0]) == [0, 0]
+        c.tombstone([5, 10_000_000, 5])                               # out-of-range and repeated rows are ignored
+        assert c.live_rows == 599
+        c.clear()
+        assert c.rows == 0 and c.live_rows == 0
+        s, r = c.search(corpus[:1], 3)
+        assert (r == np.uint64(gpu.SENTINEL_ROW)).all()
+        assert c.append(corpus[:10]) == 0                             # rows restart at 0 after clear
+        s, r = c.search(corpus[3:4], 1)
+        assert int(r[0, 0]) == 3
+    c.close()
+    c.close()                                                         # double close is harmless
+
+
+def test_launch_counter_counts_library_kernels(gpu):
+    before = gpu.launch_count()
+    with gpu.Corpus(128) as c:
+        c.fill_synthetic(0, 0, 1000)
+        c.search(synth.uniform_queries(1, 3, 128), 4)
+    assert gpu.launch_count() - before >= 4          # fill, live-mask, scan, merge

@@ -254,6 +254,8 @@ class Corpus:
             filter_mask = np.ascontiguousarray(filter_mask, dtype=np.uint32)
             if filter_mask.shape[0] * 32 < self.rows:
                 raise ValueError("filter mask is shorter than the corpus")
+        if k < 1:
+            raise VliteB200Error(EINVAL, f"k must be in [1, {MAX_K}]")
         if out_scores is None:
             out_scores = np.empty((nq, k), dtype=np.uint32)
         if out_rows is None:
