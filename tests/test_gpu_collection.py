@@ -254,3 +254,23 @@ def test_large_collection_splits_into_v1_part_files(gpu, golden, tmp_path):
     assert list(d.iterdir()) == []
     v.close()
     v2.close()
+
+
+def test_compact_ubinary_ctx_round_trip(gpu, golden, tmp_path):
+    """Opt-in CTX extension: embedding_dtype "ubinary" stores packed bytes (a quarter of the float32
+    layout); the default stays the reference's float32 layout."""
+    from vlite_b200 import VLite
+    v = _build(gpu, golden, tmp_path)
+    v.save()
+    f32_size = (tmp_path / "contexts" / "golden.ctx").stat().st_size
+    v.ctx_dtype = "ubinary"
+    v.save()
+    path = tmp_path / "contexts" / "golden.ctx"
+    assert path.stat().st_size < f32_size - 120 * 64 * 3 + 64
+    v2 = VLite("golden", ctx_dir=str(tmp_path / "contexts"), embedder=bits_embedder(golden["queries"]))
+    assert v2.count() == 120
+    np.testing.assert_array_equal(v2._corpus.read(), v._corpus.read())
+    q = osearch.to_ref_encoding(golden["queries"][0])
+    assert v2.rank_and_filter(q, 5) == v.rank_and_filter(q, 5)
+    v.close()
+    v2.close()

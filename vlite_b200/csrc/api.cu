@@ -296,7 +296,8 @@ using namespace vl;
 
 // back at least `cap_rows` rows (rounded up to whole tiles) with physical memory -- no copy, no move
 int grow_to(vl_corpus* c, uint64_t cap_rows) {
-    if (cap_rows > 0xFFFFFF00ull) return fail(VL_EINVAL, "a corpus shard holds at most 2^32-256 rows");
+    // local rows are u32 in the kernels and a signed 32-bit TMA coordinate
+    if (cap_rows > 0x7FFFFF00ull) return fail(VL_EINVAL, "a corpus shard holds at most 2^31-256 rows");
     const uint64_t cap = (cap_rows + kTileRows - 1) / kTileRows * kTileRows;
     if (cap <= c->capacity) return VL_OK;
     TRY(c->rows_arena.grow(cap * (uint64_t)c->w));
@@ -309,7 +310,7 @@ int grow_to(vl_corpus* c, uint64_t cap_rows) {
     // everything that is mapped is usable capacity (whole tiles only)
     const uint64_t by_rows = c->rows_arena.mapped / (uint64_t)c->w;
     const uint64_t by_live = (uint64_t)c->live_arena.mapped * 8;
-    c->capacity = std::min<uint64_t>(std::min(by_rows, by_live), 0xFFFFFF00ull) / kTileRows * kTileRows;
+    c->capacity = std::min<uint64_t>(std::min(by_rows, by_live), 0x7FFFFF00ull) / kTileRows * kTileRows;
     return VL_OK;
 }
 

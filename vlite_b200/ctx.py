@@ -15,8 +15,11 @@ Differences from the reference, all deliberate:
   * the row width follows ``header["embedding_size"]`` when it is 64 or 128 (the reference writes
     that field, vlite/main.py:285, but always reads and writes 64 floats, vlite/ctx.py:70, :114);
     512 is accepted as the legacy one-float-per-bit layout of tests/contexts/vlite-bench.ctx;
-  * ``save()`` from a ``with`` block still loads on enter and saves on exit (vlite/ctx.py:157-162)
-    but ``VLite.save`` passes ``fresh=True`` so a collection is not appended to itself.
+  * ``header["embedding_dtype"] == "ubinary"`` (opt-in extension, not readable by the reference):
+    rows are stored as raw packed bytes, ``embedding_size`` bytes per row -- a quarter of the
+    float32 layout, and what the device holds, so loading is a straight copy;
+  * a ``with`` block still loads on enter and saves on exit (vlite/ctx.py:157-162); ``VLite.save``
+    writes a fresh ``CtxFile`` without entering it, so a collection is not appended to itself.
 """
 from __future__ import annotations
 
@@ -36,6 +39,10 @@ class CtxSectionType(Enum):       # vlite/ctx.py:16-20
     EMBEDDINGS = 1
     CONTEXTS = 2
     METADATA = 3
+
+
+def is_ubinary(header: dict) -> bool:
+    return isinstance(header, dict) and header.get("embedding_dtype") == "ubinary"
 
 
 def row_floats_for(header: dict) -> int:
@@ -92,6 +99,7 @@ class CtxFile:
         width = row_floats_for(self.header)
         if width == 512:
             width = LEGACY_ROW_FLOATS
+        elem = np.dtype("u1") if is_ubinary(self.header) else np.dtype("<f4")
         with open(self.file_path, "wb") as f:
             f.write(self.MAGIC_NUMBER)
             f.write(struct.pack("<I", self.VERSION))
@@ -101,16 +109,16 @@ class CtxFile:
             n_emb = len(self.embeddings)
             if n_emb:                                        # section omitted when empty (ctx.py:68)
                 if isinstance(self.embeddings, np.ndarray):
-                    arr = np.ascontiguousarray(self.embeddings[:, :width], dtype="<f4")
+                    arr = np.ascontiguousarray(self.embeddings[:, :width], dtype=elem)
                 else:
                     rows = []
                     for emb in self.embeddings:
-                        r = np.asarray(emb, dtype="<f4").reshape(-1)[:width]   # emb[:64] (ctx.py:70)
+                        r = np.asarray(emb, dtype=elem).reshape(-1)[:width]   # emb[:64] (ctx.py:70)
                         if r.shape[0] != width:
                             raise struct.error(f"pack expected {width} items for packing (got {r.shape[0]})")
                         rows.append(r)
                     arr = np.stack(rows)
-                data_len = arr.shape[0] * width * 4
+                data_len = arr.shape[0] * width * elem.itemsize
                 if data_len >= 1 << 32:
                     raise ValueError("EMBEDDINGS section exceeds the u32 length field of CTXF v1 "
                                      "(at most 16.7M rows of 64 floats); split the collection")
@@ -150,9 +158,10 @@ class CtxFile:
                     self.embeddings_section = (f.tell(), section_length)
                     if materialise and section_length:
                         width = row_floats_for(self.header)
+                        elem = np.dtype("u1") if is_ubinary(self.header) else np.dtype("<f4")
                         data = f.read(section_length)
-                        n = len(data) // (width * 4)         # floor (ctx.py:115)
-                        self._emb_array = np.frombuffer(data, dtype="<f4", count=n * width).reshape(n, width)
+                        n = len(data) // (width * elem.itemsize)         # floor (ctx.py:115)
+                        self._emb_array = np.frombuffer(data, dtype=elem, count=n * width).reshape(n, width)
                         self.embeddings = self._emb_array
                     else:
                         f.seek(section_length, os.SEEK_CUR)
@@ -176,7 +185,7 @@ class CtxFile:
     @property
     def n_embeddings(self) -> int:
         if self.embeddings_section is not None and self._emb_array is None and not len(self.embeddings):
-            return self.embeddings_section[1] // (row_floats_for(self.header) * 4)
+            return self.embeddings_section[1] // (row_floats_for(self.header) * (1 if is_ubinary(self.header) else 4))
         return len(self.embeddings)
 
     def __repr__(self):

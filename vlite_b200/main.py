@@ -31,7 +31,7 @@ from uuid import uuid4
 import numpy as np
 
 from . import _capi
-from .ctx import Ctx, row_floats_for
+from .ctx import Ctx, is_ubinary, row_floats_for
 from .model import EmbeddingModel, from_reference_encoding, to_reference_encoding
 
 logger = logging.getLogger(__name__)
@@ -128,7 +128,9 @@ class VLite:
         if width:
             self.model.binary_dims = width * 8      # e.g. width=128: keep all 1024 dims (no MRL cut)
         self.ctx = Ctx(ctx_dir)
-        self.max_rows_per_file = 1 << 24       # CTXF v1: u32 section length => 4 GiB of float32 rows
+        self.max_rows_per_file = 1 << 26       # further capped by the u32 section length of CTXF v1
+        # "float32" = the reference's layout (default); "ubinary" = packed bytes, 4x smaller, opt-in
+        self.ctx_dtype = "float32"
         self._width = width
         self._corpus = None
         self._row_of = {}          # chunk_id -> row (None: no stored vector)
@@ -207,7 +209,10 @@ class VLite:
         n_emb = cf.n_embeddings
         n_take = min(len(keys), n_emb)
         if n_take:
-            kind = _capi.SRC_F32_BITS if floats == 512 else _capi.SRC_F32_OFFSET
+            if is_ubinary(cf.header):
+                kind = _capi.SRC_U8
+            else:
+                kind = _capi.SRC_F32_BITS if floats == 512 else _capi.SRC_F32_OFFSET
             width = floats // 8 if floats == 512 else floats
             off, length = cf.embeddings_section
             c = self._ensure_corpus(width)
@@ -429,20 +434,25 @@ class VLite:
         rows = [self._row_of[k] for k in keys]
         if keys and any(r is None for r in rows):
             raise ValueError("cannot save: some chunks have no stored vector")
-        per_file = max(1, min(self.max_rows_per_file, ((1 << 32) - 1) // (width * 4)))
+        compact = self.ctx_dtype == "ubinary"
+        per_file = max(1, min(self.max_rows_per_file, ((1 << 32) - 1) // (width * (1 if compact else 4))))
         n_parts = max(1, -(-len(keys) // per_file))
         all_rows = self._corpus.read() if keys else None                     # one D2H copy
         for part in range(n_parts):
             cf = self.ctx.create(self._part_name(part))
             cf.set_header(embedding_model="mixedbread-ai/mxbai-embed-large-v1", embedding_size=width,
-                          embedding_dtype=self.model.embedding_dtype, context_length=self.model.context_length)
+                          embedding_dtype="ubinary" if compact else self.model.embedding_dtype,
+                          context_length=self.model.context_length)
             if n_parts > 1:
                 cf.header["parts"] = n_parts
                 cf.header["part"] = part
             lo, hi = part * per_file, min(len(keys), (part + 1) * per_file)
             if hi > lo:
                 sel = np.asarray(rows[lo:hi])
-                cf.set_embeddings_array(to_reference_encoding(all_rows[sel]).astype(np.float32))
+                if compact:
+                    cf.set_embeddings_array(all_rows[sel])
+                else:
+                    cf.set_embeddings_array(to_reference_encoding(all_rows[sel]).astype(np.float32))
             for k in keys[lo:hi]:
                 cf.add_context(self._texts[k])
                 cf.add_metadata(k, self._metas[k])
