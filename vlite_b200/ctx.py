@@ -94,93 +94,101 @@ class CtxFile:
     def add_metadata(self, key: str, value: Union[int, float, str]):
         self.metadata[key] = value
 
-    # ---- writer (vlite/ctx.py:55-82) ----
-    def save(self):
+    # ---- writer: byte layout of vlite/ctx.py:55-82 ----
+    def _embedding_payload(self) -> bytes:
+        """Rows as one contiguous block; every row is cut to the stored width like ``emb[:64]``
+        (vlite/ctx.py:70) and a shorter row is the same struct.error the reference raises."""
         width = row_floats_for(self.header)
-        if width == 512:
-            width = LEGACY_ROW_FLOATS
+        width = LEGACY_ROW_FLOATS if width == 512 else width
         elem = np.dtype("u1") if is_ubinary(self.header) else np.dtype("<f4")
-        with open(self.file_path, "wb") as f:
-            f.write(self.MAGIC_NUMBER)
-            f.write(struct.pack("<I", self.VERSION))
-            header_json = json.dumps(self.header).encode("utf-8")
-            f.write(struct.pack("<II", CtxSectionType.HEADER.value, len(header_json)))
-            f.write(header_json)
-            n_emb = len(self.embeddings)
-            if n_emb:                                        # section omitted when empty (ctx.py:68)
-                if isinstance(self.embeddings, np.ndarray):
-                    arr = np.ascontiguousarray(self.embeddings[:, :width], dtype=elem)
-                else:
-                    rows = []
-                    for emb in self.embeddings:
-                        r = np.asarray(emb, dtype=elem).reshape(-1)[:width]   # emb[:64] (ctx.py:70)
-                        if r.shape[0] != width:
-                            raise struct.error(f"pack expected {width} items for packing (got {r.shape[0]})")
-                        rows.append(r)
-                    arr = np.stack(rows)
-                data_len = arr.shape[0] * width * elem.itemsize
-                if data_len >= 1 << 32:
-                    raise ValueError("EMBEDDINGS section exceeds the u32 length field of CTXF v1 "
-                                     "(at most 16.7M rows of 64 floats); split the collection")
-                f.write(struct.pack("<II", CtxSectionType.EMBEDDINGS.value, data_len))
-                f.write(arr.tobytes())
-            contexts_data = b"".join(
-                struct.pack("<I", len(c.encode("utf-8"))) + c.encode("utf-8") for c in self.contexts)
-            f.write(struct.pack("<II", CtxSectionType.CONTEXTS.value, len(contexts_data)))
-            f.write(contexts_data)
-            metadata_json = json.dumps(self.metadata).encode("utf-8")
-            f.write(struct.pack("<II", CtxSectionType.METADATA.value, len(metadata_json)))
-            f.write(metadata_json)
+        if isinstance(self.embeddings, np.ndarray):
+            block = np.ascontiguousarray(self.embeddings[:, :width], dtype=elem)
+        else:
+            block = np.empty((len(self.embeddings), width), dtype=elem)
+            for i, emb in enumerate(self.embeddings):
+                row = np.asarray(emb, dtype=elem).reshape(-1)[:width]
+                if row.shape[0] != width:
+                    raise struct.error(f"pack expected {width} items for packing (got {row.shape[0]})")
+                block[i] = row
+        if block.nbytes >= 1 << 32:
+            raise ValueError("EMBEDDINGS section exceeds the u32 length field of CTXF v1 "
+                             "(at most 16.7M rows of 64 floats); split the collection")
+        return block.tobytes()
 
-    # ---- reader (vlite/ctx.py:85-139) ----
+    def save(self):
+        def utf8(text):
+            return text.encode("utf-8")
+
+        sections = [(CtxSectionType.HEADER, utf8(json.dumps(self.header)))]
+        if len(self.embeddings):                              # section omitted when empty (ctx.py:68)
+            sections.append((CtxSectionType.EMBEDDINGS, self._embedding_payload()))
+        packed_contexts = bytearray()
+        for text in self.contexts:
+            raw = utf8(text)
+            packed_contexts += struct.pack("<I", len(raw)) + raw
+        sections.append((CtxSectionType.CONTEXTS, bytes(packed_contexts)))
+        sections.append((CtxSectionType.METADATA, utf8(json.dumps(self.metadata))))
+        with open(self.file_path, "wb") as out:
+            out.write(self.MAGIC_NUMBER + struct.pack("<I", self.VERSION))
+            for kind, payload in sections:
+                out.write(struct.pack("<II", kind.value, len(payload)))
+                out.write(payload)
+
+    # ---- reader: accepts exactly what vlite/ctx.py:85-139 accepts ----
     def load(self, materialise: bool = True):
         """Parse the file.  ``materialise=False`` leaves the EMBEDDINGS payload on disk (only its
-        offset/length are recorded in ``embeddings_section``) for streaming to the device."""
-        try:
-            f = open(self.file_path, "rb")
-        except FileNotFoundError:
-            return                                           # swallowed, like vlite/ctx.py:138-139
-        with f:
-            magic = f.read(len(self.MAGIC_NUMBER))
-            if magic != self.MAGIC_NUMBER:
-                raise ValueError(f"Invalid magic number: {magic}")
-            version = struct.unpack("<I", f.read(4))[0]
+        offset/length are recorded in ``embeddings_section``) for streaming to the device.
+        A missing file is not an error (vlite/ctx.py:138-139); bad magic, version or section type
+        raise the reference's ValueErrors (vlite/ctx.py:95-99, :137)."""
+        if not os.path.exists(self.file_path):
+            return
+        size = os.path.getsize(self.file_path)
+        with open(self.file_path, "rb") as src:
+            preamble = src.read(8)
+            if preamble[:4] != self.MAGIC_NUMBER:
+                raise ValueError(f"Invalid magic number: {preamble[:4]}")
+            (version,) = struct.unpack("<I", preamble[4:8])
             if version != self.VERSION:
                 raise ValueError(f"Unsupported version: {version}")
-            while True:
-                section_header = f.read(8)
-                if not section_header:
-                    break
-                section_type, section_length = struct.unpack("<II", section_header)
-                if section_type == CtxSectionType.HEADER.value:
-                    self.header = json.loads(f.read(section_length).decode("utf-8"))
-                elif section_type == CtxSectionType.EMBEDDINGS.value:
-                    self.embeddings_section = (f.tell(), section_length)
-                    if materialise and section_length:
-                        width = row_floats_for(self.header)
-                        elem = np.dtype("u1") if is_ubinary(self.header) else np.dtype("<f4")
-                        data = f.read(section_length)
-                        n = len(data) // (width * elem.itemsize)         # floor (ctx.py:115)
-                        self._emb_array = np.frombuffer(data, dtype=elem, count=n * width).reshape(n, width)
-                        self.embeddings = self._emb_array
-                    else:
-                        f.seek(section_length, os.SEEK_CUR)
-                elif section_type == CtxSectionType.CONTEXTS.value:
-                    data = f.read(section_length)
-                    self.contexts = []
-                    off = 0
-                    while off < len(data):
-                        (clen,) = struct.unpack_from("<I", data, off)
-                        off += 4
-                        try:
-                            self.contexts.append(data[off:off + clen].decode("utf-8"))
-                        except UnicodeDecodeError:
-                            pass                             # logged and skipped (ctx.py:130-131)
-                        off += clen
-                elif section_type == CtxSectionType.METADATA.value:
-                    self.metadata = json.loads(f.read(section_length).decode("utf-8"))
+            pos = 8
+            while pos + 8 <= size:
+                src.seek(pos)
+                kind, length = struct.unpack("<II", src.read(8))
+                body = pos + 8
+                pos = body + length
+                if kind == CtxSectionType.EMBEDDINGS.value:
+                    self.embeddings_section = (body, length)
+                    if materialise and length:
+                        self._materialise(src.read(length))
+                elif kind == CtxSectionType.HEADER.value:
+                    self.header = json.loads(src.read(length).decode("utf-8"))
+                elif kind == CtxSectionType.CONTEXTS.value:
+                    self.contexts = self._split_contexts(src.read(length))
+                elif kind == CtxSectionType.METADATA.value:
+                    self.metadata = json.loads(src.read(length).decode("utf-8"))
                 else:
-                    raise ValueError(f"Unknown section type: {section_type}")
+                    raise ValueError(f"Unknown section type: {kind}")
+
+    def _materialise(self, payload: bytes):
+        width = row_floats_for(self.header)
+        elem = np.dtype("u1") if is_ubinary(self.header) else np.dtype("<f4")
+        n = len(payload) // (width * elem.itemsize)               # whole rows only (ctx.py:115)
+        self._emb_array = np.frombuffer(payload, dtype=elem, count=n * width).reshape(n, width)
+        self.embeddings = self._emb_array
+
+    @staticmethod
+    def _split_contexts(payload: bytes) -> List[str]:
+        """(u32 length, utf-8 bytes)*; an undecodable string is dropped (ctx.py:130-131)."""
+        out, pos = [], 0
+        while pos < len(payload):
+            (n,) = struct.unpack_from("<I", payload, pos)
+            pos += 4
+            try:
+                out.append(payload[pos:pos + n].decode("utf-8"))
+            except UnicodeDecodeError:
+                pass
+            pos += n
+        return out
 
     @property
     def n_embeddings(self) -> int:
