@@ -71,10 +71,10 @@ def test_large_k_multipass(gpu, k):
         _check(c, corpus, queries, k, HAMMING)
 
 
-@pytest.mark.parametrize("k", [300, 1000, 2048])
+@pytest.mark.parametrize("k", [33, 100, 300, 1000, 2048])
 @pytest.mark.parametrize("period", [0, 700])
 def test_large_k_sampled_path_and_fallback(gpu, k, period):
-    """k > 256 on a corpus larger than the candidate buffer: sampled threshold + collect + select.
+    """k > 32 on a corpus larger than the candidate buffer: sampled threshold + collect + select.
     period=700 makes every score value shared by ~290 rows, so buffers overflow and the exact
     multi-pass fallback must answer -- the result is the same either way."""
     n = 200_000
