@@ -19,7 +19,9 @@
  *     the same contract the reference's single mutable VLite object has
  *     (vlite/server.py:14).  When every pointer passed to a call is device
  *     memory the call only ENQUEUES work on the handle's stream and returns
- *     without synchronising; with any host pointer it returns after the
+ *     without synchronising (exception: vl_search with k > 32 waits for its
+ *     own kernels, because it checks a device flag to decide whether the exact
+ *     fallback pass is needed); with any host pointer it returns after the
  *     data has landed.
  *   - results are ordered ascending by (score, global row); slots past the
  *     number of eligible rows hold VL_SENTINEL_SCORE / VL_SENTINEL_ROW.
