@@ -625,7 +625,8 @@ int search_large_k(vl_corpus* c, ScanParams p, int n_queries, int k, int metric,
     // sample list length: enough hits at the threshold for a tight estimate (relative spread
     // 1/sqrt(ks)) without paying for long lists; about 3k corpus rows are expected at or below it
     const int ks = std::min(kLargeKSample, std::max(16, k / 4));
-    const uint32_t stride = std::max<uint32_t>(1, (3u * (uint32_t)k) / (uint32_t)ks);
+    // sample every `stride`-th tile: at least 3k expected candidates, and never more than 5 % of a scan
+    const uint32_t stride = std::max<uint32_t>(20u, (3u * (uint32_t)k) / (uint32_t)ks);
     const uint32_t visited = (p.n_tiles + stride - 1) / stride;
     TRY(c->lk_keys.ensure(key_bytes));
     TRY(c->lk_misc.ensure((size_t)n_queries * (4 + 4 + kLargeKSample * 12) + 64));

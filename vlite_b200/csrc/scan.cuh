@@ -71,6 +71,61 @@ struct ScanParams {
     uint32_t one;  // == 1, opaque to ptxas: keeps "acc += popc" on IMAD (FMA pipe) instead of IADD3 (ALU pipe)
 };
 
+// ---- warp-wide selection network for k <= 32: keys are (score << 32 | local row), unique per row ----
+__device__ __forceinline__ uint64_t warp_sort32(uint64_t key, int lane) {
+    // bitonic sort, ascending across the 32 lanes
+#pragma unroll
+    for (int size = 2; size <= 32; size <<= 1) {
+#pragma unroll
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            const uint64_t other = __shfl_xor_sync(kFullMask, key, stride);
+            const bool take_min = (((lane & size) == 0) == ((lane & stride) == 0));
+            key = take_min ? min(key, other) : max(key, other);
+        }
+    }
+    return key;
+}
+__device__ __forceinline__ uint64_t warp_bitonic_merge32(uint64_t key, int lane) {
+    // input: a bitonic sequence across the lanes; output: ascending
+#pragma unroll
+    for (int stride = 16; stride > 0; stride >>= 1) {
+        const uint64_t other = __shfl_xor_sync(kFullMask, key, stride);
+        key = ((lane & stride) == 0) ? min(key, other) : max(key, other);
+    }
+    return key;
+}
+// Merge up to 32 new candidates (one per lane, ~0 = none) into the warp's sorted k-list (k <= 32)
+// in one go: sort the newcomers, pair them in reverse with the list (the element-wise minimum is a
+// bitonic sequence holding the 32 smallest keys of the union), bitonic-merge, keep the first k.
+// Returns the new k-th best score.  Ordering is by the key itself, so ties break on the row index
+// no matter in which order rows arrive.
+__device__ __noinline__ uint32_t warp_list_merge32(uint32_t* ls, uint32_t* li, int k, uint64_t cand, int lane) {
+    uint64_t cur = (lane < k) ? (((uint64_t)ls[lane] << 32) | li[lane]) : ~0ull;
+    unsigned have = __ballot_sync(kFullMask, cand != ~0ull);
+    if (__popc(have) <= 8) {
+        // few newcomers (the steady state is one): slide each into the register-held list --
+        // a vote, a shuffle-up and a select per candidate instead of a 20-stage sorting network
+        while (have) {
+            const int src = __ffs(have) - 1;
+            have &= have - 1;
+            const uint64_t key = __shfl_sync(kFullMask, cand, src);
+            const int pos = __popc(__ballot_sync(kFullMask, cur < key));   // keys are unique
+            const uint64_t up = __shfl_up_sync(kFullMask, cur, 1);
+            cur = (lane > pos) ? up : (lane == pos ? key : cur);
+        }
+    } else {
+        cand = warp_sort32(cand, lane);
+        const uint64_t rev = __shfl_sync(kFullMask, cand, 31 - lane);
+        cur = warp_bitonic_merge32(min(cur, rev), lane);
+    }
+    if (lane < k) {
+        ls[lane] = (uint32_t)(cur >> 32);
+        li[lane] = (uint32_t)cur;
+    }
+    __syncwarp();
+    return __shfl_sync(kFullMask, (uint32_t)(cur >> 32), k - 1);
+}
+
 // Insert (s, idx) into the warp's sorted list (ascending score; an equal score goes after the
 // existing equals because rows arrive in ascending index order).  Returns the new threshold.
 __device__ __noinline__ uint32_t warp_list_insert(uint32_t* ls, uint32_t* li, int k, uint32_t s, uint32_t idx,
@@ -374,8 +429,38 @@ scan_topk_kernel(const __grid_constant__ CUtensorMap tmap, const ScanParams p) {
                 hit |= best < thr[c];
             }
 
-            if (__any_sync(kFullMask, hit)) {
-                // Rare path, kept small on purpose (a compact loop, not R*C unrolled copies) so it
+            if (__any_sync(kFullMask, hit) && !collect && k <= 32) {
+                // Rare path of the common case (k-lists with k <= 32): statically indexed, one
+                // warp-uniform vote per query, then one list merge per row group that has a hit.
+                const uint32_t row_base = t * kTileRows + (uint32_t)row_in_tile0;
+#pragma unroll
+                for (int c = 0; c < C; ++c) {
+                    bool hq = false;
+#pragma unroll
+                    for (int r = 0; r < R; ++r) hq |= valid[r] && (acc[r][c] < thr[c]);
+                    if (!__any_sync(kFullMask, hq)) continue;
+                    uint32_t tc = s_thr[warp * C + c];
+#pragma unroll
+                    for (int r = 0; r < R; ++r) {
+                        const uint32_t sc = acc[r][c];
+                        const uint32_t idx = row_base + (uint32_t)(r * 32 + lane);
+                        bool mine = valid[r] && (sc < min(thr[c], tc));
+                        if (has_cursor && mine) {
+                            const uint32_t cs = s_cursor[2 * (wq * C + c)];
+                            const uint32_t cr = s_cursor[2 * (wq * C + c) + 1];
+                            mine = (sc > cs) || (sc == cs && idx > cr);
+                        }
+                        if (__any_sync(kFullMask, mine))
+                            tc = warp_list_merge32(ls + c * k, li + c * k, k,
+                                                   mine ? (((uint64_t)sc << 32) | idx) : ~0ull, lane);
+                    }
+                    if (lane == 0) s_thr[warp * C + c] = tc;
+                    thr[c] = min(thr[c], tc);
+                }
+                __syncwarp();
+                dirty = true;
+            } else if (__any_sync(kFullMask, hit)) {
+                // Rare path of the other modes (collect, k > 32), kept small on purpose (a compact loop, not R*C unrolled copies) so it
                 // does not evict the hot loop from the instruction cache.  Bit b = c*R + r of `hm`
                 // marks a candidate; queries (c) are independent, rows ascend with (r, lane).
                 uint32_t hm = 0;
