@@ -30,8 +30,8 @@
 
 namespace vl {
 
-constexpr int kTileRows = 256;
-constexpr int kMaskWordsPerTile = kTileRows / 32;  // 8 words = 32 bytes
+constexpr int kTileRows = 256;      // rows of one TMA box
+constexpr int kMaxStageRows = 512;  // a pipeline stage holds 1 or 2 boxes; capacity is padded to this
 constexpr int kScanWarps = 8;
 constexpr int kScanThreads = kScanWarps * 32;
 constexpr int kWarpListMaxK = 128;
@@ -160,10 +160,12 @@ __device__ __noinline__ uint32_t warp_list_insert(uint32_t* ls, uint32_t* li, in
     return ls[k - 1];
 }
 
-template <int W, int C, int WQ>
+template <int W, int C, int WQ, int TPS>
 struct ScanCfg {
     static constexpr int WR = kScanWarps / WQ;
-    static constexpr int RPW = kTileRows / WR;            // rows of a tile one warp scores
+    static constexpr int TR = kTileRows * TPS;            // rows per pipeline stage (TPS TMA boxes)
+    static constexpr int MASKW = TR / 32;                 // mask words per stage
+    static constexpr int RPW = TR / WR;                   // rows of a stage one warp scores
 #ifndef VL_RMAX
 #define VL_RMAX 4
 #endif
@@ -171,10 +173,11 @@ struct ScanCfg {
     static constexpr int STEPS = RPW / (32 * R);
     static constexpr int QT = C * WQ;                     // queries per CTA
     static constexpr int CHUNKS = W / 16;
-    static constexpr int TILE_BYTES = kTileRows * W;
-    static constexpr int STAGE_BYTES = TILE_BYTES + 2 * kMaskWordsPerTile * 4;
+    static constexpr int TILE_BYTES = TR * W;
+    static constexpr int STAGE_BYTES = TILE_BYTES + 2 * MASKW * 4;
     static_assert(W == 32 || W == 64 || W == 128 || W == 256, "row width");
     static_assert(WQ == 1 || WQ == 2 || WQ == 4 || WQ == 8, "warps along queries");
+    static_assert(TPS == 1 || TPS == 2, "boxes per stage");
     static size_t smem_bytes(int stages, int k) {
         return (size_t)stages * STAGE_BYTES + (size_t)QT * W + (size_t)kScanWarps * C * k * 8 +
                (size_t)QT * 8 + (size_t)kScanWarps * C * 4 + (size_t)stages * 16;
@@ -224,12 +227,12 @@ __device__ __forceinline__ uint32_t score_chunk_pair(const uint4& ra, const uint
     }
 }
 
-template <int W, int METRIC, int C, int WQ>
+template <int W, int METRIC, int C, int WQ, int TPS>
 __global__ void __launch_bounds__(kScanThreads, 2)
 scan_topk_kernel(const __grid_constant__ CUtensorMap tmap, const ScanParams p) {
-    using Cfg = ScanCfg<W, C, WQ>;
+    using Cfg = ScanCfg<W, C, WQ, TPS>;
     constexpr int WR = Cfg::WR, RPW = Cfg::RPW, R = Cfg::R, STEPS = Cfg::STEPS, QT = Cfg::QT;
-    constexpr int CHUNKS = Cfg::CHUNKS, TILE_BYTES = Cfg::TILE_BYTES;
+    constexpr int CHUNKS = Cfg::CHUNKS, TILE_BYTES = Cfg::TILE_BYTES, TR = Cfg::TR, MASKW = Cfg::MASKW;
     static_assert(CHUNKS % 2 == 0, "rows are scored two 16 B chunks at a time");
 
     extern __shared__ __align__(1024) uint8_t smem[];  // swizzled TMA tiles want 1024 B alignment
@@ -237,7 +240,7 @@ scan_topk_kernel(const __grid_constant__ CUtensorMap tmap, const ScanParams p) {
     const int k = p.k;
     uint8_t* s_tiles = smem;                                                        // stages x TILE_BYTES
     uint32_t* s_masks = reinterpret_cast<uint32_t*>(smem + (size_t)stages * TILE_BYTES);  // stages x 16 words
-    uint8_t* s_queries = reinterpret_cast<uint8_t*>(s_masks + stages * 2 * kMaskWordsPerTile);
+    uint8_t* s_queries = reinterpret_cast<uint8_t*>(s_masks + stages * 2 * MASKW);
     uint32_t* s_lscore = reinterpret_cast<uint32_t*>(s_queries + QT * W);           // [8][C][k]
     uint32_t* s_lidx = s_lscore + kScanWarps * C * k;
     uint32_t* s_cursor = s_lidx + kScanWarps * C * k;                                // [QT][2]
@@ -288,16 +291,18 @@ scan_topk_kernel(const __grid_constant__ CUtensorMap tmap, const ScanParams p) {
     auto issue_tile = [&](uint32_t i) {
         const int s = i % stages;
         const uint32_t t = (tile_begin + i) * p.tile_stride;
-        const uint32_t row0 = t * kTileRows;
-        const uint32_t mask_bytes = kMaskWordsPerTile * 4;
+        const uint32_t row0 = t * TR;
+        const uint32_t mask_bytes = MASKW * 4;
         // the tile arrives hardware-swizzled (16 B chunk index ^= row bits): rows past n_rows are
         // zero-filled by the TMA unit and the whole box is always counted
         mbar_arrive_expect_tx(&s_full[s], TILE_BYTES + mask_bytes + (p.filter ? mask_bytes : 0));
-        tma_load_2d(s_tiles + (size_t)s * TILE_BYTES, &tmap, 0, (int)row0, &s_full[s], policy);
-        uint32_t* m = s_masks + s * 2 * kMaskWordsPerTile;
-        bulk_g2s(m, p.live + (size_t)t * kMaskWordsPerTile, mask_bytes, &s_full[s]);
-        if (p.filter)
-            bulk_g2s(m + kMaskWordsPerTile, p.filter + (size_t)t * kMaskWordsPerTile, mask_bytes, &s_full[s]);
+#pragma unroll
+        for (int b = 0; b < TPS; ++b)
+            tma_load_2d(s_tiles + (size_t)s * TILE_BYTES + (size_t)b * kTileRows * W, &tmap, 0,
+                        (int)(row0 + b * kTileRows), &s_full[s], policy);
+        uint32_t* m = s_masks + s * 2 * MASKW;
+        bulk_g2s(m, p.live + (size_t)t * MASKW, mask_bytes, &s_full[s]);
+        if (p.filter) bulk_g2s(m + MASKW, p.filter + (size_t)t * MASKW, mask_bytes, &s_full[s]);
     };
     if (threadIdx.x == 0) {
         const uint32_t pre = min((uint32_t)stages, my_tiles);
@@ -375,7 +380,7 @@ scan_topk_kernel(const __grid_constant__ CUtensorMap tmap, const ScanParams p) {
             if (tau_mine) tau_pref = __ldcg(tau_ptr);
         }
         mbar_wait(&s_full[s], (i / stages) & 1);
-        const uint32_t* m = s_masks + s * 2 * kMaskWordsPerTile;
+        const uint32_t* m = s_masks + s * 2 * MASKW;
 
 #pragma unroll 1
         for (int st = 0; st < STEPS; ++st) {
@@ -384,7 +389,7 @@ scan_topk_kernel(const __grid_constant__ CUtensorMap tmap, const ScanParams p) {
 #pragma unroll
             for (int r = 0; r < R; ++r) {
                 uint32_t w = m[row_in_tile0 / 32 + r];
-                if (has_filter) w &= m[kMaskWordsPerTile + row_in_tile0 / 32 + r];
+                if (has_filter) w &= m[MASKW + row_in_tile0 / 32 + r];
                 valid[r] = (w >> lane) & 1u;
             }
             // masked rows start from a bias no real score reaches (max 255 * W), so the hot
@@ -432,7 +437,7 @@ scan_topk_kernel(const __grid_constant__ CUtensorMap tmap, const ScanParams p) {
             if (__any_sync(kFullMask, hit) && !collect && k <= 32) {
                 // Rare path of the common case (k-lists with k <= 32): statically indexed, one
                 // warp-uniform vote per query, then one list merge per row group that has a hit.
-                const uint32_t row_base = t * kTileRows + (uint32_t)row_in_tile0;
+                const uint32_t row_base = t * TR + (uint32_t)row_in_tile0;
 #pragma unroll
                 for (int c = 0; c < C; ++c) {
                     bool hq = false;
@@ -470,7 +475,7 @@ scan_topk_kernel(const __grid_constant__ CUtensorMap tmap, const ScanParams p) {
                     for (int r = 0; r < R; ++r)
                         if (valid[r] && (acc[r][c] < thr[c])) hm |= 1u << (c * R + r);
                 uint32_t any = __reduce_or_sync(kFullMask, hm);
-                const uint32_t row_base = t * kTileRows + (uint32_t)row_in_tile0;
+                const uint32_t row_base = t * TR + (uint32_t)row_in_tile0;
                 while (any) {
                     const int b = __ffs(any) - 1;
                     any &= any - 1;
