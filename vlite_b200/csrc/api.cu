@@ -428,10 +428,20 @@ int launch_scan_cfg(vl_corpus* c, ScanParams& p, int n_queries, int k, ScanPlan*
     while (stages > 1 && total(stages) > max_smem) --stages;
     const size_t smem = total(stages);
     if (smem > max_smem) return fail(VL_EINVAL, "k=%d needs %zu B of shared memory per CTA (max %zu)", k, smem, max_smem);
-    CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    // per-kernel launch attributes are set (and the occupancy asked for) once per shared-memory size
+    static thread_local size_t cached_smem[64] = {};
+    static thread_local int cached_occ[64] = {};
     int occ = 0;
-    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kScanThreads, smem));
-    if (occ < 1) return fail(VL_ECUDA, "scan kernel does not fit on an SM (smem %zu)", smem);
+    const int dev_slot = c->device & 63;
+    if (cached_smem[dev_slot] == smem && cached_occ[dev_slot] > 0) {
+        occ = cached_occ[dev_slot];
+    } else {
+        CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kScanThreads, smem));
+        if (occ < 1) return fail(VL_ECUDA, "scan kernel does not fit on an SM (smem %zu)", smem);
+        cached_smem[dev_slot] = smem;
+        cached_occ[dev_slot] = occ;
+    }
 
     const int T = (n_queries + Cfg::QT - 1) / Cfg::QT;
     const long slots = (long)c->sms * occ;
@@ -1245,28 +1255,27 @@ extern "C" int vl_quantize_binary(int device, void* cuda_stream, const float* x_
     cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
     const bool x_dev = is_device_ptr(x_any), o_dev = is_device_ptr(out_any);
     const size_t in_bytes = n * (size_t)dims * 4, out_bytes = n * (size_t)dims / 8;
-    void *xin = nullptr, *xout = nullptr;
+    // grow-only per-device scratch shared by the handle-less entry points (one call at a time per device)
+    static std::mutex mu[64];
+    static DevBuf scratch_in[64], scratch_out[64];
+    std::lock_guard<std::mutex> lock(mu[device & 63]);
     const float* src = x_any;
     uint8_t* dst = out_any;
     if (!x_dev) {
-        CU(cudaMalloc(&xin, in_bytes));
-        CU(cudaMemcpyAsync(xin, x_any, in_bytes, cudaMemcpyHostToDevice, st));
-        src = static_cast<const float*>(xin);
+        TRY(scratch_in[device & 63].ensure(in_bytes));
+        CU(cudaMemcpyAsync(scratch_in[device & 63].p, x_any, in_bytes, cudaMemcpyHostToDevice, st));
+        src = static_cast<const float*>(scratch_in[device & 63].p);
     }
     if (!o_dev) {
-        CU(cudaMalloc(&xout, out_bytes));
-        dst = static_cast<uint8_t*>(xout);
+        TRY(scratch_out[device & 63].ensure(out_bytes));
+        dst = static_cast<uint8_t*>(scratch_out[device & 63].p);
     }
     const uint64_t n_words = out_bytes / 4;
     repack_f32_bits_kernel<true><<<grid_for(n_words, 256, sms), 256, 0, st>>>(src, n_words,
                                                                             reinterpret_cast<uint32_t*>(dst), nullptr);
     LAUNCHED();
     if (!o_dev) CU(cudaMemcpyAsync(out_any, dst, out_bytes, cudaMemcpyDeviceToHost, st));
-    if (!x_dev || !o_dev) {
-        CU(cudaStreamSynchronize(st));
-        if (xin) cudaFree(xin);
-        if (xout) cudaFree(xout);
-    }
+    if (!x_dev || !o_dev) CU(cudaStreamSynchronize(st));
     return VL_OK;
 }
 
