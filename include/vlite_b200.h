@@ -150,6 +150,14 @@ int vl_merge_topk(int device, void* cuda_stream, const uint32_t* scores_dev, con
                   uint64_t score_list_stride, uint64_t row_list_stride,
                   uint32_t* out_score_dev, uint64_t* out_row_dev);
 
+/* rewrite LOCAL rows (as a shard with base_row 0 returns them) into GLOBAL rows for a shard made of
+ * several appended segments: segment i holds local rows [seg_local[i], seg_local[i+1]) and global
+ * rows seg_global[i] + (local - seg_local[i]).  Tables ascend; all pointers device memory.
+ * (Row-sharded collections: appends go to the least-full shard with the global base fixed at append
+ * time; the reference has no counterpart.) */
+int vl_map_rows(int device, void* cuda_stream, uint64_t* rows_dev, uint64_t n,
+                const uint64_t* seg_local_dev, const uint64_t* seg_global_dev, int n_segments);
+
 /* ---- rescore (north-star piece 3; no reference implementation -- nearest
  * code is the unused cos_sim, vlite/utils.py:205-208) ----------------------- */
 #define VL_QTYPE_F32 0

@@ -6,8 +6,8 @@ Exports the same two names the reference package does (vlite/__init__.py): ``VLi
 __version__ = "0.1.0"
 
 from .ctx import Ctx, CtxFile, CtxSectionType  # noqa: E402,F401
-from .main import VLite  # noqa: E402,F401
+from .main import ShardedVLite, VLite  # noqa: E402,F401
 from .model import EmbeddingModel  # noqa: E402,F401
 from ._capi import Corpus  # noqa: E402,F401
 
-__all__ = ["VLite", "EmbeddingModel", "Ctx", "CtxFile", "CtxSectionType", "Corpus"]
+__all__ = ["VLite", "ShardedVLite", "EmbeddingModel", "Ctx", "CtxFile", "CtxSectionType", "Corpus"]

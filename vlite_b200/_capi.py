@@ -81,6 +81,7 @@ def load():
         "vl_scores": (c_int, [c_void_p, c_void_p, c_int, c_u64, c_u64, c_void_p]),
         "vl_merge_topk": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_u64, c_u64,
                                   c_void_p, c_void_p]),
+        "vl_map_rows": (c_int, [c_int, c_void_p, c_void_p, c_u64, c_void_p, c_void_p, c_int]),
         "vl_rescore": (c_int, [c_void_p, c_void_p, c_u64, c_int, c_void_p, c_int, c_void_p, c_int, c_int, c_int,
                                c_void_p, c_void_p]),
         "vl_quantize_binary": (c_int, [c_int, c_void_p, c_void_p, c_u64, c_int, c_void_p]),
@@ -312,6 +313,13 @@ def merge_topk(scores_dev, rows_dev, n_lists: int, n_queries: int, k_in: int, k_
     check(load().vl_merge_topk(device, ctypes.c_void_p(stream or 0), ptr(scores_dev), ptr(rows_dev), n_lists,
                                n_queries, k_in, k_out, score_list_stride, row_list_stride,
                                ptr(out_scores_dev), ptr(out_rows_dev)))
+
+
+def map_rows(rows_dev, n: int, seg_local_dev, seg_global_dev, n_segments: int, device: int = 0,
+             stream: int | None = None):
+    """Rewrite local rows into global rows in place (device tensors); see vl_map_rows."""
+    check(load().vl_map_rows(device, ctypes.c_void_p(stream or 0), ptr(rows_dev), n, ptr(seg_local_dev),
+                             ptr(seg_global_dev), n_segments))
 
 
 def quantize_binary(x, out=None, device: int = 0, stream: int | None = None):

@@ -1168,6 +1168,19 @@ extern "C" int vl_merge_topk(int device, void* cuda_stream, const uint32_t* scor
     return rc;
 }
 
+extern "C" int vl_map_rows(int device, void* cuda_stream, uint64_t* rows_dev, uint64_t n, const uint64_t* seg_local_dev,
+                           const uint64_t* seg_global_dev, int n_segments) {
+    if (!rows_dev || !seg_local_dev || !seg_global_dev) return fail(VL_EINVAL, "NULL argument");
+    if (n_segments < 1) return fail(VL_EINVAL, "need at least one segment");
+    TRY(check_device(device, nullptr));
+    DeviceGuard g(device);
+    if (n == 0) return VL_OK;
+    map_rows_kernel<<<(unsigned)((n + 255) / 256), 256, 0, static_cast<cudaStream_t>(cuda_stream)>>>(
+        rows_dev, n, seg_local_dev, seg_global_dev, n_segments);
+    LAUNCHED();
+    return VL_OK;
+}
+
 // =============================== rescore ===============================
 extern "C" int vl_rescore(vl_corpus* c, const int8_t* docs_i8_dev, uint64_t n_docs, int dims, const void* queries_any,
                           int qtype, const uint64_t* cand_rows_any, int n_queries, int n_cand, int k,

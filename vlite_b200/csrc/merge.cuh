@@ -95,6 +95,24 @@ merge_topk_kernel(const uint32_t* __restrict__ scores, const uint64_t* __restric
     }
 }
 
+// Local -> global row numbers for a shard that holds several appended segments (base
+// offsets are fixed at append time).  Segment i covers local rows [seg_local[i], seg_local[i+1]) and
+// global rows seg_global[i] + (local - seg_local[i]); both tables ascend, so a shard's local order is
+// its global order and the local top-k stays the global top-k of that shard.
+__global__ void map_rows_kernel(uint64_t* __restrict__ rows, uint64_t n, const uint64_t* __restrict__ seg_local,
+                                const uint64_t* __restrict__ seg_global, int n_seg) {
+    const uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint64_t r = rows[i];
+    if (r == kSentinelRow) return;
+    int lo = 0, hi = n_seg - 1;                  // last segment whose start is <= r
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (seg_local[mid] <= r) lo = mid; else hi = mid - 1;
+    }
+    rows[i] = seg_global[lo] + (r - seg_local[lo]);
+}
+
 // cursor for the next pass of a multi-pass (large k) search: the last key already emitted
 __global__ void cursor_update_kernel(const uint32_t* __restrict__ out_scores, const uint64_t* __restrict__ out_rows,
                                      int n_queries, int out_stride, int last_pos, uint64_t base_row,

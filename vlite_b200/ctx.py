@@ -214,8 +214,7 @@ class CtxFile:
 class Ctx:                                                   # vlite/ctx.py:164-184
     def __init__(self, directory="contexts"):
         self.directory = directory
-        if not os.path.exists(directory):
-            os.makedirs(directory)
+        os.makedirs(directory, exist_ok=True)      # several ranks may create it at once
 
     def get(self, user):
         return os.path.join(self.directory, f"{user}.ctx")

@@ -143,6 +143,10 @@ class VLite:
         self._load_collection()
 
     # ------------------------------------------------------------------ internals
+    def _new_ids(self, n: int):
+        """fresh item ids (uuid4 like vlite/main.py:76, :261)"""
+        return [str(uuid4()) for _ in range(n)]
+
     def _ensure_corpus(self, width: int):
         if self._corpus is None:
             self._width = self._width or width
@@ -267,7 +271,7 @@ class VLite:
                 text_content = item
                 item_metadata = {}
             if item_id is None:
-                item_id = str(uuid4())
+                item_id = self._new_ids(1)[0]
             item_metadata.update(metadata or {})
             chunks = chop_and_chunk(text_content, fast=fast) if need_chunks else [text_content]
             all_chunks.extend(chunks)
@@ -413,14 +417,14 @@ class VLite:
             raise ValueError("The number of texts and metadatas must be the same.")
         if len(texts):
             first = self._append_vectors(np.asarray(embeddings))
-            for i, (text, md) in enumerate(zip(texts, metadatas)):
-                self._register(f"{uuid4()}_0", text, md, first + i)
+            for i, (text, md, uid) in enumerate(zip(texts, metadatas, self._new_ids(len(texts)))):
+                self._register(f"{uid}_0", text, md, first + i)
         self.save()
 
     def count(self):
         return len(self._row_of)
 
-    def save(self):
+    def save(self, _all_rows=None):
         """vlite/main.py:280-294, written CLEAN: one row per live key in key order (the reference's
         context manager loads the old file first and appends the whole collection to it again,
         vlite/ctx.py:157-162; a reference reader loads a clean file identically).
@@ -437,7 +441,9 @@ class VLite:
         compact = self.ctx_dtype == "ubinary"
         per_file = max(1, min(self.max_rows_per_file, ((1 << 32) - 1) // (width * (1 if compact else 4))))
         n_parts = max(1, -(-len(keys) // per_file))
-        all_rows = self._corpus.read() if keys else None                     # one D2H copy
+        if _all_rows is None and keys:
+            _all_rows = self._corpus.read()                                  # one D2H copy
+        all_rows = _all_rows
         for part in range(n_parts):
             cf = self.ctx.create(self._part_name(part))
             cf.set_header(embedding_model="mixedbread-ai/mxbai-embed-large-v1", embedding_size=width,
@@ -493,3 +499,59 @@ class VLite:
         if self._corpus is not None:
             self._corpus.close()
             self._corpus = None
+
+
+class ShardedVLite(VLite):
+    """The same collection API over a corpus row-sharded across the GPUs of one box (one process
+    per GPU, ``torch.distributed`` initialised by the launcher).  Driven SPMD: every rank makes the
+    same calls with the same arguments; host-side ids, texts and metadata are replicated, vectors
+    live on exactly one GPU each (``ShardedCorpus``: least-full appends, shard-local tombstones, one
+    all-gather of the k candidates per search).  Every rank returns the same results; rank 0 alone
+    writes the CTX file.  The reference has no multi-GPU counterpart."""
+
+    def __init__(self, *args, group=None, backend_factory=None, **kw):
+        self._group = group
+        self._backend_factory = backend_factory
+        super().__init__(*args, **kw)
+
+    def _new_ids(self, n: int):
+        """rank 0 draws the ids, every rank uses them: the replicated tables must agree"""
+        import torch.distributed as dist
+        ids = super()._new_ids(n)
+        if dist.is_initialized() and dist.get_world_size(self._group) > 1:
+            box = [ids]
+            dist.broadcast_object_list(box, src=dist.get_global_rank(self._group, 0) if self._group else 0,
+                                       group=self._group)
+            ids = box[0]
+        return ids
+
+    def _ensure_corpus(self, width: int):
+        if self._corpus is None:
+            from .sharded import ShardedCorpus
+            self._width = self._width or width
+            backend = self._backend_factory(self._width) if self._backend_factory else None
+            self._corpus = ShardedCorpus(self._width, device=self.gpu_index, group=self._group, backend=backend)
+        return self._corpus
+
+    def save(self, _all_rows=None):
+        import torch.distributed as dist
+        rows = self._corpus.read() if (self._corpus is not None and self._row_of) else None   # collective
+        rank = dist.get_rank(self._group) if dist.is_initialized() else 0
+        if rank == 0:
+            super().save(_all_rows=rows)
+        if dist.is_initialized():
+            dist.barrier(group=self._group)
+
+    def clear(self):
+        import torch.distributed as dist
+        rank = dist.get_rank(self._group) if dist.is_initialized() else 0
+        if rank == 0:
+            super().clear()
+        else:
+            if self._corpus is not None:
+                self._corpus.clear()
+            for d in (self._row_of, self._texts, self._metas, self._extra, self._postings):
+                d.clear()
+            self._ids.clear()
+        if dist.is_initialized():
+            dist.barrier(group=self._group)

@@ -68,8 +68,9 @@ class ShardedSearcher:
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self._local_search = local_search or _cuda_local_search
         self._merge = merge or _cuda_merge
-        self.device = device if device is not None else (
-            torch.device("cuda", corpus.device) if local_search is None else torch.device("cpu"))
+        if device is None:
+            device = torch.device("cuda", corpus.device) if local_search is None else torch.device("cpu")
+        self.device = device
         self._bufs = {}
 
     def _buffers(self, nq: int, k: int):
@@ -105,3 +106,221 @@ class ShardedSearcher:
         dev_index = self.device.index if self.device.type == "cuda" else 0
         self._merge(recv, self.world, nq, k, out_s, out_r, dev_index, stream)
         return out_s, out_r
+
+
+# ==========================================================================================
+# A row-sharded, append-able collection (second half)
+# ==========================================================================================
+class CudaShardBackend:
+    """The product backend of ShardedCorpus: a local ``Corpus`` per rank + the CUDA merge."""
+
+    def __init__(self, width: int, device_index: int):
+        import torch
+        from . import _capi
+        self.torch, self._capi = torch, _capi
+        self.device = torch.device("cuda", device_index)
+        self.local = _capi.Corpus(width, device=device_index)
+        self.local.set_stream(torch.cuda.current_stream(self.device).cuda_stream)
+        self._seg_dev = None
+
+    def append(self, rows_u8):
+        return self.local.append(rows_u8)
+
+    def load_file(self, path, off, length, kind, max_rows):
+        return self.local.load_file(path, off, length, kind, max_rows)
+
+    def tombstone(self, local_rows):
+        self.local.tombstone(local_rows)
+
+    def read(self, first, n):
+        return self.local.read(first, n)
+
+    def clear(self):
+        self.local.clear()
+
+    def live_rows(self):
+        return self.local.live_rows
+
+    def set_segments(self, seg_local, seg_global):
+        t = self.torch
+        self._seg_dev = (t.tensor(seg_local, dtype=t.int64, device=self.device),
+                         t.tensor(seg_global, dtype=t.int64, device=self.device)) if seg_local else None
+
+    def local_search(self, _corpus, queries, k, metric, filter_mask, out_scores, out_rows):
+        """local top-k with LOCAL rows, rewritten to GLOBAL rows on the device before the exchange"""
+        self.local.search(queries, k, metric, filter_mask, out_scores, out_rows)
+        if self._seg_dev is not None:
+            self._capi.map_rows(out_rows, out_rows.numel(), self._seg_dev[0], self._seg_dev[1],
+                                int(self._seg_dev[0].numel()), device=self.device.index,
+                                stream=self.torch.cuda.current_stream(self.device).cuda_stream)
+
+    merge = staticmethod(_cuda_merge)
+
+    def to_device(self, host_array):
+        return self.torch.from_numpy(np.ascontiguousarray(host_array)).to(self.device)
+
+    def close(self):
+        self.local.close()
+
+
+class ShardedCorpus:
+    """A collection row-sharded over the ranks of a process group, driven SPMD: every rank
+    constructs it and makes the SAME calls with the SAME host arguments.
+
+      * append: the whole batch goes to the least-full shard (ties: lowest rank); its GLOBAL base
+        row is fixed at append time = the running global count, so global rows are insertion order
+        and results do not depend on the shard count or on placement;
+      * tombstones are shard-local (the owner clears its live bit);
+      * search: local scan -> local rows rewritten to global rows on the device (vl_map_rows) ->
+        ONE all-gather of the k candidates -> the same merge on every rank;
+      * load_file: each rank reads its own byte range of the EMBEDDINGS payload.
+
+    Offers the slice of the ``Corpus`` interface that ``VLite`` uses, with global row numbers, so
+    ``ShardedVLite`` is the single-GPU class with a different corpus behind it."""
+
+    def __init__(self, width: int, device: int | None = None, group=None, backend=None):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist = torch, dist
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.width = width
+        self.backend = backend or CudaShardBackend(width, device if device is not None else 0)
+        self.counts = [0] * self.world            # local rows per shard (replicated bookkeeping)
+        self.segments = []                        # (global_base, owner, local_start, n), ascending global_base
+        self.total = 0
+        self._searcher = ShardedSearcher(None, group=group, local_search=self.backend.local_search,
+                                         merge=self.backend.merge, device=getattr(self.backend, "device", None))
+
+    # ---- bookkeeping ----
+    def _add_segment(self, owner: int, n: int) -> int:
+        base = self.total
+        self.segments.append((base, owner, self.counts[owner], n))
+        self.counts[owner] += n
+        self.total += n
+        mine = [s for s in self.segments if s[1] == self.rank]
+        self.backend.set_segments([s[2] for s in mine], [s[0] for s in mine])
+        return base
+
+    def locate(self, global_row: int):
+        """(owner rank, local row) of a global row."""
+        import bisect
+        i = bisect.bisect_right([s[0] for s in self.segments], global_row) - 1
+        if i < 0 or global_row >= self.segments[i][0] + self.segments[i][3]:
+            raise IndexError(f"global row {global_row} out of range")
+        base, owner, lstart, _ = self.segments[i]
+        return owner, lstart + (global_row - base)
+
+    @property
+    def rows(self) -> int:
+        return self.total
+
+    @property
+    def live_rows(self) -> int:
+        t = self.torch.tensor([self.backend.live_rows()], dtype=self.torch.int64,
+                              device=self._searcher.device)
+        if self.world > 1:
+            self.dist.all_reduce(t, group=self.group)
+        return int(t.item())
+
+    # ---- ingest ----
+    def append(self, rows_u8) -> int:
+        rows_u8 = np.ascontiguousarray(rows_u8, dtype=np.uint8)
+        n = int(rows_u8.shape[0])
+        if n == 0:
+            return self.total
+        owner = min(range(self.world), key=lambda r: (self.counts[r], r))      # least-full shard
+        if owner == self.rank:
+            first_local = self.backend.append(rows_u8)
+            assert first_local == self.counts[owner]
+        return self._add_segment(owner, n)
+
+    def load_file(self, path: str, byte_off: int, byte_len: int, kind: int, max_rows: int = 0):
+        """Every rank streams ITS contiguous slice of the file's rows to its own GPU."""
+        from . import _capi
+        row_bytes = {_capi.SRC_U8: self.width, _capi.SRC_F32_OFFSET: self.width * 4,
+                     _capi.SRC_F32_BITS: self.width * 32}[kind]
+        n = byte_len // row_bytes
+        if max_rows:
+            n = min(n, max_rows)
+        plan = ShardPlan(n, self.world)
+        first = self.total
+        lo, cnt = plan.base_row(self.rank), plan.shard_rows(self.rank)
+        if cnt:
+            self.backend.load_file(path, byte_off + lo * row_bytes, cnt * row_bytes, kind, cnt)
+        for r in range(self.world):
+            if plan.shard_rows(r):
+                self._add_segment(r, plan.shard_rows(r))
+        return first, n
+
+    def tombstone(self, global_rows) -> None:
+        mine = []
+        for g in np.asarray(global_rows, dtype=np.int64).reshape(-1):
+            try:
+                owner, local = self.locate(int(g))
+            except IndexError:
+                continue
+            if owner == self.rank:
+                mine.append(local)
+        if mine:
+            self.backend.tombstone(mine)
+
+    def clear(self):
+        self.backend.clear()
+        self.counts = [0] * self.world
+        self.segments = []
+        self.total = 0
+        self.backend.set_segments([], [])
+
+    # ---- query ----
+    def _local_mask(self, mask_words_global):
+        """global bit-per-row mask -> this shard's local mask (host-side bit gather)"""
+        bits = np.unpackbits(np.ascontiguousarray(mask_words_global, dtype=np.uint32).view(np.uint8),
+                             bitorder="little")
+        n_local = self.counts[self.rank]
+        local = np.zeros((n_local + 31) // 32 * 32, dtype=np.uint8)
+        for base, owner, lstart, n in self.segments:
+            if owner == self.rank:
+                local[lstart:lstart + n] = bits[base:base + n]
+        return np.packbits(local.reshape(-1, 32), axis=1, bitorder="little").view(np.uint32).reshape(-1)
+
+    def search(self, queries, k: int, metric: int = 0, filter_mask=None):
+        """queries (Q, W) uint8 host array, identical on every rank; filter_mask: optional GLOBAL
+        bit-per-row mask.  Returns host arrays (scores uint32 (Q,k), rows uint64 (Q,k)) with global
+        rows, the same on every rank."""
+        q = np.ascontiguousarray(np.atleast_2d(queries), dtype=np.uint8)
+        nq = q.shape[0]
+        pad = (nq * k) % 2                       # the exchange block wants an even Q*k
+        if pad:
+            q = np.concatenate([q, q[:1]])
+        mask = None
+        if filter_mask is not None and self.counts[self.rank]:
+            mask = self._local_mask(filter_mask)
+        dq = self.backend.to_device(q)
+        s, r = self._searcher.search(dq, k, metric, mask)
+        # copies: the searcher hands out views of its reusable exchange buffers
+        s = s.cpu().numpy().view(np.uint32)[:nq].copy()
+        r = r.cpu().numpy().view(np.uint64)[:nq].copy()
+        return s, r
+
+    def read(self, first: int = 0, n: int | None = None) -> np.ndarray:
+        """rows [first, first+n) by GLOBAL number, assembled on every rank (collective)."""
+        if n is None:
+            n = self.total - first
+        out = np.zeros((n, self.width), dtype=np.uint8)
+        pieces = []
+        for base, owner, lstart, cnt in self.segments:
+            lo, hi = max(base, first), min(base + cnt, first + n)
+            if lo < hi and owner == self.rank:
+                pieces.append((lo - first, self.backend.read(lstart + (lo - base), hi - lo)))
+        if self.world > 1:
+            gathered = [None] * self.world
+            self.dist.all_gather_object(gathered, pieces, group=self.group)
+            pieces = [p for part in gathered for p in part]
+        for off, block in pieces:
+            out[off:off + len(block)] = block
+        return out
+
+    def close(self):
+        self.backend.close()
