@@ -456,9 +456,10 @@ int launch_scan_cfg(vl_corpus* c, ScanParams& p, int n_queries, int k, ScanPlan*
             s = std::min(s, max_splits);
             const long ctas = s * T;
             const double eff = (double)ctas / ((double)((ctas + slots - 1) / slots) * slots);
-            // an extra wave re-pays per-CTA prologue, list write-out and merge work: take it only
-            // for a clear gain in SM fill (measured: 1 wave of 288 CTAs beats 2 full waves of 592)
-            if (eff > best_eff + 0.08) {
+            // an extra wave re-pays per-CTA prologue, list warm-up and merge work: take it only when
+            // it fills the SMs better (measured at 500k x 1024: 2 exact waves of 592 CTAs beat 1 wave
+            // of 288 by 2 % now that list maintenance is cheap; 4 waves lose)
+            if (eff > best_eff + 0.02) {
                 best_eff = eff;
                 S = s;
             }
