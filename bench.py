@@ -316,14 +316,16 @@ def run_ours(args):
     t_hbm = alg_bytes / (hbm_peak * 1e9)
     t_int = alg_popc / popc_peak
     t_roof = max(t_hbm, t_int)
-    traffic = None
+    traffic, pipes = None, None
     tpath = os.path.join(ROOT, "profiles", "traffic_cfg2.json")
-    if os.path.exists(tpath):
-        traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
+    if os.path.exists(tpath):       # from the committed ncu --set full capture of this same kernel and workload
+        tj = json.load(open(tpath))
+        traffic = tj.get("dram_bytes_per_launch")
+        pipes = {k: tj[k] for k in ("alu_pipe_pct", "xu_pipe_pct", "fma_pipe_pct", "issue_slots_pct") if k in tj}
     roofline = {
         "bound": "int_pipe" if t_int >= t_hbm else "hbm",
         "achieved": alg_popc / (scan_avg_ms * 1e-3) / 1e12, "peak": popc_peak / 1e12, "unit": "TPOPC/s",
-        "frac": t_roof / (scan_avg_ms * 1e-3), "traffic": traffic,
+        "frac": t_roof / (scan_avg_ms * 1e-3), "traffic": traffic, "int_pipe_utilisation_ncu": pipes,
         "kernel": "scan_topk_kernel<128,HAMMING,8,8>", "kernel_ms": scan_avg_ms,
         "algorithmic": {"bytes_per_launch": alg_bytes, "popc_per_launch": alg_popc,
                         "per_unit": "W bytes and W/4 32-bit POPC per (query,row) pair; W=128"},

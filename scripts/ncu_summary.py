@@ -68,6 +68,13 @@ def full(rep, out, traffic=None):
                 t = {"dram_bytes_read": num("dram__bytes_read.sum"), "dram_bytes_write": num("dram__bytes_write.sum")}
                 t["dram_bytes_per_launch"] = t["dram_bytes_read"] + t["dram_bytes_write"]
                 t["source"] = rep.split("/")[-1]
+                for key, name in (("sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active", "alu_pipe_pct"),
+                                  ("sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active", "xu_pipe_pct"),
+                                  ("sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active", "fma_pipe_pct"),
+                                  ("sm__issue_active.avg.pct_of_peak_sustained_elapsed", "issue_slots_pct"),
+                                  ("gpu__time_duration.sum", "kernel_time")):
+                    if key in d:
+                        t[name] = float(d[key][0].replace(",", ""))
                 json.dump(t, open(traffic, "w"), indent=1)
     print(open(out).read())
 
