@@ -278,3 +278,34 @@ def test_large_corpus_properties(gpu):
         # returned number of rows strictly below it
         full = c.scores(q[0], HAMMING, 0, 4_000_000)
         assert (full < s[0, -1]).sum() <= k
+
+
+def test_random_differential(gpu):
+    """Seeded random shapes against the oracle: corpus size, query count, k, width, metric, masks,
+    tombstones and duplicates all vary; every case must match bit for bit."""
+    rng = np.random.default_rng(20240607)
+    for case in range(60):
+        w = int(rng.choice([64, 128]))
+        n = int(rng.choice([1, 2, 31, 32, 33, 255, 256, 257, 511, 1000, 4097, 9999, 30000]))
+        nq = int(rng.choice([1, 2, 3, 4, 7, 8, 9, 16, 17, 31, 33, 64, 65, 100]))
+        k = int(rng.choice([1, 2, 5, 10, 31, 32, 33, 40, 64, 130]))
+        metric = int(rng.integers(0, 2))
+        period = int(rng.choice([0, 0, 0, 7, 100]))
+        corpus = synth.corpus_rows(1000 + case, 0, n, w, period)
+        queries = synth.uniform_queries(2000 + case, nq, w)
+        if n > 3:
+            queries[0] = corpus[n - 1]
+        valid = np.ones(n, dtype=bool)
+        mask = None
+        if rng.random() < 0.5:
+            valid &= rng.random(n) < rng.choice([0.02, 0.3, 0.9])
+            mask = synth.pack_mask(valid)
+        with gpu.Corpus(w) as c:
+            c.append(corpus)
+            if rng.random() < 0.4 and n > 4:
+                dead = rng.choice(n, size=max(1, n // 7), replace=False)
+                c.tombstone(dead)
+                valid[dead] = False
+            s, r = c.search(queries, k, metric, mask)
+        es, er = cscan.search(queries, corpus, k, metric, synth.pack_mask(valid))
+        assert np.array_equal(s, es) and np.array_equal(r, er), (case, w, n, nq, k, metric, period)
