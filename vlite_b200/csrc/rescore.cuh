@@ -42,7 +42,15 @@ __global__ void __launch_bounds__(kRescoreThreads) rescore_kernel(const RescoreP
     {
         const uint4* src = reinterpret_cast<const uint4*>(static_cast<const uint8_t*>(p.queries) + (size_t)q * qbytes);
         uint4* dst = reinterpret_cast<uint4*>(s_q);
-        for (int i = threadIdx.x; i < (int)(qbytes / 16); i += kRescoreThreads) dst[i] = src[i];
+        if constexpr (QI8) {
+            for (int i = threadIdx.x; i < (int)(qbytes / 16); i += kRescoreThreads) dst[i] = src[i];
+        } else {
+            // fp32 query: the 4 float4 that face one 16-byte doc chunk are stored chunk-minor
+            // ([j][chunk]) so that the 32 lanes of a warp read consecutive float4 (no bank conflicts)
+            const int n_chunks = dims / 16;
+            for (int i = threadIdx.x; i < (int)(qbytes / 16); i += kRescoreThreads)
+                dst[(i & 3) * n_chunks + (i >> 2)] = src[i];
+        }
     }
     for (int i = threadIdx.x; i < p.n_sort; i += kRescoreThreads) {
         s_score[i] = -CUDART_INF_F;
@@ -51,47 +59,72 @@ __global__ void __launch_bounds__(kRescoreThreads) rescore_kernel(const RescoreP
     __syncthreads();
 
     const int chunks = dims / 16;  // 16 int8 per 128-bit load
-    for (int c = warp; c < p.n_cand; c += kRescoreThreads / 32) {
-        const uint64_t grow = p.cand[(size_t)q * p.n_cand + c];
-        if (grow == kSentinelRow) continue;
-        const uint64_t lrow = grow - p.base_row;
-        if (lrow >= p.n_docs) continue;  // not on this shard
-        const uint4* d = reinterpret_cast<const uint4*>(p.docs + lrow * (uint64_t)dims);
-        float facc = 0.f;
-        int iacc = 0;
-        for (int ch = lane; ch < chunks; ch += 32) {
-            const uint4 v = ldg128_stream(d + ch);
-            const uint32_t w[4] = {v.x, v.y, v.z, v.w};
-            if constexpr (QI8) {
-                const uint4 qv = reinterpret_cast<const uint4*>(s_q)[ch];
-                iacc = __dp4a((int)w[0], (int)qv.x, iacc);
-                iacc = __dp4a((int)w[1], (int)qv.y, iacc);
-                iacc = __dp4a((int)w[2], (int)qv.z, iacc);
-                iacc = __dp4a((int)w[3], (int)qv.w, iacc);
-            } else {
-                const float4* qf = reinterpret_cast<const float4*>(s_q) + ch * 4;
+    // one 1 KB gather per candidate is latency-bound: every warp keeps U rows (2 x 128-bit loads per
+    // lane each) in flight before it starts the arithmetic of the first
+    constexpr int U = 4;
+    auto accumulate = [&](const uint4& v, int ch, float& facc, int& iacc) {
+        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+        if constexpr (QI8) {
+            const uint4 qv = reinterpret_cast<const uint4*>(s_q)[ch];
+            iacc = __dp4a((int)w[0], (int)qv.x, iacc);
+            iacc = __dp4a((int)w[1], (int)qv.y, iacc);
+            iacc = __dp4a((int)w[2], (int)qv.z, iacc);
+            iacc = __dp4a((int)w[3], (int)qv.w, iacc);
+        } else {
+            const float4* qf = reinterpret_cast<const float4*>(s_q) + ch;
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const float4 qq = qf[j];
-                    const int x = (int)w[j];
-                    facc = fmaf((float)(int8_t)(x & 0xFF), qq.x, facc);
-                    facc = fmaf((float)(int8_t)((x >> 8) & 0xFF), qq.y, facc);
-                    facc = fmaf((float)(int8_t)((x >> 16) & 0xFF), qq.z, facc);
-                    facc = fmaf((float)(int8_t)((x >> 24) & 0xFF), qq.w, facc);
-                }
+            for (int j = 0; j < 4; ++j) {
+                const float4 qq = qf[j * chunks];
+                // int8 -> float without the conversion unit: byte b of (x ^ 0x80808080) is d + 128 in
+                // [0, 255]; PRMT drops it under the exponent of 2^23, so the float is 8388736 + d exactly
+                const uint32_t u = w[j] ^ 0x80808080u;
+                facc = fmaf(__uint_as_float(__byte_perm(u, 0x4B000000u, 0x7440)) - 8388736.f, qq.x, facc);
+                facc = fmaf(__uint_as_float(__byte_perm(u, 0x4B000000u, 0x7441)) - 8388736.f, qq.y, facc);
+                facc = fmaf(__uint_as_float(__byte_perm(u, 0x4B000000u, 0x7442)) - 8388736.f, qq.z, facc);
+                facc = fmaf(__uint_as_float(__byte_perm(u, 0x4B000000u, 0x7443)) - 8388736.f, qq.w, facc);
             }
         }
-        if constexpr (QI8) {
+    };
+    for (int c0 = warp * U; c0 < p.n_cand; c0 += (kRescoreThreads / 32) * U) {
+        uint64_t grow[U];
+        const uint4* d[U];
+        uint4 v[U][2];
 #pragma unroll
-            for (int off = 16; off > 0; off >>= 1) iacc += __shfl_xor_sync(kFullMask, iacc, off);
-            facc = (float)iacc;
-        } else {
-#pragma unroll
-            for (int off = 16; off > 0; off >>= 1) facc += __shfl_xor_sync(kFullMask, facc, off);
+        for (int u = 0; u < U; ++u) {
+            const int c = c0 + u;
+            grow[u] = c < p.n_cand ? p.cand[(size_t)q * p.n_cand + c] : kSentinelRow;
+            const uint64_t lrow = grow[u] - p.base_row;
+            if (grow[u] != kSentinelRow && lrow >= p.n_docs) grow[u] = kSentinelRow;  // not on this shard
+            d[u] = reinterpret_cast<const uint4*>(p.docs + (grow[u] == kSentinelRow ? 0 : lrow) * (uint64_t)dims);
         }
-        if (lane == 0) {
-            s_score[c] = facc;
-            s_row[c] = grow;
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int ch = lane + 32 * h;
+                v[u][h] = (grow[u] != kSentinelRow && ch < chunks) ? ldg128_stream(d[u] + ch) : make_uint4(0, 0, 0, 0);
+            }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            if (grow[u] == kSentinelRow) continue;   // warp-uniform
+            float facc = 0.f;
+            int iacc = 0;
+#pragma unroll
+            for (int h = 0; h < 2; ++h)
+                if (lane + 32 * h < chunks) accumulate(v[u][h], lane + 32 * h, facc, iacc);
+            for (int ch = lane + 64; ch < chunks; ch += 32) accumulate(ldg128_stream(d[u] + ch), ch, facc, iacc);
+            if constexpr (QI8) {
+#pragma unroll
+                for (int off = 16; off > 0; off >>= 1) iacc += __shfl_xor_sync(kFullMask, iacc, off);
+                facc = (float)iacc;
+            } else {
+#pragma unroll
+                for (int off = 16; off > 0; off >>= 1) facc += __shfl_xor_sync(kFullMask, facc, off);
+            }
+            if (lane == 0) {
+                s_score[c0 + u] = facc;
+                s_row[c0 + u] = grow[u];
+            }
         }
     }
     __syncthreads();
