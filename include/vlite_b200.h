@@ -9,7 +9,7 @@
  *   - every function returns 0 on success and a negative VL_E* code on
  *     failure; vl_last_error() then returns a thread-local message.
  *   - corpus rows and queries are RAW UBINARY bytes (np.packbits output,
- *     MSB-first within a byte), width W in {64, 128} bytes per row (512 / 1024 bits).  The
+ *     MSB-first within a byte), width W in {32, 64, 128} bytes per row (256 / 512 / 1024 bits).  The
  *     reference's stored encoding int8(u8)-128 (vlite/model.py:44) gives
  *     identical XOR scores; vl_corpus_append_f32 converts it on the device.
  *   - pointers named *_any may be host or device memory (the library asks

@@ -52,7 +52,7 @@ def test_no_cpu_fallback_without_a_device():
 def test_argument_validation_does_not_need_a_device():
     lib = _capi.load()
     h = ctypes.c_void_p()
-    assert lib.vl_corpus_create(0, 100, 0, ctypes.byref(h)) == _capi.EINVAL      # bad width
+    assert lib.vl_corpus_create(0, 100, 0, ctypes.byref(h)) == _capi.EINVAL      # bad width (32/64/128 only)
     assert b"width_bytes" in lib.vl_last_error()
     assert lib.vl_search(None, None, 1, 1, 0, None, None, None) == _capi.EINVAL
     assert lib.vl_corpus_destroy(None) == 0

@@ -23,7 +23,7 @@ def _check(c, corpus, queries, k, metric, mask_words=None, base_row=0):
     np.testing.assert_array_equal(r, er)
 
 
-@pytest.mark.parametrize("width", [64, 128])
+@pytest.mark.parametrize("width", [32, 64, 128])
 @pytest.mark.parametrize("metric", [HAMMING, XORSUM])
 def test_full_score_vector_bit_exact(gpu, width, metric):
     n = 5000
@@ -37,7 +37,7 @@ def test_full_score_vector_bit_exact(gpu, width, metric):
     np.testing.assert_array_equal(got.astype(np.int64), osearch.scores(q, corpus, metric))
 
 
-@pytest.mark.parametrize("width", [64, 128])
+@pytest.mark.parametrize("width", [32, 64, 128])
 @pytest.mark.parametrize("metric", [HAMMING, XORSUM])
 @pytest.mark.parametrize("nq", [1, 2, 3, 5, 8, 13, 24, 40, 64, 65, 130])
 def test_topk_all_query_tilings(gpu, width, metric, nq):
@@ -285,7 +285,7 @@ def test_random_differential(gpu):
     tombstones and duplicates all vary; every case must match bit for bit."""
     rng = np.random.default_rng(20240607)
     for case in range(60):
-        w = int(rng.choice([64, 128]))
+        w = int(rng.choice([32, 64, 128]))
         n = int(rng.choice([1, 2, 31, 32, 33, 255, 256, 257, 511, 1000, 4097, 9999, 30000]))
         nq = int(rng.choice([1, 2, 3, 4, 7, 8, 9, 16, 17, 31, 33, 64, 65, 100]))
         k = int(rng.choice([1, 2, 5, 10, 31, 32, 33, 40, 64, 130]))

@@ -394,7 +394,9 @@ int make_corpus_tmap(const vl_corpus* c, CUtensorMap* out) {
     const cuuint64_t strides[1] = {(cuuint64_t)c->w};
     const cuuint32_t box[2] = {(cuuint32_t)c->w, (cuuint32_t)kTileRows};
     const cuuint32_t estr[2] = {1, 1};
-    const CUtensorMapSwizzle sw = c->w == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
+    const CUtensorMapSwizzle sw = c->w == 128  ? CU_TENSOR_MAP_SWIZZLE_128B
+                                  : c->w == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
+                                               : CU_TENSOR_MAP_SWIZZLE_32B;
     CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, c->rows, dims, strides, box, estr,
                     CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -500,6 +502,7 @@ int launch_scan(vl_corpus* c, ScanParams& p, int nq, int k, int metric, ScanPlan
         return metric == VL_METRIC_HAMMING ? launch_scan_wm<Wv, kHamming>(c, p, nq, k, plan, dry) \
                                            : launch_scan_wm<Wv, kXorSum>(c, p, nq, k, plan, dry);
     switch (c->w) {
+        VL_W(32)
         VL_W(64)
         VL_W(128)
         default:
@@ -721,8 +724,8 @@ extern "C" int vl_device_count(void) {
 extern "C" int vl_corpus_create(int device, int width_bytes, uint64_t capacity_rows, vl_corpus** out) {
     if (!out) return fail(VL_EINVAL, "out is NULL");
     *out = nullptr;
-    if (width_bytes != 64 && width_bytes != 128)
-        return fail(VL_EINVAL, "width_bytes must be 64 or 128 (got %d)", width_bytes);
+    if (width_bytes != 32 && width_bytes != 64 && width_bytes != 128)
+        return fail(VL_EINVAL, "width_bytes must be 32, 64 or 128 (got %d)", width_bytes);
     int sms = 0;
     TRY(check_device(device, &sms));
     DeviceGuard g(device);

@@ -339,8 +339,8 @@ scan_topk_kernel(const __grid_constant__ CUtensorMap tmap, const ScanParams p) {
         }
     }
 
-    // TMA wrote the tile with the 128 B (W=128) / 64 B (W=64) swizzle: logical chunk j of row r sits
-    // at physical chunk j ^ rot(r), rot = r & 7 (resp. (r >> 1) & 3).  Lane l owns row l (mod 32), so
+    // TMA wrote the tile with the 128 B / 64 B / 32 B swizzle (W = 128 / 64 / 32): logical chunk j of
+    // row r sits at physical chunk j ^ rot(r), rot = r & 7, (r >> 1) & 3, (r >> 2) & 1.  Lane l owns row l (mod 32), so
     // its physical offset is (j * 16) ^ rot16 -- one row per lane at stride W, conflict-free 128-bit LDS
     constexpr int LANES_PER_128B = (W >= 128) ? 1 : 128 / W;
     constexpr int ROT_MASK = (CHUNKS < 8 ? CHUNKS : 8) - 1;

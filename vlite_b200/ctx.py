@@ -12,7 +12,7 @@ file the reference itself wrote).
 Differences from the reference, all deliberate:
   * no telemetry (the reference posts to PostHog and drops a ``.telm`` id file on every load/save,
     vlite/ctx.py:38, :58-59, :89-90);
-  * the row width follows ``header["embedding_size"]`` when it is 64 or 128 (the reference writes
+  * the row width follows ``header["embedding_size"]`` when it is 32, 64 or 128 (the reference writes
     that field, vlite/main.py:285, but always reads and writes 64 floats, vlite/ctx.py:70, :114);
     512 is accepted as the legacy one-float-per-bit layout of tests/contexts/vlite-bench.ctx;
   * ``header["embedding_dtype"] == "ubinary"`` (opt-in extension, not readable by the reference):
@@ -48,7 +48,7 @@ def is_ubinary(header: dict) -> bool:
 def row_floats_for(header: dict) -> int:
     """How many float32 one stored row holds."""
     size = header.get("embedding_size", 0) if isinstance(header, dict) else 0
-    return size if size in (64, 128, 512) else LEGACY_ROW_FLOATS
+    return size if size in (32, 64, 128, 512) else LEGACY_ROW_FLOATS
 
 
 class CtxFile:
