@@ -188,8 +188,9 @@ int vl_microbench(int device, int kind, int iters, double* ops_per_sec_out, doub
  * scan_ms = the scan kernel alone */
 int vl_last_timing(vl_corpus* c, float* total_ms, float* scan_ms);
 int vl_set_timing(vl_corpus* c, int enabled);
-/* tuning knobs for experiments (0 = automatic) */
-int vl_set_tuning(vl_corpus* c, int row_splits, int reserved);
+/* tuning knobs for experiments and tests (0 = automatic): row_splits = CTAs per query tile;
+ * stages = depth of the TMA ring, or -1 to force the exact multi-pass path for k > 32 */
+int vl_set_tuning(vl_corpus* c, int row_splits, int stages);
 
 #ifdef __cplusplus
 }

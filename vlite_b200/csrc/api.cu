@@ -276,7 +276,7 @@ struct vl_corpus {
     uint64_t count = 0;
     uint64_t live_count = 0;
     uint64_t base_row = 0;
-    DevBuf q_buf, filt_buf, part_s, part_r, out_s, out_r, stage[2], rows_buf, cand_buf, misc, lk_keys, lk_misc;
+    DevBuf q_buf, filt_buf, part_s, part_r, out_s, out_r, stage[2], cand_buf, misc, lk_keys, lk_misc;
     int force_multipass = 0;  // tuning/testing: disable the sampled large-k path
     void* pinned[2] = {nullptr, nullptr};
     size_t pinned_bytes = 0;
@@ -767,7 +767,7 @@ extern "C" int vl_corpus_destroy(vl_corpus* c) {
     c->rows_arena.destroy();
     c->live_arena.destroy();
     for (DevBuf* b : {&c->q_buf, &c->filt_buf, &c->part_s, &c->part_r, &c->out_s, &c->out_r, &c->stage[0],
-                      &c->stage[1], &c->rows_buf, &c->cand_buf, &c->misc, &c->lk_keys, &c->lk_misc})
+                      &c->stage[1], &c->cand_buf, &c->misc, &c->lk_keys, &c->lk_misc})
         b->release();
     for (int i = 0; i < 2; ++i) {
         if (c->pinned[i]) cudaFreeHost(c->pinned[i]);
