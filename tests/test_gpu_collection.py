@@ -274,3 +274,27 @@ def test_compact_ubinary_ctx_round_trip(gpu, golden, tmp_path):
     assert v2.rank_and_filter(q, 5) == v.rank_and_filter(q, 5)
     v.close()
     v2.close()
+
+
+@pytest.mark.parametrize("width", [32, 128])
+def test_other_row_widths_round_trip_through_ctx(gpu, tmp_path, width):
+    """256-bit and 1024-bit collections: add -> retrieve -> save -> reload; the CTX header carries
+    the row width (the reference always assumes 64)."""
+    from vlite_b200 import VLite
+    rows = synth.corpus_rows(70, 0, 500, width)
+    qs = rows[[3, 499]].copy()
+    emb = lambda texts: np.unpackbits(qs[: len(texts)], axis=1).astype(np.float32) * 2 - 1
+    v = VLite("wide", ctx_dir=str(tmp_path), embedder=emb, width=width, metric="hamming")
+    v.set_batch([f"t{i}" for i in range(500)], osearch.to_ref_encoding(rows))
+    got = v.retrieve(["a", "b"], top_k=2, return_scores=True)
+    assert [(g[1], int(g[3])) for g in got] == [("t3", 0), ("t499", 0)]
+    header, emb_f32, _, _, _ = octx.read_ctx(str(tmp_path / "wide.ctx"), row_floats=width)
+    assert header["embedding_size"] == width and emb_f32.shape == (500, width)
+    v2 = VLite("wide", ctx_dir=str(tmp_path), embedder=emb, width=width, metric="hamming")
+    assert v2.count() == 500 and v2._corpus.width == width
+    np.testing.assert_array_equal(v2._corpus.read(), rows)
+    es, er = osearch.search(qs, rows, 5, osearch.HAMMING)
+    got = v2.retrieve_batch(["a", "b"], top_k=5, return_scores=True)
+    assert [[int(g[3]) for g in one] for one in got] == [list(map(int, x)) for x in es]
+    v.close()
+    v2.close()
