@@ -589,10 +589,20 @@ int search_lists(vl_corpus* c, ScanParams p, int n_queries, int k, int metric, u
     cudaStream_t st = c->stream;
     if (out_stride == 0) out_stride = k;
     const int n_pass = (k + kWarpListMaxK - 1) / kWarpListMaxK;
-    TRY(c->cand_buf.ensure((size_t)n_queries * 12));
+    // tau[Q] | cursor score[Q] | cursor row[Q] | histogram[Q][1056] (k <= 32, not for huge batches)
+    const bool want_hist = k <= 32 && n_queries <= 16384;
+    const size_t hist_bytes = want_hist ? (size_t)n_queries * kHistWords * 4 : 0;
+    TRY(c->cand_buf.ensure((size_t)n_queries * 12 + hist_bytes));
     p.tau = static_cast<uint32_t*>(c->cand_buf.p);
     uint32_t* cur_s = p.tau + n_queries;
     uint32_t* cur_r = cur_s + n_queries;
+    p.hist = want_hist ? cur_r + n_queries : nullptr;
+    {
+        const uint32_t max_score = metric == VL_METRIC_HAMMING ? 8u * c->w : 255u * c->w;
+        p.hist_shift = 0;
+        while ((max_score >> p.hist_shift) > (uint32_t)(kHistFine - 1)) ++p.hist_shift;
+        if (metric == VL_METRIC_HAMMING) p.hist_shift = 0;   // 8W <= 1024: only the all-bits-differ score overflows
+    }
     for (int pass = 0; pass < n_pass; ++pass) {
         const int k_pass = std::min(kWarpListMaxK, k - pass * kWarpListMaxK);
         p.k = k_pass;
@@ -611,6 +621,7 @@ int search_lists(vl_corpus* c, ScanParams p, int n_queries, int k, int metric, u
         p.evict_first = (plan.T == 1 && n_pass == 1 && p.tile_stride == 1 &&
                          c->count * (uint64_t)c->w > (96ull << 20)) ? 1 : 0;
         CU(cudaMemsetAsync(p.tau, 0xFF, (size_t)n_queries * 4, st));
+        if (p.hist) CU(cudaMemsetAsync(p.hist, 0, hist_bytes, st));
         TRY(launch_scan(c, p, n_queries, k_pass, metric, nullptr, /*dry=*/false));
         if (c->timing && pass == 0 && p.tile_stride == 1) CU(cudaEventRecord(c->ev1, st));
         TRY(merge_levels(st, p.part_scores, p.part_rows, n_lists, dense, dense, n_queries, k_pass, k_pass, o_s, o_r,

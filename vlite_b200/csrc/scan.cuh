@@ -36,6 +36,7 @@ constexpr int kScanWarps = 8;
 constexpr int kScanThreads = kScanWarps * 32;
 constexpr int kWarpListMaxK = 128;
 constexpr uint32_t kMaskedBias = 0x40000000u;
+constexpr int kHistFine = 1024, kHistCoarse = 32, kHistWords = kHistFine + kHistCoarse;
 
 struct ScanParams {
     const uint8_t* rows;     // corpus, n_rows x W, 256-byte aligned
@@ -59,6 +60,12 @@ struct ScanParams {
     // A full list publishes its k-th score with atomicMin; rows scoring above the bound cannot be
     // in the final top-k, so dropping them early changes no result (only prunes insert work).
     uint32_t* tau;
+    // per-query score histogram of the rows that entered some list (fine[1024] then coarse[32] per
+    // query, bucket = min(score >> hist_shift, 1023)).  Every counted row is a distinct eligible
+    // corpus row, so "k rows counted at or below bucket X" proves the final k-th best lies in or
+    // below bucket X: a device-wide bound far tighter than any single CTA's own k-th best.
+    uint32_t* hist;
+    int hist_shift;
     // tile sampling (large-k threshold estimate): the kernel visits tiles 0, stride, 2*stride, ...
     // n_tiles counts the VISITED tiles; 1 = every tile
     uint32_t tile_stride;
@@ -357,6 +364,9 @@ scan_topk_kernel(const __grid_constant__ CUtensorMap tmap, const ScanParams p) {
     const uint32_t* tau_ptr = p.tau + (qtile * QT + wq * C + (tau_mine ? lane : 0));
     uint32_t tau_pref = kSentinelScore;
     bool dirty = false;
+    // only where one warp per CTA serves a query (WQ == 8): with row-sliced warps (Q <= 32) thousands
+    // of warps would hammer the same few bins and the bound is not worth the atomics (measured)
+    const bool use_hist = WQ == 8 && p.hist != nullptr && p.collect_thr == nullptr && k <= 32;
 
     for (uint32_t i = 0; i < my_tiles; ++i) {
         const uint32_t t = (tile_begin + i) * p.tile_stride;
@@ -378,6 +388,39 @@ scan_topk_kernel(const __grid_constant__ CUtensorMap tmap, const ScanParams p) {
 #pragma unroll
             for (int c = 0; c < C; ++c) thr[c] = min(thr[c], __shfl_sync(kFullMask, g, c));
             if (tau_mine) tau_pref = __ldcg(tau_ptr);
+        }
+        // at tiles 1, 2, 4, 8, ... turn the device-wide histogram into a bound: the bucket where the
+        // running count of candidate rows reaches k caps the final k-th best score
+        if (use_hist && i != 0 && (i & (i - 1)) == 0) {
+#pragma unroll
+            for (int c = 0; c < C; ++c) {
+                const int qg = qtile * QT + wq * C + c;
+                if (qg >= p.n_queries) continue;                       // warp-uniform
+                const uint32_t* h = p.hist + (size_t)qg * kHistWords;
+                uint32_t cum = __ldcg(h + kHistFine + lane);
+#pragma unroll
+                for (int off = 1; off < 32; off <<= 1) {
+                    const uint32_t up = __shfl_up_sync(kFullMask, cum, off);
+                    if (lane >= off) cum += up;
+                }
+                const unsigned reach = __ballot_sync(kFullMask, cum >= (uint32_t)k);
+                if (!reach) continue;
+                const int bucket = __ffs(reach) - 1;
+                const uint32_t before = bucket ? __shfl_sync(kFullMask, cum, bucket - 1) : 0u;
+                uint32_t cf = __ldcg(h + bucket * 32 + lane);
+#pragma unroll
+                for (int off = 1; off < 32; off <<= 1) {
+                    const uint32_t up = __shfl_up_sync(kFullMask, cf, off);
+                    if (lane >= off) cf += up;
+                }
+                const unsigned reach2 = __ballot_sync(kFullMask, before + cf >= (uint32_t)k);
+                if (!reach2) continue;                                 // fine bins lag the coarse ones: skip
+                const int x = bucket * 32 + (__ffs(reach2) - 1);
+                if (x >= kHistFine - 1) continue;                      // the last bucket is open-ended
+                const uint32_t bound = ((uint32_t)(x + 1) << p.hist_shift) - 1u;   // k-th best <= bound
+                thr[c] = min(thr[c], bound + 1u);
+                if (lane == 0) atomicMin(p.tau + qg, bound);
+            }
         }
         mbar_wait(&s_full[s], (i / stages) & 1);
         const uint32_t* m = s_masks + s * 2 * MASKW;
@@ -438,15 +481,21 @@ scan_topk_kernel(const __grid_constant__ CUtensorMap tmap, const ScanParams p) {
                 // Rare path of the common case (k-lists with k <= 32): statically indexed, one
                 // warp-uniform vote per query, then one list merge per row group that has a hit.
                 const uint32_t row_base = t * TR + (uint32_t)row_in_tile0;
+                // one warp-wide OR tells which (query, row group) pairs have a candidate at all
+                uint32_t hm = 0;
+#pragma unroll
+                for (int c = 0; c < C; ++c)
+#pragma unroll
+                    for (int r = 0; r < R; ++r)
+                        if (valid[r] && (acc[r][c] < thr[c])) hm |= 1u << (c * R + r);
+                const uint32_t any_hit = __reduce_or_sync(kFullMask, hm);
 #pragma unroll
                 for (int c = 0; c < C; ++c) {
-                    bool hq = false;
-#pragma unroll
-                    for (int r = 0; r < R; ++r) hq |= valid[r] && (acc[r][c] < thr[c]);
-                    if (!__any_sync(kFullMask, hq)) continue;
+                    if (((any_hit >> (c * R)) & ((1u << R) - 1u)) == 0) continue;   // warp-uniform
                     uint32_t tc = s_thr[warp * C + c];
 #pragma unroll
                     for (int r = 0; r < R; ++r) {
+                        if (((any_hit >> (c * R + r)) & 1u) == 0) continue;         // warp-uniform
                         const uint32_t sc = acc[r][c];
                         const uint32_t idx = row_base + (uint32_t)(r * 32 + lane);
                         bool mine = valid[r] && (sc < min(thr[c], tc));
@@ -455,9 +504,16 @@ scan_topk_kernel(const __grid_constant__ CUtensorMap tmap, const ScanParams p) {
                             const uint32_t cr = s_cursor[2 * (wq * C + c) + 1];
                             mine = (sc > cs) || (sc == cs && idx > cr);
                         }
-                        if (__any_sync(kFullMask, mine))
+                        if (__any_sync(kFullMask, mine)) {
+                            if (use_hist && mine) {
+                                const uint32_t b = min(sc >> p.hist_shift, (uint32_t)(kHistFine - 1));
+                                uint32_t* h = p.hist + (size_t)(qtile * QT + wq * C + c) * kHistWords;
+                                atomicAdd(h + b, 1u);
+                                atomicAdd(h + kHistFine + (b >> 5), 1u);
+                            }
                             tc = warp_list_merge32(ls + c * k, li + c * k, k,
                                                    mine ? (((uint64_t)sc << 32) | idx) : ~0ull, lane);
+                        }
                     }
                     if (lane == 0) s_thr[warp * C + c] = tc;
                     thr[c] = min(thr[c], tc);
