@@ -174,6 +174,17 @@ int vl_rescore(vl_corpus* c, const int8_t* docs_i8_dev, uint64_t n_docs, int dim
  * x_any: n x dims float32, out_any: n x dims/8 bytes. */
 int vl_quantize_binary(int device, void* cuda_stream, const float* x_any, uint64_t n, int dims,
                        uint8_t* out_any);
+/* The whole quantisation tail of EmbeddingModel.embed (vlite/model.py:34-44) in one launch, on
+ * device memory only, so an encoder's output never round-trips through the host:
+ * x_dev: n x dims float32 (the CLS embedding, normalised or not).  Each row is L2-normalised over
+ * all `dims` features (x / max(||x||, 1e-12), model.py:35); the first `binary_dims` features are
+ * sign-packed MSB-first into out_u8_dev (n x binary_dims/8 -- bit-identical to
+ * vl_quantize_binary on the same columns); out_f32_dev (optional, n x dims) receives the
+ * normalised row and out_i8_dev (optional, n x dims) rint(clamp(x_norm * i8_scale, -127, 127)):
+ * the query / document forms vl_rescore takes.  Asynchronous on cuda_stream. */
+int vl_quantize_embeddings(int device, void* cuda_stream, const float* x_dev, uint64_t n, int dims,
+                           int binary_dims, float i8_scale, uint8_t* out_u8_dev, int8_t* out_i8_dev,
+                           float* out_f32_dev);
 /* bench data: fill n x dims int8 documents with the synthetic generator */
 int vl_synth_docs_i8(int device, void* cuda_stream, uint64_t seed, uint64_t first_row, uint64_t n,
                      int dims, int8_t* out_dev);

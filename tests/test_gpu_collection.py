@@ -64,6 +64,56 @@ def test_prefilter_is_true_filtered_topk(gpu, golden, tmp_path):
     v.close()
 
 
+def test_filter_masks_follow_updates_deletes_and_none_terms(gpu, tmp_path):
+    """The (key, value) bitmap index behind the in-scan filter stays exact through set_batch,
+    update (chunks sharing one metadata dict), delete, terms with value None (md.get(k) == None
+    also matches rows without k, vlite/main.py:162) and values the index cannot hold."""
+    from vlite_b200 import VLite
+    rng = np.random.default_rng(21)
+    n, w = 700, 64
+    corpus = synth.corpus_rows(77, 0, n, w)
+    queries = synth.uniform_queries(78, 3, w)
+    v = VLite("filt", ctx_dir=str(tmp_path / "contexts"), embedder=bits_embedder(queries), width=w)
+    metas = []
+    for i in range(n):
+        md = {"lang": ["en", "fr", None][int(rng.integers(3))]} if rng.random() < 0.8 else {}
+        if rng.random() < 0.5:
+            md["year"] = int(rng.integers(2020, 2023))
+        if i % 50 == 0:
+            md["tags"] = ["x", i % 100]
+        metas.append(md)
+    v.set_batch([f"t{i}" for i in range(n)], osearch.to_ref_encoding(corpus), [dict(m) for m in metas])
+    keys = list(v.dump().keys())
+
+    def check(filters):
+        live = [k in v.dump() for k in keys]
+        for md in filters:
+            valid = np.array([live[i] and all(v.dump()[k]["metadata"].get(a) == b for a, b in md.items())
+                              if live[i] else False for i, k in enumerate(keys)])
+            got = v.retrieve_batch(["q"] * 3, top_k=7, metadata=md, return_scores=True)
+            es, er = osearch.search(queries, corpus, 7, osearch.XORSUM, valid=valid)
+            for qi in range(3):
+                keep = er[qi] != osearch.SENTINEL_ROW
+                assert [g[0] for g in got[qi]] == [keys[int(r)] for r in er[qi][keep]], md
+                assert [int(g[3]) for g in got[qi]] == [int(x) for x in es[qi][keep]], md
+
+    filters = [{"lang": "en"}, {"lang": None}, {"lang": "fr", "year": 2021}, {"year": 2022.0},
+               {"tags": ["x", 0]}, {"nope": 1}]
+    check(filters)
+    for k in keys[10:200:7]:                                         # update: value replaced in place
+        assert v.update(k.rsplit("_", 1)[0], metadata={"lang": "de", "year": 2021})
+    for k in keys[300:400:9]:
+        assert v.delete(k.rsplit("_", 1)[0]) == 1
+    check(filters + [{"lang": "de"}, {"lang": "de", "year": 2021}])
+    # chunks of one add() share a metadata dict; update must move every chunk's bits
+    v.add(["a", "b", "c"], metadata={"lang": "xx"}, item_id="shared")
+    assert len(v.retrieve_batch(["q"], top_k=10, metadata={"lang": "xx"})[0]) == 3
+    v.update("shared", metadata={"lang": "yy"})
+    assert v.retrieve_batch(["q"], top_k=10, metadata={"lang": "xx"})[0] == []
+    assert len(v.retrieve_batch(["q"], top_k=10, metadata={"lang": "yy"})[0]) == 3
+    v.close()
+
+
 def test_retrieve_merges_all_queries_like_reference(gpu, golden, tmp_path):
     v = _build(gpu, golden, tmp_path)
     r = v.retrieve(["a", "b"], top_k=4, return_scores=True)          # two query rows -> ONE list
@@ -186,6 +236,48 @@ def test_quantize_binary_matches_packbits(gpu):
     np.testing.assert_array_equal(gpu.quantize_binary(x), osearch.quantize_binary(x))
     x2 = rng.standard_normal((5, 1024)).astype(np.float32)
     np.testing.assert_array_equal(gpu.quantize_binary(x2), np.packbits(x2 > 0, axis=-1))
+
+
+def test_fused_quantisation_tail_on_device(gpu):
+    """normalize -> sign -> pack (+ int8 / float32 copies) in one launch on device tensors
+    (vlite/model.py:35-44); normalisation is compared with torch's own on the CPU in float64."""
+    import torch
+    from vlite_b200.model import EmbeddingModel
+    rng = np.random.default_rng(11)
+    for n, dims, bdims in ((37, 1024, 512), (5, 1024, 1024), (3, 96, 64), (1, 32, 32), (2, 4096, 1024)):
+        x = (rng.standard_normal((n, dims)) * rng.uniform(0.01, 30.0, size=(n, 1))).astype(np.float32)
+        x[0, :4] = 0.0
+        if n > 2:
+            x[2] = 0.0                                                   # zero row: eps guard, all-zero outputs
+        xd = torch.from_numpy(x).cuda()
+        u8 = torch.empty((n, bdims // 8), dtype=torch.uint8, device="cuda")
+        i8 = torch.empty((n, dims), dtype=torch.int8, device="cuda")
+        f32 = torch.empty((n, dims), dtype=torch.float32, device="cuda")
+        scale = 400.0
+        gpu.quantize_embeddings(xd, bdims, u8, i8, f32, i8_scale=scale)
+        torch.cuda.synchronize()
+        np.testing.assert_array_equal(u8.cpu().numpy(), osearch.quantize_binary(x[:, :bdims]))
+        want = torch.nn.functional.normalize(torch.from_numpy(x).double(), p=2, dim=1).numpy()
+        np.testing.assert_allclose(f32.cpu().numpy(), want, rtol=2e-6, atol=1e-12)
+        t = np.clip(want * scale, -127, 127)
+        got = i8.cpu().numpy().astype(np.int64)
+        off = got != np.rint(t)
+        assert np.all(np.abs(np.abs(t[off] - np.floor(t[off])) - 0.5) < 1e-3)    # only at rounding ties
+        assert off.mean() < 1e-3
+        only_bits = torch.empty_like(u8)
+        gpu.quantize_embeddings(xd, bdims, only_bits)                       # optional outputs omitted
+        assert torch.equal(only_bits, u8)
+    # the model mirror: a CUDA-tensor embedder goes through the fused tail
+    emb = torch.from_numpy(rng.standard_normal((6, 1024)).astype(np.float32)).cuda()
+    m = EmbeddingModel(embedder=lambda texts: emb[:len(texts)])
+    out = m.embed_device(["t"] * 6, int8=True, float32=True)
+    np.testing.assert_array_equal(out["ubinary"].cpu().numpy(), osearch.quantize_binary(emb.cpu().numpy()[:, :512]))
+    assert out["int8"].shape == (6, 1024) and out["float32"].shape == (6, 1024)
+    np.testing.assert_array_equal(m.embed(["t"] * 6), osearch.to_ref_encoding(out["ubinary"].cpu().numpy()))
+    with pytest.raises(gpu.VliteB200Error):
+        gpu.quantize_embeddings(emb, 2048, out["ubinary"])                 # binary_dims > dims
+    with pytest.raises(gpu.VliteB200Error):
+        gpu.quantize_embeddings(emb.cpu(), 512, out["ubinary"])            # host pointer
 
 
 def test_ctx_embeddings_stream_to_hbm(gpu, tmp_path):

@@ -85,6 +85,8 @@ def load():
         "vl_rescore": (c_int, [c_void_p, c_void_p, c_u64, c_int, c_void_p, c_int, c_void_p, c_int, c_int, c_int,
                                c_void_p, c_void_p]),
         "vl_quantize_binary": (c_int, [c_int, c_void_p, c_void_p, c_u64, c_int, c_void_p]),
+        "vl_quantize_embeddings": (c_int, [c_int, c_void_p, c_void_p, c_u64, c_int, c_int, ctypes.c_float,
+                                           c_void_p, c_void_p, c_void_p]),
         "vl_synth_docs_i8": (c_int, [c_int, c_void_p, c_u64, c_u64, c_u64, c_int, c_void_p]),
         "vl_microbench": (c_int, [c_int, c_int, c_int, P(ctypes.c_double), P(ctypes.c_double)]),
         "vl_last_timing": (c_int, [c_void_p, P(ctypes.c_float), P(ctypes.c_float)]),
@@ -331,6 +333,19 @@ def quantize_binary(x, out=None, device: int = 0, stream: int | None = None):
         out = np.empty((n, dims // 8), dtype=np.uint8)
     check(load().vl_quantize_binary(device, ctypes.c_void_p(stream or 0), ptr(x), n, dims, ptr(out)))
     return out
+
+
+def quantize_embeddings(x_dev, binary_dims: int, out_u8_dev, out_i8_dev=None, out_f32_dev=None,
+                        i8_scale: float = 127.0, device: int = 0, stream: int | None = None):
+    """Fused normalise + sign-pack (+ int8 / float32 copies) on device tensors; see
+    ``vl_quantize_embeddings``.  x_dev: (n, dims) float32 CUDA tensor."""
+    n, dims = int(x_dev.shape[0]), int(x_dev.shape[1])
+    nul = ctypes.c_void_p(0)
+    check(load().vl_quantize_embeddings(device, ctypes.c_void_p(stream or 0), ptr(x_dev), n, dims, int(binary_dims),
+                                        float(i8_scale), ptr(out_u8_dev),
+                                        ptr(out_i8_dev) if out_i8_dev is not None else nul,
+                                        ptr(out_f32_dev) if out_f32_dev is not None else nul))
+    return out_u8_dev
 
 
 def synth_docs_i8(seed: int, first_row: int, n: int, dims: int, out_dev, device: int = 0, stream: int | None = None):

@@ -1307,6 +1307,27 @@ extern "C" int vl_quantize_binary(int device, void* cuda_stream, const float* x_
     return VL_OK;
 }
 
+extern "C" int vl_quantize_embeddings(int device, void* cuda_stream, const float* x_dev, uint64_t n, int dims,
+                                      int binary_dims, float i8_scale, uint8_t* out_u8_dev, int8_t* out_i8_dev,
+                                      float* out_f32_dev) {
+    if (!x_dev || !out_u8_dev) return fail(VL_EINVAL, "NULL argument");
+    if (dims < 32 || dims % 32 || dims > 8192) return fail(VL_EINVAL, "dims must be a multiple of 32, at most 8192");
+    if (binary_dims < 32 || binary_dims % 32 || binary_dims > dims)
+        return fail(VL_EINVAL, "binary_dims must be a multiple of 32, at most dims");
+    if (out_i8_dev && !(i8_scale > 0.f)) return fail(VL_EINVAL, "i8_scale must be positive");
+    int sms = 0;
+    TRY(check_device(device, &sms));
+    DeviceGuard g(device);
+    if (!is_device_ptr(x_dev) || !is_device_ptr(out_u8_dev) || (out_i8_dev && !is_device_ptr(out_i8_dev)) ||
+        (out_f32_dev && !is_device_ptr(out_f32_dev)))
+        return fail(VL_EINVAL, "vl_quantize_embeddings takes device pointers only");
+    if (n == 0) return VL_OK;
+    quantize_embeddings_kernel<<<grid_for(n * 32, 256, sms), 256, 0, static_cast<cudaStream_t>(cuda_stream)>>>(
+        x_dev, n, dims, binary_dims, i8_scale, reinterpret_cast<uint32_t*>(out_u8_dev), out_i8_dev, out_f32_dev);
+    LAUNCHED();
+    return VL_OK;
+}
+
 extern "C" int vl_synth_docs_i8(int device, void* cuda_stream, uint64_t seed, uint64_t first_row, uint64_t n, int dims,
                                 int8_t* out_dev) {
     if (!out_dev || !is_device_ptr(out_dev)) return fail(VL_EINVAL, "out must be device memory");

@@ -89,6 +89,66 @@ __global__ void sign_i8_kernel(const int8_t* __restrict__ src, uint64_t n_words,
     }
 }
 
+// Quantisation tail of the encoder (vlite/model.py:34-44), one warp per row, the row read once
+// from HBM (the second pass hits L1): L2-normalise the CLS embedding over all `dims` features
+// (torch.nn.functional.normalize: x / max(||x||, 1e-12)), sign-pack the first `binary_dims` of
+// them MSB-first (what the scan reads), and optionally write the normalised float32 row and its
+// int8 copy rint(clamp(x * i8_scale, -127, 127)) -- the two query/document forms vl_rescore takes.
+// A lane owns float4 l, l+32, ...: 8 neighbouring lanes hold the 32 values of one packed word.
+__global__ void quantize_embeddings_kernel(const float* __restrict__ x, uint64_t n, int dims, int binary_dims,
+                                           float i8_scale, uint32_t* __restrict__ out_bits,
+                                           int8_t* __restrict__ out_i8, float* __restrict__ out_f32) {
+    const int lane = threadIdx.x & 31;
+    const uint64_t warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    const int n4 = dims >> 2, b4 = binary_dims >> 2;
+    for (uint64_t row = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; row < n; row += warps) {
+        const float4* src = reinterpret_cast<const float4*>(x + row * (uint64_t)dims);
+        float ss = 0.f;
+        for (int f = lane; f < n4; f += 32) {
+            const float4 v = src[f];
+            ss = fmaf(v.x, v.x, ss);
+            ss = fmaf(v.y, v.y, ss);
+            ss = fmaf(v.z, v.z, ss);
+            ss = fmaf(v.w, v.w, ss);
+        }
+#pragma unroll
+        for (int o = 16; o; o >>= 1) ss += __shfl_xor_sync(kFullMask, ss, o);
+        const float inv = 1.f / fmaxf(sqrtf(ss), 1e-12f);
+        for (int f0 = 0; f0 < n4; f0 += 32) {       // warp-uniform trip count: shuffles stay converged
+            const int f = f0 + lane;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (f < n4) v = src[f];
+            const float e[4] = {v.x, v.y, v.z, v.w};
+            if (f0 < b4) {
+                uint32_t bits = 0;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int bit_index = (f & 7) * 4 + j;
+                    if (f < b4 && e[j] > 0.f) bits |= 1u << (8 * (bit_index >> 3) + (7 - (bit_index & 7)));
+                }
+                bits |= __shfl_xor_sync(kFullMask, bits, 1);
+                bits |= __shfl_xor_sync(kFullMask, bits, 2);
+                bits |= __shfl_xor_sync(kFullMask, bits, 4);
+                if ((lane & 7) == 0 && f < b4) out_bits[row * (uint64_t)(binary_dims >> 5) + (f >> 3)] = bits;
+            }
+            if (f < n4) {
+                const float4 u = make_float4(v.x * inv, v.y * inv, v.z * inv, v.w * inv);
+                if (out_f32) reinterpret_cast<float4*>(out_f32 + row * (uint64_t)dims)[f] = u;
+                if (out_i8) {
+                    const float q[4] = {u.x, u.y, u.z, u.w};
+                    uint32_t packed = 0;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const int r = __float2int_rn(fminf(fmaxf(q[j] * i8_scale, -127.f), 127.f));
+                        packed |= (uint32_t)(r & 0xFF) << (8 * j);
+                    }
+                    reinterpret_cast<uint32_t*>(out_i8 + row * (uint64_t)dims)[f] = packed;
+                }
+            }
+        }
+    }
+}
+
 // set live bits for rows [first, first+n)
 __global__ void live_set_range_kernel(uint32_t* __restrict__ live, uint64_t first, uint64_t n) {
     const uint64_t w0 = first >> 5, w1 = (first + n + 31) >> 5;

@@ -32,6 +32,7 @@ import numpy as np
 
 from . import _capi
 from .ctx import Ctx, is_ubinary, row_floats_for
+from .metaindex import MetaIndex
 from .model import EmbeddingModel, from_reference_encoding, to_reference_encoding
 
 logger = logging.getLogger(__name__)
@@ -58,14 +59,6 @@ def chop_and_chunk(text, max_seq_length=512, fast=False):
             else:
                 chunks.extend(enc.decode(ids[i:i + max_seq_length]) for i in range(0, len(ids), max_seq_length))
     return chunks
-
-
-def _hashable(v):
-    try:
-        hash(v)
-        return True
-    except TypeError:
-        return False
 
 
 class _IndexView(dict):
@@ -138,7 +131,7 @@ class VLite:
         self._texts = {}           # chunk_id -> text
         self._metas = {}           # chunk_id -> metadata dict
         self._extra = {}           # chunk_id -> {'vector': ...} written by update() (main.py:180)
-        self._postings = {}        # (key, value) -> list of rows, for filter masks
+        self._meta_index = MetaIndex()   # (key, value) -> row bitmap, for filter masks
         self.index = _IndexView(self)
         self._load_collection()
 
@@ -164,9 +157,7 @@ class VLite:
         return e
 
     def _post(self, chunk_id, row):
-        for kv in self._metas[chunk_id].items():
-            if _hashable(kv[1]):
-                self._postings.setdefault(kv, []).append(row)
+        self._meta_index.set_row(self._metas[chunk_id], row)
 
     def _register(self, chunk_id, text, metadata, row):
         old = self._row_of.get(chunk_id)
@@ -230,23 +221,22 @@ class VLite:
             self._register(chunk_id, text, cf.metadata.get(chunk_id, {}), row)
 
     def _filter_rows(self, metadata: dict):
-        """Rows whose metadata satisfies all(md.get(k) == v) (main.py:162)."""
+        """Rows whose metadata satisfies all(md.get(k) == v) (main.py:162), found by walking the
+        rows: only for terms the bitmap index cannot hold (unhashable values, NaN)."""
         items = list(metadata.items())
-        if all(_hashable(v) for _, v in items):
-            lists = [self._postings.get(kv, []) for kv in items]
-            seed = min(lists, key=len)
-            rows = [r for r in seed if self._ids[r] is not None
-                    and all(self._metas[self._ids[r]].get(k) == v for k, v in items)]
-        else:
-            rows = [r for cid, r in self._row_of.items() if r is not None
-                    and all(self._metas[cid].get(k) == v for k, v in items)]
+        rows = [r for cid, r in self._row_of.items() if r is not None
+                and all(self._metas[cid].get(k) == v for k, v in items)]
         return np.unique(np.asarray(rows, dtype=np.int64))
 
     def _filter_mask(self, metadata: dict):
+        """One bit per corpus row, uint32 words: the AND of the per-(key, value) bitmaps."""
         n = self._corpus.rows
-        bits = np.zeros((n + 31) // 32 * 32, dtype=bool)
-        bits[self._filter_rows(metadata)] = True
-        return np.packbits(bits.reshape(-1, 32), axis=1, bitorder="little").view(np.uint32).reshape(-1)
+        words = self._meta_index.mask(metadata, n)
+        if words is None:
+            bits = np.zeros((n + 31) // 32 * 32, dtype=bool)
+            bits[self._filter_rows(metadata)] = True
+            words = np.packbits(bits.reshape(-1, 32), axis=1, bitorder="little").view(np.uint32).reshape(-1)
+        return words
 
     def _search(self, queries_u8, k, mask=None):
         if self._corpus is None or self._corpus.live_rows == 0 or queries_u8.shape[1] != self._corpus.width:
@@ -339,16 +329,19 @@ class VLite:
         chunk_ids = [cid for cid in self._row_of if cid.startswith(f"{id}_")]
         if not chunk_ids:
             return False
+        if metadata is not None:
+            # chunks of one add() share a metadata dict: read every old value before changing any
+            for cid in chunk_ids:
+                row = self._row_of[cid]
+                if row is not None:
+                    replaced = {k: self._metas[cid][k] for k in metadata if k in self._metas[cid]}
+                    self._meta_index.clear_row(replaced, row)
+                    self._meta_index.set_row(metadata, row)
         for cid in chunk_ids:
             if text is not None:
                 self._texts[cid] = text
             if metadata is not None:
                 self._metas[cid].update(metadata)
-                row = self._row_of[cid]
-                if row is not None:
-                    for kv in metadata.items():
-                        if _hashable(kv[1]):
-                            self._postings.setdefault(kv, []).append(row)
             if vector is not None:
                 self._extra.setdefault(cid, {})["vector"] = vector
         self.save()
@@ -477,7 +470,7 @@ class VLite:
         self._texts.clear()
         self._metas.clear()
         self._extra.clear()
-        self._postings.clear()
+        self._meta_index.clear()
         i = 0
         while i == 0 or os.path.exists(self.ctx.get(self._part_name(i))):
             self.ctx.delete(self._part_name(i))
@@ -550,7 +543,7 @@ class ShardedVLite(VLite):
         else:
             if self._corpus is not None:
                 self._corpus.clear()
-            for d in (self._row_of, self._texts, self._metas, self._extra, self._postings):
+            for d in (self._row_of, self._texts, self._metas, self._extra, self._meta_index):
                 d.clear()
             self._ids.clear()
         if dist.is_initialized():

@@ -10,8 +10,9 @@ Same names and argument meaning as the reference class; the arithmetic runs in t
     unspecified (vlite/model.py:85).
   * ``embed(texts, precision="binary")`` (vlite/model.py:25-48) -- the Hugging Face forward pass
     stays on the reference path (torch + transformers, out of scope for this build); the
-    quantisation tail ``(x > 0) -> packbits -> int8 - 128`` (vlite/model.py:39-44) runs on the
-    device (``vl_quantize_binary``).  Returned values are the reference's stored encoding
+    quantisation tail ``normalize -> CLS -> (x > 0) -> packbits -> int8 - 128`` (vlite/model.py:35-44)
+    runs on the device (``vl_quantize_embeddings`` for a CUDA tensor, ``vl_quantize_binary`` for a
+    host array); ``embed_device`` also hands out the int8 / float32 forms the rescorer takes.  Returned values are the reference's stored encoding
     ``int8(u8) - 128`` as int16 in [-256, -1] (what numpy 1.x produces for that line).
   * ``hamming_distance`` (vlite/model.py:71-74) -- on 0/1 arrays, computed as popcount(XOR) of the
     packed bits on the device.
@@ -69,16 +70,18 @@ class EmbeddingModel:
         self.model = AutoModel.from_pretrained(self.model_name).to(self.device)
 
     def _forward(self, texts):
-        """float embeddings (B, D): CLS token of the L2-normalised last hidden state
-        (vlite/model.py:30-36)."""
+        """float embeddings (B, D): the CLS token of the last hidden state (vlite/model.py:30-36).
+        An ``embedder`` callable returns whatever it returns (numpy or a CUDA tensor); the HF path
+        returns the raw CLS rows as a CUDA tensor -- normalising one token's row equals taking that
+        token from the normalised tensor (model.py:35-36), and the fused kernel does it."""
         if self._embedder is not None:
-            return np.asarray(self._embedder(texts), dtype=np.float32)
+            x = self._embedder(texts)
+            return x if hasattr(x, "data_ptr") else np.asarray(x, dtype=np.float32)
         import torch
         self._load_hf()
         inputs = self.tokenizer(texts, padding=True, truncation=True, return_tensors="pt").to(self.device)
         with torch.no_grad():
             outputs = self.model(**inputs).last_hidden_state
-        outputs = torch.nn.functional.normalize(outputs, p=2, dim=2)
         return outputs[:, 0].float().contiguous()
 
     def embed(self, texts, precision="binary"):
@@ -88,16 +91,45 @@ class EmbeddingModel:
             raise ValueError(f"Unsupported precision: {precision}")
         return to_reference_encoding(self.embed_ubinary(texts))
 
+    def embed_device(self, texts, int8=False, float32=False, i8_scale=127.0):
+        """The quantisation tail fused on the device (``vl_quantize_embeddings``): returns a dict of
+        CUDA tensors -- ``"ubinary"`` (B, binary_dims/8) uint8 for the scan and, on request,
+        ``"int8"`` (B, D) = rint(clamp(x_norm * i8_scale, -127, 127)) and ``"float32"`` (B, D) =
+        the L2-normalised embedding, the forms ``vl_rescore`` takes.  Nothing touches the host."""
+        import torch
+        if isinstance(texts, str):
+            texts = [texts]
+        x = self._forward(texts)
+        dev = torch.device("cuda", self.gpu_index)
+        if isinstance(x, np.ndarray):
+            x = torch.from_numpy(np.ascontiguousarray(x, dtype=np.float32))
+        x = x.to(dev, torch.float32).contiguous()
+        n, dims = x.shape
+        out = {"ubinary": torch.empty((n, self.binary_dims // 8), dtype=torch.uint8, device=dev)}
+        if int8:
+            out["int8"] = torch.empty((n, dims), dtype=torch.int8, device=dev)
+        if float32:
+            out["float32"] = torch.empty((n, dims), dtype=torch.float32, device=dev)
+        _capi.quantize_embeddings(x, self.binary_dims, out["ubinary"], out.get("int8"), out.get("float32"),
+                                  i8_scale=i8_scale, device=self.gpu_index,
+                                  stream=torch.cuda.current_stream(dev).cuda_stream)
+        return out
+
     def embed_ubinary(self, texts) -> np.ndarray:
         """Same as ``embed`` but returns raw ubinary bytes (B, binary_dims/8), the device format."""
         if isinstance(texts, str):
             texts = [texts]
         x = self._forward(texts)
-        x = x[:, : self.binary_dims]
-        if not isinstance(x, np.ndarray):                      # torch tensor on the GPU: no host round trip
-            x = x.contiguous()
-        else:
-            x = np.ascontiguousarray(x, dtype=np.float32)
+        if not isinstance(x, np.ndarray):                      # CUDA tensor: fused tail, no host round trip
+            import torch
+            x = x.to(torch.float32).contiguous()
+            if x.shape[1] % 32 or self.binary_dims % 32 or self.binary_dims > x.shape[1]:
+                raise ValueError("embedding width must be a multiple of 32 bits")
+            out = torch.empty((x.shape[0], self.binary_dims // 8), dtype=torch.uint8, device=x.device)
+            _capi.quantize_embeddings(x, self.binary_dims, out, device=x.device.index or 0,
+                                      stream=torch.cuda.current_stream(x.device).cuda_stream)
+            return out.cpu().numpy()
+        x = np.ascontiguousarray(x[:, : self.binary_dims], dtype=np.float32)
         if x.shape[1] % 32:
             raise ValueError("embedding width must be a multiple of 32 bits")
         return _capi.quantize_binary(x, device=self.gpu_index)
