@@ -114,6 +114,53 @@ def test_filter_masks_follow_updates_deletes_and_none_terms(gpu, tmp_path):
     v.close()
 
 
+def test_concurrent_callers_take_turns(gpu, tmp_path):
+    """One VLite shared by several threads (the reference's server does exactly that,
+    vlite/server.py:14): filtered retrieves stay exact while another thread keeps appending."""
+    import threading
+    from vlite_b200 import VLite
+    n, w = 2000, 128
+    corpus = synth.corpus_rows(91, 0, n, w)
+    queries = synth.uniform_queries(92, 4, w)
+    v = VLite("mt", ctx_dir=str(tmp_path / "contexts"), embedder=bits_embedder(queries), width=w, metric="hamming")
+    v.set_batch([f"t{i}" for i in range(n)], osearch.to_ref_encoding(corpus), [{"g": "old"} for _ in range(n)])
+    keys = list(v.dump().keys())
+    es, er = osearch.search(queries, corpus, 6, osearch.HAMMING)
+    want = [[(keys[int(r)], int(s)) for s, r in zip(es[q], er[q])] for q in range(4)]
+    errors, stop = [], threading.Event()
+
+    def reader():
+        try:
+            for _ in range(25):
+                got = v.retrieve_batch(["q"] * 4, top_k=6, metadata={"g": "old"}, return_scores=True)
+                assert [[(g[0], int(g[3])) for g in row] for row in got] == want
+        except Exception as e:                                            # noqa: BLE001
+            errors.append(e)
+
+    def writer():
+        i = 0
+        try:
+            while not stop.is_set() and i < 40:
+                extra = synth.corpus_rows(1000 + i, 0, 300, w)
+                v.set_batch([f"n{i}_{j}" for j in range(300)], osearch.to_ref_encoding(extra),
+                            [{"g": "new"} for _ in range(300)])
+                i += 1
+        except Exception as e:                                            # noqa: BLE001
+            errors.append(e)
+
+    readers = [threading.Thread(target=reader) for _ in range(4)]
+    wr = threading.Thread(target=writer)
+    for t in readers + [wr]:
+        t.start()
+    for t in readers:
+        t.join()
+    stop.set()
+    wr.join()
+    assert not errors, errors
+    assert v.count() > n
+    v.close()
+
+
 def test_retrieve_merges_all_queries_like_reference(gpu, golden, tmp_path):
     v = _build(gpu, golden, tmp_path)
     r = v.retrieve(["a", "b"], top_k=4, return_scores=True)          # two query rows -> ONE list

@@ -24,8 +24,10 @@ Embedding generation (the Hugging Face forward pass) stays on the reference path
 from __future__ import annotations
 
 import datetime
+import functools
 import logging
 import os
+import threading
 from uuid import uuid4
 
 import numpy as np
@@ -59,6 +61,17 @@ def chop_and_chunk(text, max_seq_length=512, fast=False):
             else:
                 chunks.extend(enc.decode(ids[i:i + max_seq_length]) for i in range(0, len(ids), max_seq_length))
     return chunks
+
+
+def _locked(method):
+    """Serialise a public method on the instance lock: the reference shares ONE VLite between all
+    server requests with no locking (vlite/server.py:14); here a handle owns a CUDA stream and
+    grow-only workspaces, so concurrent callers take turns (re-entrant: set -> update -> save)."""
+    @functools.wraps(method)
+    def wrapper(self, *args, **kw):
+        with self._lock:
+            return method(self, *args, **kw)
+    return wrapper
 
 
 class _IndexView(dict):
@@ -110,6 +123,7 @@ class VLite:
             raise ValueError(f"metric must be one of {sorted(METRICS)}")
         if filter_mode not in ("prefilter", "reference"):
             raise ValueError("filter_mode must be 'prefilter' or 'reference'")
+        self._lock = threading.RLock()
         self.device = device or "cuda"
         if collection is None:
             collection = f"vlite_{datetime.datetime.now().strftime('%Y%m%d_%H%M%S')}"
@@ -246,6 +260,7 @@ class VLite:
         return scores, rows
 
     # ------------------------------------------------------------------ API
+    @_locked
     def add(self, data, metadata=None, item_id=None, need_chunks=False, fast=True):
         """vlite/main.py:61-104 -- including its quirks: one item_id is generated and reused for
         every item of the call, chunk ids run ``{item_id}_{n}`` over all chunks, the return value is
@@ -273,6 +288,7 @@ class VLite:
                 self._register(f"{item_id}_{idx}", chunk, md, first + idx)
         return [(item_id, encoded, all_metadata[-1] if all_metadata else item_metadata)]
 
+    @_locked
     def retrieve(self, text=None, top_k=5, metadata=None, return_scores=False, top_k_multiplier=4):
         """vlite/main.py:108-128: every query row is ranked, ALL results are merged, sorted by
         score and cut to top_k -- a list of Q texts yields ONE list.  Falsy text returns None."""
@@ -288,6 +304,7 @@ class VLite:
             return [(cid, self._texts[cid], self._metas[cid], score) for cid, score in results]
         return [(cid, self._texts[cid], self._metas[cid]) for cid, _ in results]
 
+    @_locked
     def retrieve_batch(self, texts, top_k=5, metadata=None, return_scores=False, top_k_multiplier=4):
         """One result list PER query (the reference merges them, main.py:116-121).  One batched scan."""
         queries = self.model.embed(texts, precision="binary")
@@ -319,11 +336,13 @@ class VLite:
             out.append([(self._ids[int(r)], np.int64(s)) for s, r in zip(s_row[keep], r_row[keep])])
         return out
 
+    @_locked
     def rank_and_filter(self, query_binary_vector, top_k, metadata=None, top_k_multiplier=4):
         """vlite/main.py:130-168 for ONE query vector: list of (chunk_id, score)."""
         q = np.array(query_binary_vector).reshape(1, -1)
         return self._rank_batch(q, top_k, metadata, top_k_multiplier)[0]
 
+    @_locked
     def update(self, id, text=None, metadata=None, vector=None):
         """vlite/main.py:170-188 (the vector is stored under 'vector' and not searched, as there)."""
         chunk_ids = [cid for cid in self._row_of if cid.startswith(f"{id}_")]
@@ -347,6 +366,7 @@ class VLite:
         self.save()
         return True
 
+    @_locked
     def delete(self, ids):
         """vlite/main.py:190-205: prefix match on ``{id}_``; returns the number of chunks removed."""
         if isinstance(ids, str):
@@ -368,6 +388,7 @@ class VLite:
             self.save()
         return deleted
 
+    @_locked
     def get(self, ids=None, where=None):
         """vlite/main.py:207-231."""
         items = []
@@ -389,6 +410,7 @@ class VLite:
             items = [it for it in items if all(it[2].get(k) == v for k, v in where.items())]
         return items
 
+    @_locked
     def set(self, id, text=None, metadata=None, vector=None):
         """vlite/main.py:233-240."""
         if any(cid.startswith(f"{id}_") for cid in self._row_of):
@@ -396,6 +418,7 @@ class VLite:
         else:
             self.add(text, metadata=metadata, item_id=id)
 
+    @_locked
     def set_batch(self, texts, embeddings, metadatas=None):
         """vlite/main.py:243-274: precomputed embeddings, one fresh uuid per row, then save()."""
         if not isinstance(texts, list):
@@ -414,9 +437,11 @@ class VLite:
                 self._register(f"{uid}_0", text, md, first + i)
         self.save()
 
+    @_locked
     def count(self):
         return len(self._row_of)
 
+    @_locked
     def save(self, _all_rows=None):
         """vlite/main.py:280-294, written CLEAN: one row per live key in key order (the reference's
         context manager loads the old file first and appends the whole collection to it again,
@@ -461,6 +486,7 @@ class VLite:
             self.ctx.delete(self._part_name(stale))
             stale += 1
 
+    @_locked
     def clear(self):
         """vlite/main.py:296-300."""
         if self._corpus is not None:
@@ -488,6 +514,7 @@ class VLite:
     def dump(self):
         return self.index
 
+    @_locked
     def close(self):
         if self._corpus is not None:
             self._corpus.close()
