@@ -8,21 +8,24 @@
 // tensor cores):
 //   grid  = (query tiles, row splits).  A CTA owns QT = C*WQ queries (staged in
 //           shared memory once) and a contiguous range of 256-row corpus tiles.
-//   warps = 8 per CTA, two CTAs per SM.  One elected thread streams tiles (rows +
-//           the tile's 32 B of live mask + 32 B of filter mask) global -> shared
-//           with cp.async.bulk (TMA, SASS UBLKCP) into a multi-stage mbarrier
-//           ring (full/empty barriers); no warp touches global memory in the
-//           loop.  Warp (wq, wr): query group wq (C queries in a register
-//           tile), row slice wr of every tile.
-//   lane  = one corpus row per lane (R rows per step), 128-bit LDS.  Lane l
-//           walks its row's 16 B chunks in the rotated order j ^ rot(l), which
-//           makes both the row reads (stride W) and the query reads bank-
-//           conflict free on the linear tile layout TMA 1-D copies produce.
+//   warps = 8 per CTA, two CTAs per SM.  One elected thread streams tiles global ->
+//           shared into a multi-stage mbarrier ring (full/empty barriers): the rows
+//           by 2-D tensor loads through a CUtensorMap of the corpus
+//           (cp.async.bulk.tensor.2d, SASS UTMALDG, hardware swizzle), the tile's
+//           32 B of live mask + 32 B of filter mask by 1-D bulk copies (UBLKCP).
+//           No warp touches global memory in the loop.  Warp (wq, wr): query
+//           group wq (C queries in a register tile), row slice wr of every tile.
+//   lane  = one corpus row per lane (R rows per step), 128-bit LDS.  The TMA
+//           swizzle stores logical 16 B chunk j of row r at physical chunk
+//           j ^ f(r), so the stride-W row reads are bank-conflict free while all
+//           lanes work on the same logical chunk (query reads are broadcasts).
+//   score = HAMMING: carry-save adders (LOP3) + POPC + IMAD; XORSUM: LOP3 + IDP4A.
 //   top-k = each (warp, query) keeps a sorted k-list in shared memory and its
-//           k-th best score in a register; rows are visited in ascending
-//           index order, so "score < threshold" + insert-after-equals IS the
-//           (score, row) tie-break.  A step whose 32*R*C scores all fail the
-//           threshold test costs one vote; insertions are warp-cooperative.
+//           k-th best score in a register; the hot loop compares the minimum of
+//           a query's R scores with that threshold.  On a hit the flagged rows
+//           enter the list by key (score << 32 | row) -- the (score, row)
+//           tie-break whatever the arrival order.  Device-wide per-query bounds
+//           (tau, candidate histogram) let every CTA prune rows early.
 //   out   = every (split, row slice) list goes to a partial buffer that the
 //           merge kernel (merge.cuh) reduces with the same (score, row) order.
 #pragma once
@@ -235,7 +238,10 @@ __device__ __forceinline__ uint32_t score_chunk_pair(const uint4& ra, const uint
 }
 
 template <int W, int METRIC, int C, int WQ, int TPS>
-__global__ void __launch_bounds__(kScanThreads, 2)
+#ifndef VL_MINBLOCKS
+#define VL_MINBLOCKS 2
+#endif
+__global__ void __launch_bounds__(kScanThreads, VL_MINBLOCKS)
 scan_topk_kernel(const __grid_constant__ CUtensorMap tmap, const ScanParams p) {
     using Cfg = ScanCfg<W, C, WQ, TPS>;
     constexpr int WR = Cfg::WR, RPW = Cfg::RPW, R = Cfg::R, STEPS = Cfg::STEPS, QT = Cfg::QT;
