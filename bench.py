@@ -127,7 +127,8 @@ def make_queries(n_rows_total: int, nq: int, width: int):
 # ------------------------------------------------------------------------------------------
 # reference arm / cpu_baseline: the oracle's torch-op port of EmbeddingModel.search on host cores
 # ------------------------------------------------------------------------------------------
-def time_reference(steps: int, warmup: int, budget_s: float = 150.0):
+def time_reference(steps, warmup: int, budget_s: float = 150.0, target_s: float = 15.0):
+    """steps=None: as many one-query calls as fit ~target_s seconds of CPU work (6..1024)."""
     import torch
     from oracle import ref_port, synth
     rows = ROWS_PER_GPU
@@ -142,6 +143,8 @@ def time_reference(steps: int, warmup: int, budget_s: float = 150.0):
     ref_port.search_port(q_ref[0], e, TOP_K)
     per_row = (time.perf_counter() - t0) / probe_n
     n_sample = rows
+    if steps is None:
+        steps = int(min(1024, max(6, target_s / max(per_row * rows, 1e-9))))
     est = per_row * rows * (steps + warmup)
     if est > budget_s:
         n_sample = max(probe_n, int(rows * budget_s / est) // 1000 * 1000)
@@ -372,7 +375,7 @@ def run_ours(args):
                 tt.append(corpus.last_timing()[0])
         extra["xorsum_same_workload"] = {"ms_per_step": float(np.mean(tt)), "qps": nq / (float(np.mean(tt)) * 1e-3)}
         if rank == 0 and not args.no_cpu:
-            qps, ms, cores, sample = time_reference(6, 1, budget_s=40.0)
+            qps, ms, cores, sample = time_reference(None, 2, budget_s=40.0, target_s=15.0)
             cpu_baseline = {"value": qps, "unit": "queries/s", "cores": cores, "kind": "port", "sample": sample}
 
     if rank == 0:
