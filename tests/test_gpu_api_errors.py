@@ -73,3 +73,50 @@ def test_launch_counter_counts_library_kernels(gpu):
         c.fill_synthetic(0, 0, 1000)
         c.search(synth.uniform_queries(1, 3, 128), 4)
     assert gpu.launch_count() - before >= 4          # fill, live-mask, scan, merge
+
+
+def test_out_of_memory_is_an_error_not_a_crash(gpu):
+    """Asking for more rows than the device can back fails with VL_ENOMEM (one failed
+    cuMemCreate, nothing half-mapped) and leaves the handle usable."""
+    corpus = synth.corpus_rows(8, 0, 300, 128)
+    with gpu.Corpus(128) as c:
+        c.append(corpus)
+        ptrs = c.device_ptrs()
+        with pytest.raises(gpu.VliteB200Error) as ei:
+            c.reserve(2_100_000_000)                                  # 269 GB of rows on a 180 GB device
+        assert ei.value.code in (gpu.ENOMEM, gpu.EINVAL)
+        assert c.device_ptrs() == ptrs and c.rows == 300
+        c.append(corpus[:10])
+        s, r = c.search(corpus[3:4], 2, gpu.HAMMING)
+        assert list(r[0]) == [3, 303] and list(s[0]) == [0, 0]
+
+
+def test_independent_handles_on_concurrent_threads(gpu):
+    """Different handles are independent (include/vlite_b200.h): two threads, each with its own
+    corpus, stream, k and row width, search at the same time (ctypes drops the GIL) and both stay
+    exact -- kernel attributes are per device, not per handle."""
+    import threading
+    from oracle import search as osearch
+    specs = [(128, 32, osearch.HAMMING, 41), (64, 3, osearch.XORSUM, 42), (128, 100, osearch.XORSUM, 43)]
+    errors = []
+
+    def worker(w, k, metric, seed):
+        try:
+            corpus = synth.corpus_rows(seed, 0, 5000, w)
+            q = synth.uniform_queries(seed + 100, 9, w)
+            es, er = osearch.search(q, corpus, k, metric)
+            with gpu.Corpus(w) as c:
+                c.append(corpus)
+                for _ in range(40):
+                    s, r = c.search(q, k, metric)
+                    np.testing.assert_array_equal(s, es)
+                    np.testing.assert_array_equal(r, er)
+        except Exception as e:                                        # noqa: BLE001
+            errors.append(e)
+
+    threads = [threading.Thread(target=worker, args=sp) for sp in specs]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors

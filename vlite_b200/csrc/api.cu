@@ -404,6 +404,24 @@ int make_corpus_tmap(const vl_corpus* c, CUtensorMap* out) {
     return VL_OK;
 }
 
+// Opt a kernel in to the full 227 KB of dynamic shared memory ONCE per device.  The attribute
+// belongs to the (function, context), not to a handle or a thread: setting it to each launch's
+// own size would let two handles on different threads shrink it under each other.
+int allow_max_smem_fn(const void* kern, int device) {
+    static std::mutex mu;
+    static std::vector<std::pair<const void*, int>> done;   // (kernel, device) pairs already opted in
+    std::lock_guard<std::mutex> lock(mu);
+    for (const auto& d : done)
+        if (d.first == kern && d.second == device) return VL_OK;
+    CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    done.emplace_back(kern, device);
+    return VL_OK;
+}
+template <typename K>
+int allow_max_smem(K kern, int device) {
+    return allow_max_smem_fn(reinterpret_cast<const void*>(kern), device);
+}
+
 // ---- scan dispatch -------------------------------------------------------------
 
 struct ScanPlan {
@@ -430,7 +448,8 @@ int launch_scan_cfg(vl_corpus* c, ScanParams& p, int n_queries, int k, ScanPlan*
     while (stages > 1 && total(stages) > max_smem) --stages;
     const size_t smem = total(stages);
     if (smem > max_smem) return fail(VL_EINVAL, "k=%d needs %zu B of shared memory per CTA (max %zu)", k, smem, max_smem);
-    // per-kernel launch attributes are set (and the occupancy asked for) once per shared-memory size
+    TRY(allow_max_smem(kern, c->device));
+    // the occupancy of this kernel at this shared-memory size is asked for once per thread
     static thread_local size_t cached_smem[64] = {};
     static thread_local int cached_occ[64] = {};
     int occ = 0;
@@ -438,7 +457,6 @@ int launch_scan_cfg(vl_corpus* c, ScanParams& p, int n_queries, int k, ScanPlan*
     if (cached_smem[dev_slot] == smem && cached_occ[dev_slot] > 0) {
         occ = cached_occ[dev_slot];
     } else {
-        CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kScanThreads, smem));
         if (occ < 1) return fail(VL_ECUDA, "scan kernel does not fit on an SM (smem %zu)", smem);
         cached_smem[dev_slot] = smem;
@@ -697,7 +715,7 @@ int search_large_k(vl_corpus* c, ScanParams p, int n_queries, int k, int metric,
     TRY(launch_scan(c, pc, n_queries, 1, metric, nullptr, /*dry=*/false));
     if (c->timing) CU(cudaEventRecord(c->ev1, st));
     const size_t smem = (size_t)cap * 8;
-    CU(cudaFuncSetAttribute(collect_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    TRY(allow_max_smem(collect_select_kernel, c->device));
     collect_select_kernel<<<n_queries, kSelectThreads, smem, st>>>(pc.collect_keys, cnt, thr, cap, k, c->base_row, o_s,
                                                                 o_r, flags);
     LAUNCHED();
@@ -1256,10 +1274,10 @@ extern "C" int vl_rescore(vl_corpus* c, const int8_t* docs_i8_dev, uint64_t n_do
     c->timed = false;
     if (c->timing) CU(cudaEventRecord(c->ev0, st));
     if (qtype == VL_QTYPE_I8) {
-        CU(cudaFuncSetAttribute(rescore_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        TRY(allow_max_smem(rescore_kernel<true>, c->device));
         rescore_kernel<true><<<n_queries, kRescoreThreads, smem, st>>>(p);
     } else {
-        CU(cudaFuncSetAttribute(rescore_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        TRY(allow_max_smem(rescore_kernel<false>, c->device));
         rescore_kernel<false><<<n_queries, kRescoreThreads, smem, st>>>(p);
     }
     LAUNCHED();
