@@ -203,6 +203,25 @@ int vl_set_timing(vl_corpus* c, int enabled);
  * stages = depth of the TMA ring, or -1 to force the exact multi-pass path for k > 32 */
 int vl_set_tuning(vl_corpus* c, int row_splits, int stages);
 
+/* ---- shard group: several shards searched as one corpus, in one process --- */
+/* The in-process twin of the one-process-per-GPU path (the reference has no
+ * multi-GPU counterpart).  A group borrows corpus handles -- usually one per GPU, any mix of
+ * devices works -- whose base rows the caller has set (vl_corpus_set_base_row) so that global rows
+ * are disjoint.  vl_shard_group_search replicates the queries to every shard, lets all shards scan
+ * concurrently on their own streams, moves each shard's k candidates to the first shard's device
+ * with a peer copy (NVLink between peers) and merges them there by (score, global row): the
+ * result equals vl_search over the concatenated corpus.  Host pointers only; the call returns
+ * when the results are in out_*.  filter_masks_or_null: NULL, or one mask pointer (or NULL) per
+ * shard, each in that shard's local row numbering.  A group does not own its shards: destroy the
+ * group first, then the handles.  One call at a time per group. */
+typedef struct vl_shard_group vl_shard_group;
+int vl_shard_group_create(int n_shards, vl_corpus* const* shards, vl_shard_group** out);
+int vl_shard_group_destroy(vl_shard_group* g);
+int vl_shard_group_rows(const vl_shard_group* g, uint64_t* rows, uint64_t* live_rows);
+int vl_shard_group_search(vl_shard_group* g, const uint8_t* queries_host, int n_queries, int k, int metric,
+                          const uint32_t* const* filter_masks_or_null, uint32_t* out_score_host,
+                          uint64_t* out_row_host);
+
 #ifdef __cplusplus
 }
 #endif

@@ -84,6 +84,11 @@ def load():
         "vl_map_rows": (c_int, [c_int, c_void_p, c_void_p, c_u64, c_void_p, c_void_p, c_int]),
         "vl_rescore": (c_int, [c_void_p, c_void_p, c_u64, c_int, c_void_p, c_int, c_void_p, c_int, c_int, c_int,
                                c_void_p, c_void_p]),
+        "vl_shard_group_create": (c_int, [c_int, ctypes.POINTER(c_void_p), ctypes.POINTER(c_void_p)]),
+        "vl_shard_group_destroy": (c_int, [c_void_p]),
+        "vl_shard_group_rows": (c_int, [c_void_p, ctypes.POINTER(c_u64), ctypes.POINTER(c_u64)]),
+        "vl_shard_group_search": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, ctypes.POINTER(c_void_p),
+                                          c_void_p, c_void_p]),
         "vl_quantize_binary": (c_int, [c_int, c_void_p, c_void_p, c_u64, c_int, c_void_p]),
         "vl_quantize_embeddings": (c_int, [c_int, c_void_p, c_void_p, c_u64, c_int, c_int, ctypes.c_float,
                                            c_void_p, c_void_p, c_void_p]),
@@ -306,6 +311,76 @@ class Corpus:
 
     def set_tuning(self, row_splits: int = 0, stages: int = 0):
         check(self._L.vl_set_tuning(self._h, row_splits, stages))
+
+
+class ShardGroup:
+    """Several ``Corpus`` shards (usually one per GPU) searched as one corpus from this process
+    (``vl_shard_group_*``).  The group borrows the shards; their base rows must be disjoint."""
+
+    def __init__(self, shards):
+        self._L = load()
+        self.shards = list(shards)
+        arr = (ctypes.c_void_p * len(self.shards))(*[c._h.value for c in self.shards])
+        self._h = ctypes.c_void_p()
+        check(self._L.vl_shard_group_create(len(self.shards), arr, ctypes.byref(self._h)))
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            self._L.vl_shard_group_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    @property
+    def rows(self) -> int:
+        n, live = ctypes.c_uint64(), ctypes.c_uint64()
+        check(self._L.vl_shard_group_rows(self._h, ctypes.byref(n), ctypes.byref(live)))
+        return n.value
+
+    @property
+    def live_rows(self) -> int:
+        n, live = ctypes.c_uint64(), ctypes.c_uint64()
+        check(self._L.vl_shard_group_rows(self._h, ctypes.byref(n), ctypes.byref(live)))
+        return live.value
+
+    def search(self, queries, k: int, metric: int = HAMMING, filter_masks=None):
+        """queries (Q, W) uint8 host array; filter_masks: None or one uint32 mask (or None) per
+        shard in that shard's local row numbering.  Returns host (scores (Q,k), rows (Q,k))."""
+        q = np.ascontiguousarray(np.atleast_2d(queries), dtype=np.uint8)
+        if q.shape[1] != self.shards[0].width:
+            raise ValueError("query width does not match the corpus")
+        if k < 1:
+            raise VliteB200Error(EINVAL, "k must be >= 1")
+        nq = q.shape[0]
+        scores = np.empty((nq, k), dtype=np.uint32)
+        rows = np.empty((nq, k), dtype=np.uint64)
+        masks = None
+        keep = []
+        if filter_masks is not None:
+            if len(filter_masks) != len(self.shards):
+                raise ValueError("one filter mask (or None) per shard")
+            masks = (ctypes.c_void_p * len(self.shards))()
+            for i, (m, c) in enumerate(zip(filter_masks, self.shards)):
+                if m is None:
+                    masks[i] = None
+                    continue
+                m = np.ascontiguousarray(m, dtype=np.uint32)
+                if m.shape[0] * 32 < c.rows:
+                    raise ValueError("filter mask shorter than its shard")
+                keep.append(m)
+                masks[i] = m.ctypes.data
+        check(self._L.vl_shard_group_search(self._h, ptr(q), nq, int(k), int(metric), masks, ptr(scores), ptr(rows)))
+        return scores, rows
 
 
 def merge_topk(scores_dev, rows_dev, n_lists: int, n_queries: int, k_in: int, k_out: int,
