@@ -503,12 +503,13 @@ int launch_scan_cfg(vl_corpus* c, ScanParams& p, int n_queries, int k, ScanPlan*
 
 template <int W, int METRIC>
 int launch_scan_wm(vl_corpus* c, ScanParams& p, int nq, int k, ScanPlan* plan, bool dry) {
-    // Q <= 2 is HBM-bound: one box per stage.  3 <= Q <= 16 has few queries per warp: where two
+    // Q = 1 is HBM-bound: one box per stage.  2 <= Q <= 16 has few queries per warp: where two
     // boxes still fit a 32 KB stage (W = 64) a stage carries two, so every warp scores twice the rows
     // per step at unchanged occupancy (+8 %); at W = 128 the lost CTA per SM costs more (-15 %, measured).
     constexpr int VL_MIDQ_TPS = (W <= 64) ? 2 : 1;
+    // (two boxes per stage at W <= 64 also for Q = 2: 5.0 -> 6.1 TB/s on 32M x 64 B; Q = 1 gains nothing)
     if (nq <= 1) return launch_scan_cfg<W, METRIC, 1, 1, 1>(c, p, nq, k, plan, dry);
-    if (nq <= 2) return launch_scan_cfg<W, METRIC, 2, 1, 1>(c, p, nq, k, plan, dry);
+    if (nq <= 2) return launch_scan_cfg<W, METRIC, 2, 1, VL_MIDQ_TPS>(c, p, nq, k, plan, dry);
     if (nq <= 4) return launch_scan_cfg<W, METRIC, 4, 1, VL_MIDQ_TPS>(c, p, nq, k, plan, dry);
     if (nq <= 8) return launch_scan_cfg<W, METRIC, 8, 1, VL_MIDQ_TPS>(c, p, nq, k, plan, dry);
     if (nq <= 16) return launch_scan_cfg<W, METRIC, 8, 2, VL_MIDQ_TPS>(c, p, nq, k, plan, dry);
