@@ -217,6 +217,12 @@ int vl_set_tuning(vl_corpus* c, int row_splits, int stages);
 typedef struct vl_shard_group vl_shard_group;
 int vl_shard_group_create(int n_shards, vl_corpus* const* shards, vl_shard_group** out);
 int vl_shard_group_destroy(vl_shard_group* g);
+/* Optional, for shards that grow by interleaved appends: segment i of `shard` covers its local rows
+ * from seg_local[i] (up to the next start) and global rows from seg_global[i]; both tables ascend
+ * and the shard's base row must be 0.  Results then carry those global rows (insertion order), so
+ * they do not depend on how batches were placed.  n_segments = 0 switches back to base rows. */
+int vl_shard_group_set_segments(vl_shard_group* g, int shard, const uint64_t* seg_local,
+                                const uint64_t* seg_global, int n_segments);
 int vl_shard_group_rows(const vl_shard_group* g, uint64_t* rows, uint64_t* live_rows);
 int vl_shard_group_search(vl_shard_group* g, const uint8_t* queries_host, int n_queries, int k, int metric,
                           const uint32_t* const* filter_masks_or_null, uint32_t* out_score_host,

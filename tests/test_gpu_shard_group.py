@@ -112,3 +112,60 @@ def test_group_spread_over_every_gpu(gpu):
             np.testing.assert_array_equal(r, er)
     for c in shards:
         c.close()
+
+
+def test_vlite_over_several_shards_in_one_process(gpu, tmp_path):
+    """VLite(gpus=[...]) row-shards the collection inside this process; every answer must equal
+    the single-GPU collection's -- same ids, same scores, same order -- through interleaved adds,
+    filters, deletes, save and reload."""
+    from vlite_b200 import VLite
+    from oracle import search as osearch
+    n_dev = gpu.device_count()
+    gpus = list(range(n_dev)) if n_dev >= 2 else [0, 0, 0]
+    w = 64
+    corpus = synth.corpus_rows(31, 0, 2600, w, period=500)             # duplicates: ties across shards
+    queries = synth.uniform_queries(32, 4, w)
+
+    def embedder(texts):
+        return np.unpackbits(queries[:len(texts)], axis=1).astype(np.float32) * 2 - 1
+
+    def build(name, **kw):
+        v = VLite(name, ctx_dir=str(tmp_path / name), embedder=embedder, width=w, metric="hamming", **kw)
+        off = 0
+        for b, size in enumerate((700, 1, 900, 333, 666)):               # ragged batches -> interleaved segments
+            enc = osearch.to_ref_encoding(corpus[off:off + size])
+            first = v._append_vectors(enc)
+            for i in range(size):
+                v._register(f"doc{off + i}_0", f"text {off + i}", {"batch": b, "odd": (off + i) % 2}, first + i)
+            off += size
+        return v
+
+    one, many = build("one"), build("many", gpus=gpus)
+    assert many.count() == one.count() == 2600
+
+    def same(**kw):
+        a = one.retrieve_batch(["q"] * 4, return_scores=True, **kw)
+        b = many.retrieve_batch(["q"] * 4, return_scores=True, **kw)
+        assert a == b
+        return a
+
+    same(top_k=7)
+    same(top_k=40)
+    same(top_k=9, metadata={"odd": 1})
+    same(top_k=9, metadata={"batch": 2, "odd": 0})
+    for v in (one, many):
+        assert v.delete([f"doc{i}" for i in (0, 699, 700, 701, 1600, 2599)]) == 6
+    got = same(top_k=12)
+    assert all(cid not in ("doc700_0", "doc2599_0") for row in got for cid, *_ in row)
+    np.testing.assert_array_equal(many._corpus.read(), one._corpus.read())
+    many.save()
+    many.close()
+    again = VLite("many", ctx_dir=str(tmp_path / "many"), embedder=embedder, width=w, metric="hamming", gpus=gpus)
+    assert again.count() == one.count()
+    a = one.retrieve_batch(["q"] * 4, top_k=10, return_scores=True)
+    b = again.retrieve_batch(["q"] * 4, top_k=10, return_scores=True)
+    assert [[(c, int(s)) for c, _, _, s in row] for row in a] == [[(c, int(s)) for c, _, _, s in row] for row in b]
+    again.clear()
+    assert again.count() == 0
+    again.close()
+    one.close()

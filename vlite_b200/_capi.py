@@ -86,6 +86,7 @@ def load():
                                c_void_p, c_void_p]),
         "vl_shard_group_create": (c_int, [c_int, ctypes.POINTER(c_void_p), ctypes.POINTER(c_void_p)]),
         "vl_shard_group_destroy": (c_int, [c_void_p]),
+        "vl_shard_group_set_segments": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int]),
         "vl_shard_group_rows": (c_int, [c_void_p, ctypes.POINTER(c_u64), ctypes.POINTER(c_u64)]),
         "vl_shard_group_search": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, ctypes.POINTER(c_void_p),
                                           c_void_p, c_void_p]),
@@ -352,6 +353,13 @@ class ShardGroup:
         n, live = ctypes.c_uint64(), ctypes.c_uint64()
         check(self._L.vl_shard_group_rows(self._h, ctypes.byref(n), ctypes.byref(live)))
         return live.value
+
+    def set_segments(self, shard: int, seg_local, seg_global):
+        sl = np.ascontiguousarray(seg_local, dtype=np.uint64)
+        sg = np.ascontiguousarray(seg_global, dtype=np.uint64)
+        if sl.shape != sg.shape:
+            raise ValueError("segment tables differ in length")
+        check(self._L.vl_shard_group_set_segments(self._h, shard, ptr(sl), ptr(sg), int(sl.shape[0])))
 
     def search(self, queries, k: int, metric: int = HAMMING, filter_masks=None):
         """queries (Q, W) uint8 host array; filter_masks: None or one uint32 mask (or None) per

@@ -1453,6 +1453,8 @@ struct vl_shard_group {
     cudaStream_t stream = nullptr;       // on the home device
     std::vector<cudaEvent_t> ev;         // per shard, created on the shard's device
     std::vector<DevBuf> q, s, r;         // per shard, on the shard's device
+    std::vector<DevBuf> seg;             // per shard: [local starts | global starts] of its appended segments
+    std::vector<int> n_seg;
     DevBuf gather_s, gather_r, out_s, out_r;  // home device
     void* pinned = nullptr;              // host staging: queries in, results out
     size_t pinned_bytes = 0;
@@ -1488,6 +1490,8 @@ extern "C" int vl_shard_group_create(int n_shards, vl_corpus* const* shards, vl_
     g->q.resize(n_shards);
     g->s.resize(n_shards);
     g->r.resize(n_shards);
+    g->seg.resize(n_shards);
+    g->n_seg.assign(n_shards, 0);
     int rc = VL_OK;
     {
         DeviceGuard dg(g->home);
@@ -1524,6 +1528,7 @@ extern "C" int vl_shard_group_destroy(vl_shard_group* g) {
         g->q[i].release();
         g->s[i].release();
         g->r[i].release();
+        g->seg[i].release();
     }
     {
         DeviceGuard dg(g->home);
@@ -1537,6 +1542,26 @@ extern "C" int vl_shard_group_destroy(vl_shard_group* g) {
         if (g->pinned) cudaFreeHost(g->pinned);
     }
     delete g;
+    return VL_OK;
+}
+
+extern "C" int vl_shard_group_set_segments(vl_shard_group* g, int shard, const uint64_t* seg_local,
+                                           const uint64_t* seg_global, int n_segments) {
+    if (!g) return fail(VL_EINVAL, "group is NULL");
+    if (shard < 0 || shard >= (int)g->shards.size()) return fail(VL_EINVAL, "shard %d out of range", shard);
+    if (n_segments < 0 || (n_segments > 0 && (!seg_local || !seg_global))) return fail(VL_EINVAL, "bad segment table");
+    for (int i = 1; i < n_segments; ++i)
+        if (seg_local[i] <= seg_local[i - 1] || seg_global[i] <= seg_global[i - 1])
+            return fail(VL_EINVAL, "segment starts must ascend");
+    vl_corpus* c = g->shards[shard];
+    DeviceGuard dg(c->device);
+    CU(cudaStreamSynchronize(c->stream));  // no search may still be reading the old table
+    g->n_seg[shard] = n_segments;
+    if (n_segments == 0) return VL_OK;
+    TRY(g->seg[shard].ensure((size_t)n_segments * 16));
+    uint64_t* d = static_cast<uint64_t*>(g->seg[shard].p);
+    CU(cudaMemcpy(d, seg_local, (size_t)n_segments * 8, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(d + n_segments, seg_global, (size_t)n_segments * 8, cudaMemcpyHostToDevice));
     return VL_OK;
 }
 
@@ -1592,6 +1617,12 @@ extern "C" int vl_shard_group_search(vl_shard_group* g, const uint8_t* queries_h
         TRY(vl_search(c, static_cast<const uint8_t*>(g->q[i].p), n_queries, k, metric,
                       filter_masks_or_null ? filter_masks_or_null[i] : nullptr, static_cast<uint32_t*>(g->s[i].p),
                       static_cast<uint64_t*>(g->r[i].p)));
+        if (g->n_seg[i] > 0) {  // shard-local rows -> global rows fixed at append time
+            const uint64_t* sl = static_cast<const uint64_t*>(g->seg[i].p);
+            map_rows_kernel<<<(unsigned)((n_out + 255) / 256), 256, 0, c->stream>>>(
+                static_cast<uint64_t*>(g->r[i].p), n_out, sl, sl + g->n_seg[i], g->n_seg[i]);
+            LAUNCHED();
+        }
         CU(cudaMemcpyPeerAsync(static_cast<uint32_t*>(g->gather_s.p) + (size_t)i * n_out, g->home, g->s[i].p, c->device,
                                n_out * 4, c->stream));
         CU(cudaMemcpyPeerAsync(static_cast<uint64_t*>(g->gather_r.p) + (size_t)i * n_out, g->home, g->r[i].p, c->device,

@@ -114,11 +114,13 @@ class _IndexView(dict):
 class VLite:
     def __init__(self, collection=None, device=None, model_name="mixedbread-ai/mxbai-embed-large-v1", *,
                  embedder=None, metric="xorsum", width=None, filter_mode="prefilter", ctx_dir="contexts",
-                 gpu_index=0):
+                 gpu_index=0, gpus=None):
         """collection / device / model_name: as vlite/main.py:20.  Keyword-only additions:
         embedder (texts -> float array), metric ("xorsum" = the reference's live score,
         "hamming" = true Hamming distance), width (bytes per row, default from the data: 64),
-        filter_mode ("prefilter" | "reference"), ctx_dir, gpu_index."""
+        filter_mode ("prefilter" | "reference"), ctx_dir, gpu_index, gpus (a list of device
+        indices: the collection is row-sharded over them inside this process; results are the
+        same as on one GPU)."""
         if metric not in METRICS:
             raise ValueError(f"metric must be one of {sorted(METRICS)}")
         if filter_mode not in ("prefilter", "reference"):
@@ -130,6 +132,9 @@ class VLite:
         self.collection = f"{collection}"
         self.metric = METRICS[metric]
         self.filter_mode = filter_mode
+        self.gpus = list(gpus) if gpus else None
+        if self.gpus:
+            gpu_index = self.gpus[0]
         self.gpu_index = gpu_index
         self.model = EmbeddingModel(model_name, device=self.device, embedder=embedder, gpu_index=gpu_index)
         if width:
@@ -157,7 +162,11 @@ class VLite:
     def _ensure_corpus(self, width: int):
         if self._corpus is None:
             self._width = self._width or width
-            self._corpus = _capi.Corpus(self._width, device=self.gpu_index)
+            if self.gpus and len(self.gpus) > 1:
+                from .sharded import LocalShardedCorpus
+                self._corpus = LocalShardedCorpus(self._width, self.gpus)
+            else:
+                self._corpus = _capi.Corpus(self._width, device=self.gpu_index)
         return self._corpus
 
     def _entry(self, chunk_id):

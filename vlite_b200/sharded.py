@@ -324,3 +324,131 @@ class ShardedCorpus:
 
     def close(self):
         self.backend.close()
+
+
+class LocalShardedCorpus:
+    """The single-process twin of ``ShardedCorpus``: one ``Corpus`` per listed GPU, searched as one
+    collection through ``vl_shard_group_*`` (per-device scans run concurrently, candidates travel to
+    the first GPU by peer copy, one merge there).  Placement and numbering follow the same rules --
+    a batch goes to the least-full shard, its GLOBAL base row is the running global count, tombstones
+    are shard-local -- so results equal the single-GPU collection's and the torchrun path's.
+
+    Offers the slice of the ``Corpus`` interface ``VLite`` uses, with global row numbers."""
+
+    def __init__(self, width: int, devices):
+        from . import _capi
+        self._capi = _capi
+        self.width = width
+        self.devices = list(devices)
+        if not self.devices:
+            raise ValueError("need at least one GPU")
+        self.shards = [_capi.Corpus(width, device=d) for d in self.devices]
+        self.group = _capi.ShardGroup(self.shards)
+        self.counts = [0] * len(self.shards)
+        self.segments = []                        # (global_base, owner, local_start, n), ascending global_base
+        self.total = 0
+
+    # ---- bookkeeping (same rules as ShardedCorpus) ----
+    def _add_segment(self, owner: int, n: int) -> int:
+        base = self.total
+        self.segments.append((base, owner, self.counts[owner], n))
+        self.counts[owner] += n
+        self.total += n
+        mine = [s for s in self.segments if s[1] == owner]
+        self.group.set_segments(owner, [s[2] for s in mine], [s[0] for s in mine])
+        return base
+
+    def locate(self, global_row: int):
+        import bisect
+        i = bisect.bisect_right([s[0] for s in self.segments], global_row) - 1
+        if i < 0 or global_row >= self.segments[i][0] + self.segments[i][3]:
+            raise IndexError(f"global row {global_row} out of range")
+        base, owner, lstart, _ = self.segments[i]
+        return owner, lstart + (global_row - base)
+
+    @property
+    def rows(self) -> int:
+        return self.total
+
+    @property
+    def live_rows(self) -> int:
+        return self.group.live_rows
+
+    # ---- ingest ----
+    def append(self, rows_u8) -> int:
+        rows_u8 = np.ascontiguousarray(rows_u8, dtype=np.uint8)
+        n = int(rows_u8.shape[0])
+        if n == 0:
+            return self.total
+        owner = min(range(len(self.shards)), key=lambda r: (self.counts[r], r))
+        first_local = self.shards[owner].append(rows_u8)
+        assert first_local == self.counts[owner]
+        return self._add_segment(owner, n)
+
+    def load_file(self, path: str, byte_off: int, byte_len: int, kind: int, max_rows: int = 0):
+        """The file's rows are cut into one contiguous slice per GPU, each streamed to its device."""
+        _capi = self._capi
+        row_bytes = {_capi.SRC_U8: self.width, _capi.SRC_F32_OFFSET: self.width * 4,
+                     _capi.SRC_F32_BITS: self.width * 32}[kind]
+        n = byte_len // row_bytes
+        if max_rows:
+            n = min(n, max_rows)
+        plan = ShardPlan(n, len(self.shards))
+        first = self.total
+        for r, c in enumerate(self.shards):
+            lo, cnt = plan.base_row(r), plan.shard_rows(r)
+            if cnt:
+                c.load_file(path, byte_off + lo * row_bytes, cnt * row_bytes, kind, max_rows=cnt)
+                self._add_segment(r, cnt)
+        return first, n
+
+    def tombstone(self, global_rows) -> None:
+        per = {}
+        for g in np.asarray(global_rows, dtype=np.int64).reshape(-1):
+            try:
+                owner, local = self.locate(int(g))
+            except IndexError:
+                continue
+            per.setdefault(owner, []).append(local)
+        for owner, rows in per.items():
+            self.shards[owner].tombstone(rows)
+
+    def clear(self):
+        for i, c in enumerate(self.shards):
+            c.clear()
+            self.group.set_segments(i, [], [])
+        self.counts = [0] * len(self.shards)
+        self.segments = []
+        self.total = 0
+
+    # ---- query ----
+    def _local_masks(self, mask_words_global):
+        bits = np.unpackbits(np.ascontiguousarray(mask_words_global, dtype=np.uint32).view(np.uint8),
+                             bitorder="little")
+        local = [np.zeros((n + 31) // 32 * 32, dtype=np.uint8) for n in self.counts]
+        for base, owner, lstart, n in self.segments:
+            local[owner][lstart:lstart + n] = bits[base:base + n]
+        return [np.packbits(b.reshape(-1, 32), axis=1, bitorder="little").view(np.uint32).reshape(-1) if b.size
+                else None for b in local]
+
+    def search(self, queries, k: int, metric: int = 0, filter_mask=None):
+        masks = self._local_masks(filter_mask) if filter_mask is not None else None
+        return self.group.search(queries, k, metric, masks)
+
+    def read(self, first: int = 0, n: int | None = None) -> np.ndarray:
+        if n is None:
+            n = self.total - first
+        out = np.zeros((n, self.width), dtype=np.uint8)
+        for base, owner, lstart, cnt in self.segments:
+            lo, hi = max(base, first), min(base + cnt, first + n)
+            if lo < hi:
+                out[lo - first:hi - first] = self.shards[owner].read(lstart + (lo - base), hi - lo)
+        return out
+
+    def close(self):
+        if self.group is not None:
+            self.group.close()
+            self.group = None
+        for c in self.shards:
+            c.close()
+        self.shards = []
