@@ -309,3 +309,15 @@ def test_random_differential(gpu):
             s, r = c.search(queries, k, metric, mask)
         es, er = cscan.search(queries, corpus, k, metric, synth.pack_mask(valid))
         assert np.array_equal(s, es) and np.array_equal(r, er), (case, w, n, nq, k, metric, period)
+
+
+def test_very_large_query_batch(gpu):
+    """17k queries in one call (past the size where the candidate histogram is skipped): still
+    bit-exact, both metrics."""
+    n, w, nq = 3000, 128, 17_000
+    corpus = synth.corpus_rows(61, 0, n, w, period=700)
+    queries = synth.uniform_queries(62, nq, w)
+    with gpu.Corpus(w) as c:
+        c.append(corpus)
+        for metric, k in ((HAMMING, 5), (XORSUM, 32)):
+            _check(c, corpus, queries, k, metric)
