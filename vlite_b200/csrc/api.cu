@@ -677,8 +677,10 @@ int search_large_k(vl_corpus* c, ScanParams p, int n_queries, int k, int metric,
     while (cap < 6u * (uint32_t)k) cap <<= 1;                       // expected ~3k candidates per query
     const size_t key_bytes = (size_t)n_queries * cap * 8;
     if (key_bytes > (8ull << 30)) return VL_OK;                      // would need > 8 GB of scratch
-    // sample list length: enough hits at the threshold for a tight estimate (relative spread
-    // 1/sqrt(ks)) without paying for long lists; about 3k corpus rows are expected at or below it
+    // sample list length: 16..32 keeps the sampled pass on the scan's register-list fast path and lets
+    // it visit few tiles; the threshold's relative spread is 1/sqrt(ks) <= 25 %, far inside the margin
+    // between the ~3k rows expected at or below it and both failure modes (fewer than k: fallback;
+    // more than cap >= 6k: fallback)
     const int ks = std::min(kLargeKSample, std::max(16, k / 4));
     // sample every `stride`-th tile: at least 3k expected candidates, and never more than 5 % of a scan
     const uint32_t stride = std::max<uint32_t>(20u, (3u * (uint32_t)k) / (uint32_t)ks);

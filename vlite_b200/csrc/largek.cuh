@@ -14,7 +14,7 @@
 namespace vl {
 
 constexpr int kSelectThreads = 512;
-constexpr int kLargeKSample = 128;
+constexpr int kLargeKSample = 32;   // sample list length cap: the register-list fast path of the scan
 
 __global__ void extract_thr_kernel(const uint32_t* __restrict__ sample_scores, const uint64_t* __restrict__ sample_rows,
                                    int n_queries, int ks, uint32_t* __restrict__ thr) {
