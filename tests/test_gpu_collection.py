@@ -209,6 +209,8 @@ def test_errors_and_set_batch_like_reference(gpu, golden, tmp_path):
     v = VLite("empty", ctx_dir=str(tmp_path / "contexts"), embedder=bits_embedder(golden["queries"]))
     with pytest.raises(ValueError, match=golden["empty_error"]):
         v.rank_and_filter(osearch.to_ref_encoding(golden["queries"][0]), 3)
+    with pytest.raises(ValueError, match=golden["empty_error"]):        # the same with a metadata filter
+        v.rank_and_filter(osearch.to_ref_encoding(golden["queries"][0]), 3, {"i": 0})
     enc = osearch.to_ref_encoding(golden["corpus"])
     with pytest.raises(ValueError) as e1:
         v.set_batch(["a", "b"], enc[:1])

@@ -326,6 +326,8 @@ class VLite:
         return out
 
     def _rank_batch(self, queries, top_k, metadata, top_k_multiplier):
+        if self._corpus is None or self._corpus.live_rows == 0:
+            raise ValueError("No valid binary vectors found for comparison.")     # main.py:149
         q = from_reference_encoding(queries)
         if metadata and self.filter_mode == "reference":
             scores, rows = self._search(q, top_k * top_k_multiplier)           # main.py:134-137
