@@ -38,10 +38,24 @@ def rand_meta():
     return md
 
 
-tmp = tempfile.mkdtemp()
-kw = dict(ctx_dir=tmp, embedder=embedder, width=W, metric="hamming")
-if gpus:
-    kw["gpus"] = gpus
+world = int(os.environ.get("WORLD_SIZE", "1"))
+if world > 1:                                    # under torchrun: the SPMD ShardedVLite, one rank per GPU
+    import torch
+    import torch.distributed as dist
+    from vlite_b200.main import ShardedVLite
+    local = int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    box = [tempfile.mkdtemp() if dist.get_rank() == 0 else None]
+    dist.broadcast_object_list(box, src=0)
+    tmp = box[0]
+    kw = dict(ctx_dir=tmp, embedder=embedder, width=W, metric="hamming", gpu_index=local)
+    VLite = ShardedVLite                          # noqa: F811
+else:
+    tmp = tempfile.mkdtemp()
+    kw = dict(ctx_dir=tmp, embedder=embedder, width=W, metric="hamming")
+    if gpus:
+        kw["gpus"] = gpus
 v = VLite("fuzz", **kw)
 model = []          # live entries in row order: [chunk_id, pool index, metadata dict]
 next_vec, next_item, checks, stored = 0, 0, 0, 0   # stored: rows the device must hold (tombstones included)
@@ -122,3 +136,6 @@ check({"lang": "en"}, 10)
 print(f"fuzz_collection: {steps} steps, {checks} checked query batches, {len(model)} live rows, {v._corpus.rows} rows stored"
       f" (seed {seed}, gpus {gpus})")
 v.close()
+if world > 1:
+    dist.barrier()
+    dist.destroy_process_group()
