@@ -61,3 +61,25 @@ def test_ranges_rows_and_cache():
     assert b is not a and b[1999 // 32] >> (1999 % 32) & 1
     idx.clear()
     assert len(idx) == 0 and not idx.mask({"src": "bulk"}, 2000).any()
+
+
+def test_bulk_registration_matches_row_by_row():
+    rng = np.random.default_rng(9)
+    metas = []
+    for i in range(3000):
+        md = {"lang": ["en", "fr", None][int(rng.integers(3))]} if rng.random() < 0.8 else {}
+        if rng.random() < 0.5:
+            md["year"] = int(rng.integers(2020, 2023))
+        if i % 97 == 0:
+            md["tags"] = [i]
+        metas.append(md)
+    one, bulk = MetaIndex(), MetaIndex()
+    for r, md in enumerate(metas):
+        one.set_row(md, r + 11)
+    bulk.set_many(metas[:1000], 11)
+    bulk.set_many(metas[1000:], 1011)
+    shared = {"src": "same"}
+    one.set_range(shared, 4000, 500)
+    bulk.set_many([shared] * 500, 4000)                    # one dict shared by every row: range fill
+    for q in ({"lang": "en"}, {"lang": None}, {"year": 2021, "lang": "fr"}, {"src": "same"}, {"nope": 1}, {}):
+        np.testing.assert_array_equal(bulk.mask(q, 4600), one.mask(q, 4600), err_msg=str(q))

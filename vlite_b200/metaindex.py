@@ -100,6 +100,27 @@ class MetaIndex:
             np.bitwise_or.at(m, rows // _WORD, np.uint64(1) << (rows % _WORD).astype(np.uint64))
         self.version += 1
 
+    def set_many(self, metadatas, first_row: int):
+        """rows first_row, first_row+1, ... carry metadatas[0], metadatas[1], ...: one pass over the
+        dicts, then one vectorised OR per distinct (key, value) term (bulk ingest, collection load)."""
+        n = len(metadatas)
+        if n == 0:
+            return
+        if all(md is metadatas[0] for md in metadatas):        # add(): one dict shared by every chunk
+            self.set_range(metadatas[0], first_row, n)
+            return
+        groups = {}
+        for i, md in enumerate(metadatas):
+            for k, v in md.items():
+                if indexable(v):
+                    groups.setdefault((k, v), []).append(i)
+                groups.setdefault((k, _HAS), []).append(i)
+        for term, idxs in groups.items():
+            rows = np.asarray(idxs, dtype=np.int64) + first_row
+            m = self._words(term, int(rows[-1]))
+            np.bitwise_or.at(m, rows >> 6, np.uint64(1) << (rows & 63).astype(np.uint64))
+        self.version += 1
+
     def clear(self):
         self._maps.clear()
         self.version += 1
