@@ -151,6 +151,7 @@ class VLite:
         self._metas = {}           # chunk_id -> metadata dict
         self._extra = {}           # chunk_id -> {'vector': ...} written by update() (main.py:180)
         self._meta_index = MetaIndex()   # (key, value) -> row bitmap, for filter masks
+        self._by_prefix = {}       # "{id}" -> {chunk_id: None} for every chunk_id that starts with "{id}_"
         self.index = _IndexView(self)
         self._load_collection()
 
@@ -179,6 +180,29 @@ class VLite:
         e.update(self._extra.get(chunk_id, {}))
         return e
 
+    # The reference finds an item's chunks with ``chunk_id.startswith(f"{id}_")`` over the whole
+    # index (vlite/main.py:173, :195, :215, :235): O(N) per id.  Here every chunk id is filed under
+    # each of its underscore-terminated prefixes, in registration order, so the same match is a lookup.
+    def _file_prefixes(self, chunk_id):
+        p = chunk_id.find("_")
+        while p != -1:
+            self._by_prefix.setdefault(chunk_id[:p], {})[chunk_id] = None
+            p = chunk_id.find("_", p + 1)
+
+    def _unfile_prefixes(self, chunk_id):
+        p = chunk_id.find("_")
+        while p != -1:
+            bucket = self._by_prefix.get(chunk_id[:p])
+            if bucket is not None:
+                bucket.pop(chunk_id, None)
+                if not bucket:
+                    del self._by_prefix[chunk_id[:p]]
+            p = chunk_id.find("_", p + 1)
+
+    def _chunks_of(self, id):
+        """chunk ids that start with ``f"{id}_"``, in index order"""
+        return list(self._by_prefix.get(f"{id}", ()))
+
     def _post(self, chunk_id, row):
         self._meta_index.set_row(self._metas[chunk_id], row)
 
@@ -187,6 +211,8 @@ class VLite:
         if old is not None:                                              # dict overwrite (main.py:91)
             self._corpus.tombstone([old])
             self._ids[old] = None
+        if chunk_id not in self._row_of:
+            self._file_prefixes(chunk_id)
         self._row_of[chunk_id] = row
         self._texts[chunk_id] = text
         self._metas[chunk_id] = metadata
@@ -219,6 +245,8 @@ class VLite:
                     self._ids[row] = cid
                 else:
                     self._ids.append(cid)
+        for cid in chunk_ids:
+            self._file_prefixes(cid)
         self._row_of.update(zip(chunk_ids, range(first_row, first_row + n)))
         self._texts.update(zip(chunk_ids, texts))
         self._metas.update(zip(chunk_ids, metadatas))
@@ -382,7 +410,7 @@ class VLite:
     @_locked
     def update(self, id, text=None, metadata=None, vector=None):
         """vlite/main.py:170-188 (the vector is stored under 'vector' and not searched, as there)."""
-        chunk_ids = [cid for cid in self._row_of if cid.startswith(f"{id}_")]
+        chunk_ids = self._chunks_of(id)
         if not chunk_ids:
             return False
         if metadata is not None:
@@ -410,8 +438,9 @@ class VLite:
             ids = [ids]
         deleted, dead_rows = 0, []
         for id in ids:
-            for cid in [c for c in self._row_of if c.startswith(f"{id}_")]:
+            for cid in self._chunks_of(id):
                 row = self._row_of.pop(cid)
+                self._unfile_prefixes(cid)
                 self._texts.pop(cid, None)
                 self._metas.pop(cid, None)
                 self._extra.pop(cid, None)
@@ -434,10 +463,9 @@ class VLite:
                 ids = [ids]
             for id in ids:
                 chunks, md = [], {}
-                for cid in self._row_of:
-                    if cid.startswith(f"{id}_"):
-                        chunks.append(self._texts[cid])
-                        md.update(self._metas[cid])
+                for cid in self._chunks_of(id):
+                    chunks.append(self._texts[cid])
+                    md.update(self._metas[cid])
                 if chunks:
                     items.append((id, " ".join(chunks), md))
         else:
@@ -450,7 +478,7 @@ class VLite:
     @_locked
     def set(self, id, text=None, metadata=None, vector=None):
         """vlite/main.py:233-240."""
-        if any(cid.startswith(f"{id}_") for cid in self._row_of):
+        if self._chunks_of(id):
             self.update(id, text, metadata, vector)
         else:
             self.add(text, metadata=metadata, item_id=id)
@@ -533,6 +561,7 @@ class VLite:
         self._metas.clear()
         self._extra.clear()
         self._meta_index.clear()
+        self._by_prefix.clear()
         i = 0
         while i == 0 or os.path.exists(self.ctx.get(self._part_name(i))):
             self.ctx.delete(self._part_name(i))
@@ -606,7 +635,7 @@ class ShardedVLite(VLite):
         else:
             if self._corpus is not None:
                 self._corpus.clear()
-            for d in (self._row_of, self._texts, self._metas, self._extra, self._meta_index):
+            for d in (self._row_of, self._texts, self._metas, self._extra, self._meta_index, self._by_prefix):
                 d.clear()
             self._ids.clear()
         if dist.is_initialized():
