@@ -11,6 +11,12 @@ search is vlite/model.py:76-90 on one device).
 ``torch.distributed`` is plumbing only (NCCL on GPUs; the host logic is
 backend-agnostic so the world_size-2 gloo tests can drive it on CPU with the
 local search and merge swapped for the oracle's).
+
+Three layers live here: ``ShardedSearcher`` (search over fixed shards: local scan, the one
+all-gather, merge), ``ShardedCorpus`` (an append-able collection over the ranks of a process
+group, driven SPMD) and ``LocalShardedCorpus`` (the same collection rules inside ONE process,
+over the C library's shard group: peer copies instead of a collective).  All three return
+identical results for identical content.
 """
 from __future__ import annotations
 
