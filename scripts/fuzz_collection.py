@@ -23,7 +23,7 @@ LANGS, YEARS = ["en", "fr", "de", None], [2020, 2021, 2022]
 
 
 def embedder(texts):
-    rows = np.stack([POOL[int(t.split(":")[1])] if t.startswith("v:") else QUERIES[int(t.split(":")[1])] for t in texts])
+    rows = np.stack([POOL[int(t.split(":")[1]) % len(POOL)] if t.startswith("v:") else QUERIES[int(t.split(":")[1])] for t in texts])
     return np.unpackbits(rows, axis=1).astype(np.float32) * 2 - 1
 
 
@@ -66,7 +66,7 @@ def check(md, k):
     assert (v._corpus.rows if v._corpus is not None else 0) == stored and v.count() == len(model)
     valid = np.array([all(e[2].get(a) == b for a, b in md.items()) for e in model], dtype=bool) if md else \
         np.ones(len(model), dtype=bool)
-    corpus = POOL[[e[1] for e in model]] if model else np.zeros((0, W), np.uint8)
+    corpus = POOL[np.asarray([e[1] for e in model]) % len(POOL)] if model else np.zeros((0, W), np.uint8)
     texts = [f"q:{i}" for i in range(len(QUERIES))]
     if not model:                                   # vlite/main.py:149: an empty collection cannot be ranked
         try:
@@ -94,7 +94,7 @@ for step in range(steps):
         stored += n
         metas = [rand_meta() for _ in idx]
         before = set(v.dump().keys())
-        v.set_batch([f"v:{i}" for i in idx], osearch.to_ref_encoding(POOL[idx]), [dict(m) for m in metas])
+        v.set_batch([f"v:{i}" for i in idx], osearch.to_ref_encoding(POOL[np.asarray(idx) % len(POOL)]), [dict(m) for m in metas])
         new_keys = [key for key in v.dump().keys() if key not in before]
         assert len(new_keys) == n
         model += [[key, i, dict(m)] for key, i, m in zip(new_keys, idx, metas)]
