@@ -373,6 +373,15 @@ def run_ours(args):
             corpus.search(dq, k, _capi.XORSUM, None, ds, dr)
             if i >= 2:
                 tt.append(corpus.last_timing()[0])
+        # the 64 MB corpus fits L2 -- the headline is timed with L2 flushed between
+        # iterations; this is the same step with the corpus left resident
+        tt_res = []
+        for i in range(6):
+            corpus.search(dq, k, _capi.HAMMING, None, ds, dr)
+            if i >= 2:
+                tt_res.append(corpus.last_timing()[0])
+        extra["l2_resident_same_workload"] = {"ms_per_step": float(np.mean(tt_res)),
+                                              "qps": nq / (float(np.mean(tt_res)) * 1e-3)}
         extra["xorsum_same_workload"] = {"ms_per_step": float(np.mean(tt)), "qps": nq / (float(np.mean(tt)) * 1e-3)}
         if rank == 0 and not args.no_cpu:
             qps, ms, cores, sample = time_reference(None, 2, budget_s=40.0, target_s=15.0)
