@@ -208,8 +208,9 @@ int vl_set_tuning(vl_corpus* c, int row_splits, int stages);
  * multi-GPU counterpart).  A group borrows corpus handles -- usually one per GPU, any mix of
  * devices works -- whose base rows the caller has set (vl_corpus_set_base_row) so that global rows
  * are disjoint.  vl_shard_group_search replicates the queries to every shard, lets all shards scan
- * concurrently on their own streams, moves each shard's k candidates to the first shard's device
- * with a peer copy (NVLink between peers) and merges them there by (score, global row): the
+ * concurrently on their own streams -- each shard's last merge kernel stores its k candidates
+ * straight into the first shard's device memory (peer stores over NVLink; a peer copy when the pair
+ * has no peer access) -- and merges them there by (score, global row): the
  * result equals vl_search over the concatenated corpus.  Host pointers only; the call returns
  * when the results are in out_*.  filter_masks_or_null: NULL, or one mask pointer (or NULL) per
  * shard, each in that shard's local row numbering.  A group does not own its shards: destroy the

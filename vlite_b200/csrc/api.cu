@@ -1457,6 +1457,7 @@ struct vl_shard_group {
     std::vector<DevBuf> q, s, r;         // per shard, on the shard's device
     std::vector<DevBuf> seg;             // per shard: [local starts | global starts] of its appended segments
     std::vector<int> n_seg;
+    std::vector<char> direct;            // per shard: its kernels may store straight into home-device memory
     DevBuf gather_s, gather_r, out_s, out_r;  // home device
     void* pinned = nullptr;              // host staging: queries in, results out
     size_t pinned_bytes = 0;
@@ -1494,6 +1495,7 @@ extern "C" int vl_shard_group_create(int n_shards, vl_corpus* const* shards, vl_
     g->r.resize(n_shards);
     g->seg.resize(n_shards);
     g->n_seg.assign(n_shards, 0);
+    g->direct.assign(n_shards, 0);
     int rc = VL_OK;
     {
         DeviceGuard dg(g->home);
@@ -1506,11 +1508,15 @@ extern "C" int vl_shard_group_create(int n_shards, vl_corpus* const* shards, vl_
         DeviceGuard dg(dev);
         if (cudaEventCreateWithFlags(&g->ev[i], cudaEventDisableTiming) != cudaSuccess)
             rc = fail(VL_ECUDA, "cannot create an event on device %d", dev);
-        if (dev != g->home) {  // direct NVLink stores when the pair allows it; the copy works either way
+        if (dev == g->home) {
+            g->direct[i] = 1;
+        } else {  // peers: the shard's merge kernel stores its k candidates straight into the home
+                  // device's gather buffer over NVLink; otherwise a peer copy (staged by the driver) does
             int can = 0;
             if (cudaDeviceCanAccessPeer(&can, dev, g->home) == cudaSuccess && can) {
                 cudaError_t e = cudaDeviceEnablePeerAccess(g->home, 0);
-                if (e != cudaSuccess) cudaGetLastError();  // already enabled is fine
+                if (e == cudaSuccess || e == cudaErrorPeerAccessAlreadyEnabled) g->direct[i] = 1;
+                if (e != cudaSuccess) cudaGetLastError();
             }
         }
     }
@@ -1613,22 +1619,31 @@ extern "C" int vl_shard_group_search(vl_shard_group* g, const uint8_t* queries_h
         vl_corpus* c = g->shards[i];
         DeviceGuard dg(c->device);
         TRY(g->q[i].ensure(qbytes));
-        TRY(g->s[i].ensure(n_out * 4));
-        TRY(g->r[i].ensure(n_out * 8));
         CU(cudaMemcpyAsync(g->q[i].p, g->pinned, qbytes, cudaMemcpyHostToDevice, c->stream));
+        uint32_t* slot_s = static_cast<uint32_t*>(g->gather_s.p) + (size_t)i * n_out;   // home-device memory
+        uint64_t* slot_r = static_cast<uint64_t*>(g->gather_r.p) + (size_t)i * n_out;
+        uint32_t* o_s = slot_s;
+        uint64_t* o_r = slot_r;
+        if (!g->direct[i]) {
+            TRY(g->s[i].ensure(n_out * 4));
+            TRY(g->r[i].ensure(n_out * 8));
+            o_s = static_cast<uint32_t*>(g->s[i].p);
+            o_r = static_cast<uint64_t*>(g->r[i].p);
+        }
+        // the exchange is the epilogue of the shard's own search: its last merge kernel writes the k
+        // candidates per query into the home device's gather slot (peer stores when direct)
         TRY(vl_search(c, static_cast<const uint8_t*>(g->q[i].p), n_queries, k, metric,
-                      filter_masks_or_null ? filter_masks_or_null[i] : nullptr, static_cast<uint32_t*>(g->s[i].p),
-                      static_cast<uint64_t*>(g->r[i].p)));
+                      filter_masks_or_null ? filter_masks_or_null[i] : nullptr, o_s, o_r));
         if (g->n_seg[i] > 0) {  // shard-local rows -> global rows fixed at append time
             const uint64_t* sl = static_cast<const uint64_t*>(g->seg[i].p);
-            map_rows_kernel<<<(unsigned)((n_out + 255) / 256), 256, 0, c->stream>>>(
-                static_cast<uint64_t*>(g->r[i].p), n_out, sl, sl + g->n_seg[i], g->n_seg[i]);
+            map_rows_kernel<<<(unsigned)((n_out + 255) / 256), 256, 0, c->stream>>>(o_r, n_out, sl, sl + g->n_seg[i],
+                                                                                  g->n_seg[i]);
             LAUNCHED();
         }
-        CU(cudaMemcpyPeerAsync(static_cast<uint32_t*>(g->gather_s.p) + (size_t)i * n_out, g->home, g->s[i].p, c->device,
-                               n_out * 4, c->stream));
-        CU(cudaMemcpyPeerAsync(static_cast<uint64_t*>(g->gather_r.p) + (size_t)i * n_out, g->home, g->r[i].p, c->device,
-                               n_out * 8, c->stream));
+        if (!g->direct[i]) {
+            CU(cudaMemcpyPeerAsync(slot_s, g->home, o_s, c->device, n_out * 4, c->stream));
+            CU(cudaMemcpyPeerAsync(slot_r, g->home, o_r, c->device, n_out * 8, c->stream));
+        }
         CU(cudaEventRecord(g->ev[i], c->stream));
         return VL_OK;
     };
