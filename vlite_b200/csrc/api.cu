@@ -7,6 +7,8 @@
 
 #include <algorithm>
 #include <atomic>
+#include <condition_variable>
+#include <functional>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -1462,6 +1464,17 @@ struct vl_shard_group {
     void* pinned = nullptr;              // host staging: queries in, results out
     size_t pinned_bytes = 0;
     cudaEvent_t home_ev = nullptr;
+    // one persistent host thread per shard: a search's per-shard enqueue work (H2D, memsets, scan,
+    // merges: ~20 us of launch calls each) runs on all of them at once instead of back to back
+    std::vector<std::thread> workers;
+    std::mutex mu;
+    std::condition_variable cv_go, cv_done;
+    uint64_t epoch = 0;
+    int pending = 0;
+    bool stop = false;
+    std::function<int(int)> job;
+    std::vector<int> rcs;
+    std::vector<std::string> msgs;
 };
 
 namespace {
@@ -1524,12 +1537,39 @@ extern "C" int vl_shard_group_create(int n_shards, vl_corpus* const* shards, vl_
         vl_shard_group_destroy(g);
         return rc;
     }
+    g->rcs.assign(n_shards, VL_OK);
+    g->msgs.assign(n_shards, std::string());
+    if (n_shards > 1) {
+        for (int i = 0; i < n_shards; ++i)
+            g->workers.emplace_back([g, i] {
+                uint64_t seen = 0;
+                for (;;) {
+                    std::unique_lock<std::mutex> lk(g->mu);
+                    g->cv_go.wait(lk, [&] { return g->stop || g->epoch != seen; });
+                    if (g->stop) return;
+                    seen = g->epoch;
+                    lk.unlock();
+                    const int r = g->job(i);
+                    lk.lock();
+                    g->rcs[i] = r;
+                    if (r != VL_OK) g->msgs[i] = g_err;  // the error text is thread-local
+                    if (--g->pending == 0) g->cv_done.notify_one();
+                }
+            });
+    }
     *out = g;
     return VL_OK;
 }
 
 extern "C" int vl_shard_group_destroy(vl_shard_group* g) {
     if (!g) return VL_OK;
+    {
+        std::lock_guard<std::mutex> lk(g->mu);
+        g->stop = true;
+    }
+    g->cv_go.notify_all();
+    for (auto& t : g->workers) t.join();
+    g->workers.clear();
     for (size_t i = 0; i < g->shards.size(); ++i) {
         DeviceGuard dg(g->shards[i]->device);
         if (g->ev[i]) cudaEventDestroy(g->ev[i]);
@@ -1612,9 +1652,9 @@ extern "C" int vl_shard_group_search(vl_shard_group* g, const uint8_t* queries_h
     }
     memcpy(g->pinned, queries_host, qbytes);
 
-    // Phase 1, one host thread: every shard's H2D + scan + local merge + peer copy is only ENQUEUED
-    // (k <= 32), so all devices run at once.  k > 32 synchronises inside vl_search (the sampled
-    // threshold sizes its collect pass): there one host thread per shard keeps the devices busy.
+    // Phase 1: every shard's H2D + scan + local merge is enqueued by that shard's own host thread, so
+    // the launch calls of all shards overlap and all devices start together (k > 32 synchronises
+    // inside vl_search -- the sampled threshold sizes its collect pass -- which the same threads absorb).
     auto shard_work = [&](int i) -> int {
         vl_corpus* c = g->shards[i];
         DeviceGuard dg(c->device);
@@ -1647,20 +1687,23 @@ extern "C" int vl_shard_group_search(vl_shard_group* g, const uint8_t* queries_h
         CU(cudaEventRecord(g->ev[i], c->stream));
         return VL_OK;
     };
-    if (k <= large_k_min() || n == 1) {
-        for (int i = 0; i < n; ++i) TRY(shard_work(i));
+    if (n == 1) {
+        TRY(shard_work(0));
     } else {
-        std::vector<int> rcs(n, VL_OK);
-        std::vector<std::string> msgs(n);
-        std::vector<std::thread> pool;
+        {
+            std::lock_guard<std::mutex> lk(g->mu);
+            g->job = shard_work;
+            g->pending = n;
+            ++g->epoch;
+        }
+        g->cv_go.notify_all();
+        {
+            std::unique_lock<std::mutex> lk(g->mu);
+            g->cv_done.wait(lk, [&] { return g->pending == 0; });
+            g->job = nullptr;
+        }
         for (int i = 0; i < n; ++i)
-            pool.emplace_back([&, i] {
-                rcs[i] = shard_work(i);
-                if (rcs[i] != VL_OK) msgs[i] = g_err;  // the error text is thread-local
-            });
-        for (auto& t : pool) t.join();
-        for (int i = 0; i < n; ++i)
-            if (rcs[i] != VL_OK) return fail(rcs[i], "shard %d: %s", i, msgs[i].c_str());
+            if (g->rcs[i] != VL_OK) return fail(g->rcs[i], "shard %d: %s", i, g->msgs[i].c_str());
     }
 
     // Phase 2: the home device waits for every shard's candidates, merges, and returns them.
