@@ -613,7 +613,10 @@ int search_lists(vl_corpus* c, ScanParams p, int n_queries, int k, int metric, u
     if (out_stride == 0) out_stride = k;
     const int n_pass = (k + kWarpListMaxK - 1) / kWarpListMaxK;
     // tau[Q] | cursor score[Q] | cursor row[Q] | histogram[Q][1056] (k <= 32, not for huge batches)
-    const bool want_hist = k <= 32 && n_queries <= 16384;
+    // (the histogram is read only by the one-warp-per-query configuration, Q > 32; the shared bound
+    // tau only by query tiles of more than two queries: small batches skip both memsets)
+    const bool want_hist = k <= 32 && n_queries > 32 && n_queries <= 16384;
+    const bool want_tau = n_queries > 2;
     const size_t hist_bytes = want_hist ? (size_t)n_queries * kHistWords * 4 : 0;
     TRY(c->cand_buf.ensure((size_t)n_queries * 12 + hist_bytes));
     p.tau = static_cast<uint32_t*>(c->cand_buf.p);
@@ -643,7 +646,7 @@ int search_lists(vl_corpus* c, ScanParams p, int n_queries, int k, int metric, u
         // corpus read once and far larger than L2 -> stream it; otherwise let L2 keep it
         p.evict_first = (plan.T == 1 && n_pass == 1 && p.tile_stride == 1 &&
                          c->count * (uint64_t)c->w > (96ull << 20)) ? 1 : 0;
-        CU(cudaMemsetAsync(p.tau, 0xFF, (size_t)n_queries * 4, st));
+        if (want_tau) CU(cudaMemsetAsync(p.tau, 0xFF, (size_t)n_queries * 4, st));
         if (p.hist) CU(cudaMemsetAsync(p.hist, 0, hist_bytes, st));
         TRY(launch_scan(c, p, n_queries, k_pass, metric, nullptr, /*dry=*/false));
         if (c->timing && pass == 0 && p.tile_stride == 1) CU(cudaEventRecord(c->ev1, st));
