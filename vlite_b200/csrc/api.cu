@@ -299,7 +299,7 @@ using namespace vl;
 // back at least `cap_rows` rows (rounded up to whole tiles) with physical memory -- no copy, no move
 int grow_to(vl_corpus* c, uint64_t cap_rows) {
     // local rows are u32 in the kernels and a signed 32-bit TMA coordinate
-    if (cap_rows > 0x7FFFFF00ull) return fail(VL_EINVAL, "a corpus shard holds at most 2^31-256 rows");
+    if (cap_rows > 0x7FFFFC00ull) return fail(VL_EINVAL, "a corpus shard holds at most 2^31-1024 rows");
     const uint64_t cap = (cap_rows + kMaxStageRows - 1) / kMaxStageRows * kMaxStageRows;
     if (cap <= c->capacity) return VL_OK;
     TRY(c->rows_arena.grow(cap * (uint64_t)c->w));
@@ -312,7 +312,7 @@ int grow_to(vl_corpus* c, uint64_t cap_rows) {
     // everything that is mapped is usable capacity (whole tiles only)
     const uint64_t by_rows = c->rows_arena.mapped / (uint64_t)c->w;
     const uint64_t by_live = (uint64_t)c->live_arena.mapped * 8;
-    c->capacity = std::min<uint64_t>(std::min(by_rows, by_live), 0x7FFFFF00ull) / kMaxStageRows * kMaxStageRows;
+    c->capacity = std::min<uint64_t>(std::min(by_rows, by_live), 0x7FFFFC00ull) / kMaxStageRows * kMaxStageRows;
     return VL_OK;
 }
 
@@ -508,9 +508,10 @@ int launch_scan_wm(vl_corpus* c, ScanParams& p, int nq, int k, ScanPlan* plan, b
     // Q = 1 is HBM-bound: one box per stage.  2 <= Q <= 16 has few queries per warp: where two
     // boxes still fit a 32 KB stage (W = 64) a stage carries two, so every warp scores twice the rows
     // per step at unchanged occupancy (+8 %); at W = 128 the lost CTA per SM costs more (-15 %, measured).
-    constexpr int VL_MIDQ_TPS = (W <= 64) ? 2 : 1;
+    constexpr int VL_MIDQ_TPS = (W <= 32) ? 4 : (W <= 64) ? 2 : 1;   // boxes per stage: 32 KB of rows either way
+    constexpr int VL_Q1_TPS = (W <= 32) ? 2 : 1;
     // (two boxes per stage at W <= 64 also for Q = 2: 5.0 -> 6.1 TB/s on 32M x 64 B; Q = 1 gains nothing)
-    if (nq <= 1) return launch_scan_cfg<W, METRIC, 1, 1, 1>(c, p, nq, k, plan, dry);
+    if (nq <= 1) return launch_scan_cfg<W, METRIC, 1, 1, VL_Q1_TPS>(c, p, nq, k, plan, dry);
     if (nq <= 2) return launch_scan_cfg<W, METRIC, 2, 1, VL_MIDQ_TPS>(c, p, nq, k, plan, dry);
     if (nq <= 4) return launch_scan_cfg<W, METRIC, 4, 1, VL_MIDQ_TPS>(c, p, nq, k, plan, dry);
     if (nq <= 8) return launch_scan_cfg<W, METRIC, 8, 1, VL_MIDQ_TPS>(c, p, nq, k, plan, dry);

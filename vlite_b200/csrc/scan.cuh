@@ -34,7 +34,7 @@
 namespace vl {
 
 constexpr int kTileRows = 256;      // rows of one TMA box
-constexpr int kMaxStageRows = 512;  // a pipeline stage holds 1 or 2 boxes; capacity is padded to this
+constexpr int kMaxStageRows = 1024;  // a pipeline stage holds 1, 2 or 4 boxes; capacity is padded to this
 constexpr int kScanWarps = 8;
 constexpr int kScanThreads = kScanWarps * 32;
 constexpr int kWarpListMaxK = 128;
@@ -187,7 +187,7 @@ struct ScanCfg {
     static constexpr int STAGE_BYTES = TILE_BYTES + 2 * MASKW * 4;
     static_assert(W == 32 || W == 64 || W == 128 || W == 256, "row width");
     static_assert(WQ == 1 || WQ == 2 || WQ == 4 || WQ == 8, "warps along queries");
-    static_assert(TPS == 1 || TPS == 2, "boxes per stage");
+    static_assert(TPS == 1 || TPS == 2 || TPS == 4, "boxes per stage");
     static size_t smem_bytes(int stages, int k) {
         return (size_t)stages * STAGE_BYTES + (size_t)QT * W + (size_t)kScanWarps * C * k * 8 +
                (size_t)QT * 8 + (size_t)kScanWarps * C * 4 + (size_t)stages * 16;
