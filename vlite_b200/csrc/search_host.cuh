@@ -1,0 +1,325 @@
+// Host side of a search: scan configuration dispatch and grid sizing, the multi-level merge, the
+// k <= 128 list path with its multi-pass extension, and the sampled collect/select path for large
+// k.  Included by api.cu only, after corpus.cuh.
+#pragma once
+
+namespace {
+
+using namespace vl;
+
+// ---- scan dispatch -------------------------------------------------------------
+
+struct ScanPlan {
+    int C, WQ, WR, QT, T, S, stages, occ;
+    size_t smem;
+};
+
+template <int W, int METRIC, int C, int WQ, int TPS>
+int launch_scan_cfg(vl_corpus* c, ScanParams& p, int n_queries, int k, ScanPlan* plan_out, bool dry) {
+    using Cfg = ScanCfg<W, C, WQ, TPS>;
+    auto kern = scan_topk_kernel<W, METRIC, C, WQ, TPS>;
+    // stages visited by this launch: every tile_stride-th stage of the shard
+    const uint32_t all_stages = (uint32_t)((p.n_rows + Cfg::TR - 1) / Cfg::TR);
+    p.n_tiles = (all_stages + p.tile_stride - 1) / p.tile_stride;
+    const size_t fixed = Cfg::smem_bytes(0, k);
+    const size_t max_smem = 227 * 1024;
+    const size_t two_per_sm = 113 * 1024;
+    int stages = (int)std::min<size_t>(8, std::max<size_t>(2, (96 * 1024) / Cfg::TILE_BYTES));
+    if (Cfg::TILE_BYTES >= 64 * 1024) stages = 3;  // two-box stages: one CTA per SM, three stages in flight
+    if (c->tune_stages > 0) stages = c->tune_stages;
+    auto total = [&](int s) { return fixed + (size_t)s * (Cfg::STAGE_BYTES + 16); };
+    if (c->tune_stages <= 0 && Cfg::TILE_BYTES < 64 * 1024)
+        while (stages > 2 && total(stages) > two_per_sm) --stages;
+    while (stages > 1 && total(stages) > max_smem) --stages;
+    const size_t smem = total(stages);
+    if (smem > max_smem) return fail(VL_EINVAL, "k=%d needs %zu B of shared memory per CTA (max %zu)", k, smem, max_smem);
+    TRY(allow_max_smem(kern, c->device));
+    // the occupancy of this kernel at this shared-memory size is asked for once per thread
+    static thread_local size_t cached_smem[64] = {};
+    static thread_local int cached_occ[64] = {};
+    int occ = 0;
+    const int dev_slot = c->device & 63;
+    if (cached_smem[dev_slot] == smem && cached_occ[dev_slot] > 0) {
+        occ = cached_occ[dev_slot];
+    } else {
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kScanThreads, smem));
+        if (occ < 1) return fail(VL_ECUDA, "scan kernel does not fit on an SM (smem %zu)", smem);
+        cached_smem[dev_slot] = smem;
+        cached_occ[dev_slot] = occ;
+    }
+
+    const int T = (n_queries + Cfg::QT - 1) / Cfg::QT;
+    const long slots = (long)c->sms * occ;
+    const long max_splits = std::max<long>(1, (long)p.n_tiles / 4);
+    long S = 1;
+    if (c->tune_splits > 0) {
+        S = c->tune_splits;
+    } else {
+        double best_eff = -1;
+        for (int waves = 1; waves <= 4; ++waves) {
+            long s = std::max<long>(1, (waves * slots) / T);
+            s = std::min(s, max_splits);
+            const long ctas = s * T;
+            const double eff = (double)ctas / ((double)((ctas + slots - 1) / slots) * slots);
+            // an extra wave re-pays per-CTA prologue, list warm-up and merge work: take it only when
+            // it fills the SMs better (measured at 500k x 1024: 2 exact waves of 592 CTAs beat 1 wave
+            // of 288 by 2 % now that list maintenance is cheap; 4 waves lose)
+            // (XORSUM steps are shorter, so the second wave's fixed costs weigh more: 1 wave of 288
+            // beats 2 exact waves by 3 % there)
+            if (eff > best_eff + (METRIC == VL_METRIC_HAMMING ? 0.02 : 0.05)) {
+                best_eff = eff;
+                S = s;
+            }
+            if (s == max_splits) break;
+        }
+    }
+    S = std::min<long>(S, std::max<long>(1, p.n_tiles));
+    S = std::min<long>(S, 65535);
+    if (plan_out) *plan_out = ScanPlan{C, WQ, Cfg::WR, Cfg::QT, T, (int)S, stages, occ, smem};
+    if (dry) return VL_OK;
+    p.stages = stages;
+    CUtensorMap tmap;
+    TRY(make_corpus_tmap(c, &tmap));
+    dim3 grid((unsigned)T, (unsigned)S);
+    kern<<<grid, kScanThreads, smem, c->stream>>>(tmap, p);
+    LAUNCHED();
+    return VL_OK;
+}
+
+template <int W, int METRIC>
+int launch_scan_wm(vl_corpus* c, ScanParams& p, int nq, int k, ScanPlan* plan, bool dry) {
+    // Q = 1 is HBM-bound: one box per stage.  2 <= Q <= 16 has few queries per warp: where two
+    // boxes still fit a 32 KB stage (W = 64) a stage carries two, so every warp scores twice the rows
+    // per step at unchanged occupancy (+8 %); at W = 128 the lost CTA per SM costs more (-15 %, measured).
+    constexpr int VL_MIDQ_TPS = (W <= 32) ? 4 : (W <= 64) ? 2 : 1;   // boxes per stage: 32 KB of rows either way
+    constexpr int VL_Q1_TPS = (W <= 32) ? 2 : 1;
+    // (two boxes per stage at W <= 64 also for Q = 2: 5.0 -> 6.1 TB/s on 32M x 64 B; Q = 1 gains nothing)
+    if (nq <= 1) return launch_scan_cfg<W, METRIC, 1, 1, VL_Q1_TPS>(c, p, nq, k, plan, dry);
+    if (nq <= 2) return launch_scan_cfg<W, METRIC, 2, 1, VL_MIDQ_TPS>(c, p, nq, k, plan, dry);
+    if (nq <= 4) return launch_scan_cfg<W, METRIC, 4, 1, VL_MIDQ_TPS>(c, p, nq, k, plan, dry);
+    if (nq <= 8) return launch_scan_cfg<W, METRIC, 8, 1, VL_MIDQ_TPS>(c, p, nq, k, plan, dry);
+    if (nq <= 16) return launch_scan_cfg<W, METRIC, 8, 2, VL_MIDQ_TPS>(c, p, nq, k, plan, dry);
+    if (nq <= 32) return launch_scan_cfg<W, METRIC, 8, 4, 1>(c, p, nq, k, plan, dry);
+    return launch_scan_cfg<W, METRIC, 8, 8, 1>(c, p, nq, k, plan, dry);
+}
+
+int launch_scan(vl_corpus* c, ScanParams& p, int nq, int k, int metric, ScanPlan* plan, bool dry) {
+#define VL_W(Wv)                                                                          \
+    case Wv:                                                                              \
+        return metric == VL_METRIC_HAMMING ? launch_scan_wm<Wv, kHamming>(c, p, nq, k, plan, dry) \
+                                           : launch_scan_wm<Wv, kXorSum>(c, p, nq, k, plan, dry);
+    switch (c->w) {
+        VL_W(32)
+        VL_W(64)
+        VL_W(128)
+        default:
+            return fail(VL_EINVAL, "unsupported row width %d", c->w);
+    }
+#undef VL_W
+}
+
+int fill_sentinels(cudaStream_t st, void* s_any, void* r_any, size_t n, bool s_dev, bool r_dev, size_t s_elem = 4) {
+    // 0xFF bytes are both sentinels (and a NaN/-inf is handled by the rescore caller)
+    if (s_dev)
+        CU(cudaMemsetAsync(s_any, 0xFF, n * s_elem, st));
+    else
+        memset(s_any, 0xFF, n * s_elem);
+    if (r_dev)
+        CU(cudaMemsetAsync(r_any, 0xFF, n * 8, st));
+    else
+        memset(r_any, 0xFF, n * 8);
+    return VL_OK;
+}
+
+// stage a filter mask into the handle's padded buffer (whole tiles, 16 B aligned)
+int stage_filter(vl_corpus* c, const uint32_t* filter_any, const uint32_t** out_dev) {
+    const uint64_t n_stages = (c->count + kMaxStageRows - 1) / kMaxStageRows;
+    const size_t padded = n_stages * (kMaxStageRows / 32) * 4;
+    const size_t given = ((c->count + 31) / 32) * 4;
+    const bool dev = is_device_ptr(filter_any);
+    if (dev && given == padded && (reinterpret_cast<uintptr_t>(filter_any) & 15) == 0) {
+        *out_dev = filter_any;
+        return VL_OK;
+    }
+    TRY(c->filt_buf.ensure(padded));
+    if (padded > given)
+        CU(cudaMemsetAsync(static_cast<uint8_t*>(c->filt_buf.p) + given, 0, padded - given, c->stream));
+    CU(cudaMemcpyAsync(c->filt_buf.p, filter_any, given, dev ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice,
+                       c->stream));
+    *out_dev = static_cast<const uint32_t*>(c->filt_buf.p);
+    return VL_OK;
+}
+
+// Multi-level merge: <= kMergeGroup lists per warp per level.  tmp_* must hold
+// merge_tmp_lists(n_lists) lists of n_queries x k_out entries (unused when n_lists <= kMergeGroup).
+size_t merge_tmp_lists(size_t n_lists) {
+    size_t total = 0;
+    while (n_lists > (size_t)kMergeGroup) {
+        n_lists = (n_lists + kMergeGroup - 1) / kMergeGroup;
+        total += n_lists;
+    }
+    return total;
+}
+
+int merge_levels(cudaStream_t st, const uint32_t* in_s, const uint64_t* in_r, size_t n_lists, size_t s_stride,
+                 size_t r_stride, int n_queries, int k_in, int k_out, uint32_t* out_s, uint64_t* out_r,
+                 int out_stride, int out_offset, uint32_t* tmp_s, uint64_t* tmp_r) {
+    const unsigned gx = (unsigned)((n_queries + kMergeWarps - 1) / kMergeWarps);
+    const size_t dense = (size_t)n_queries * k_out;
+    while (true) {
+        const size_t groups = (n_lists + kMergeGroup - 1) / kMergeGroup;
+        if (groups <= 1) {
+            merge_topk_kernel<<<dim3(gx, 1), kMergeWarps * 32, 0, st>>>(in_s, in_r, (int)n_lists, n_queries, k_in, k_out,
+                                                                      out_s, out_r, out_stride, out_offset, s_stride,
+                                                                      r_stride, 0);
+            LAUNCHED();
+            return VL_OK;
+        }
+        merge_topk_kernel<<<dim3(gx, (unsigned)groups), kMergeWarps * 32, 0, st>>>(
+            in_s, in_r, (int)n_lists, n_queries, k_in, k_out, tmp_s, tmp_r, k_out, 0, s_stride, r_stride, dense);
+        LAUNCHED();
+        in_s = tmp_s;
+        in_r = tmp_r;
+        tmp_s += groups * dense;
+        tmp_r += groups * dense;
+        n_lists = groups;
+        k_in = k_out;
+        s_stride = r_stride = dense;
+    }
+}
+
+// k <= 128: one scan + merge.  Larger k: ceil(k/128) passes, each returning the next 128 keys after
+// a per-query cursor (exact and deterministic for any tie pattern).  `p` arrives with the corpus,
+// queries and masks filled in.
+int search_lists(vl_corpus* c, ScanParams p, int n_queries, int k, int metric, uint32_t* o_s, uint64_t* o_r,
+                 int out_stride = 0) {
+    cudaStream_t st = c->stream;
+    if (out_stride == 0) out_stride = k;
+    const int n_pass = (k + kWarpListMaxK - 1) / kWarpListMaxK;
+    // tau[Q] | cursor score[Q] | cursor row[Q] | histogram[Q][1056] (k <= 32, not for huge batches)
+    // (the histogram is read only by the one-warp-per-query configuration, Q > 32; the shared bound
+    // tau only by query tiles of more than two queries: small batches skip both memsets)
+    const bool want_hist = k <= 32 && n_queries > 32 && n_queries <= 16384;
+    const bool want_tau = n_queries > 2;
+    const size_t hist_bytes = want_hist ? (size_t)n_queries * kHistWords * 4 : 0;
+    TRY(c->cand_buf.ensure((size_t)n_queries * 12 + hist_bytes));
+    p.tau = static_cast<uint32_t*>(c->cand_buf.p);
+    uint32_t* cur_s = p.tau + n_queries;
+    uint32_t* cur_r = cur_s + n_queries;
+    p.hist = want_hist ? cur_r + n_queries : nullptr;
+    {
+        const uint32_t max_score = metric == VL_METRIC_HAMMING ? 8u * c->w : 255u * c->w;
+        p.hist_shift = 0;
+        while ((max_score >> p.hist_shift) > (uint32_t)(kHistFine - 1)) ++p.hist_shift;
+        if (metric == VL_METRIC_HAMMING) p.hist_shift = 0;   // 8W <= 1024: only the all-bits-differ score overflows
+    }
+    for (int pass = 0; pass < n_pass; ++pass) {
+        const int k_pass = std::min(kWarpListMaxK, k - pass * kWarpListMaxK);
+        p.k = k_pass;
+        p.cur_score = pass ? cur_s : nullptr;
+        p.cur_row = pass ? cur_r : nullptr;
+        ScanPlan plan{};
+        TRY(launch_scan(c, p, n_queries, k_pass, metric, &plan, /*dry=*/true));
+        const size_t n_lists = (size_t)plan.S * plan.WR;
+        const size_t dense = (size_t)n_queries * k_pass;
+        const size_t n_part = (n_lists + merge_tmp_lists(n_lists)) * dense;
+        TRY(c->part_s.ensure(n_part * 4));
+        TRY(c->part_r.ensure(n_part * 8));
+        p.part_scores = static_cast<uint32_t*>(c->part_s.p);
+        p.part_rows = static_cast<uint64_t*>(c->part_r.p);
+        // corpus read once and far larger than L2 -> stream it; otherwise let L2 keep it
+        p.evict_first = (plan.T == 1 && n_pass == 1 && p.tile_stride == 1 &&
+                         c->count * (uint64_t)c->w > (96ull << 20)) ? 1 : 0;
+        if (want_tau) CU(cudaMemsetAsync(p.tau, 0xFF, (size_t)n_queries * 4, st));
+        if (p.hist) CU(cudaMemsetAsync(p.hist, 0, hist_bytes, st));
+        TRY(launch_scan(c, p, n_queries, k_pass, metric, nullptr, /*dry=*/false));
+        if (c->timing && pass == 0 && p.tile_stride == 1) CU(cudaEventRecord(c->ev1, st));
+        TRY(merge_levels(st, p.part_scores, p.part_rows, n_lists, dense, dense, n_queries, k_pass, k_pass, o_s, o_r,
+                         out_stride, pass * kWarpListMaxK, p.part_scores + n_lists * dense,
+                         p.part_rows + n_lists * dense));
+        if (pass + 1 < n_pass) {
+            cursor_update_kernel<<<(n_queries + 127) / 128, 128, 0, st>>>(
+                o_s, o_r, n_queries, out_stride, pass * kWarpListMaxK + k_pass - 1, c->base_row, cur_s, cur_r);
+            LAUNCHED();
+        }
+    }
+    return VL_OK;
+}
+
+// above this k the sampled collect/select path replaces the per-warp k-lists (tuning override:
+// VLITE_B200_LARGEK_MIN)
+int large_k_min() {
+    static int v = [] {
+        const char* e = getenv("VLITE_B200_LARGEK_MIN");
+        return e ? atoi(e) : 32;  // measured crossover: equal at k=32, 1.7x faster at k=100, 3x at k=256
+    }();
+    return v;
+}
+
+// k > large_k_min(): sampled threshold + collect + select (largek.cuh).  *done = false asks the caller to run
+// the exact multi-pass path instead (tiny corpus, or a buffer overflowed / came up short).
+int search_large_k(vl_corpus* c, ScanParams p, int n_queries, int k, int metric, uint32_t* o_s, uint64_t* o_r,
+                   bool* done) {
+    *done = false;
+    cudaStream_t st = c->stream;
+    uint32_t cap = 8192;
+    while (cap < 6u * (uint32_t)k) cap <<= 1;                       // expected ~3k candidates per query
+    const size_t key_bytes = (size_t)n_queries * cap * 8;
+    if (key_bytes > (8ull << 30)) return VL_OK;                      // would need > 8 GB of scratch
+    // sample list length: 16..32 keeps the sampled pass on the scan's register-list fast path and lets
+    // it visit few tiles; the threshold's relative spread is 1/sqrt(ks) <= 25 %, far inside the margin
+    // between the ~3k rows expected at or below it and both failure modes (fewer than k: fallback;
+    // more than cap >= 6k: fallback)
+    const int ks = std::min(kLargeKSample, std::max(16, k / 4));
+    // sample every `stride`-th tile: at least 3k expected candidates, and never more than 5 % of a scan
+    const uint32_t stride = std::max<uint32_t>(20u, (3u * (uint32_t)k) / (uint32_t)ks);
+    TRY(c->lk_keys.ensure(key_bytes));
+    TRY(c->lk_misc.ensure((size_t)n_queries * (4 + 4 + kLargeKSample * 12) + 64));
+    uint32_t* thr = static_cast<uint32_t*>(c->lk_misc.p);
+    uint32_t* cnt = thr + n_queries;
+    uint64_t* smp_r = reinterpret_cast<uint64_t*>(cnt + n_queries);  // 8*Q bytes in: 8-byte aligned
+    uint32_t* smp_s = reinterpret_cast<uint32_t*>(smp_r + (size_t)n_queries * kLargeKSample);
+    int* flags = c->d_err;
+    if (c->count <= cap) {
+        // the whole shard fits a buffer: no sampling, collect every eligible row
+        CU(cudaMemsetAsync(thr, 0xFF, (size_t)n_queries * 4, st));
+    } else {
+        ScanParams ps = p;
+        ps.tile_stride = stride;
+        TRY(search_lists(c, ps, n_queries, ks, metric, smp_s, smp_r));
+        extract_thr_kernel<<<(n_queries + 127) / 128, 128, 0, st>>>(smp_s, smp_r, n_queries, ks, thr);
+        LAUNCHED();
+    }
+    CU(cudaMemsetAsync(cnt, 0, (size_t)n_queries * 4, st));
+    ScanParams pc = p;
+    pc.k = 1;
+    pc.collect_thr = thr;
+    pc.collect_keys = static_cast<unsigned long long*>(c->lk_keys.p);
+    pc.collect_count = cnt;
+    pc.collect_cap = cap;
+    TRY(c->cand_buf.ensure((size_t)n_queries * 12));
+    pc.tau = static_cast<uint32_t*>(c->cand_buf.p);
+    TRY(c->part_s.ensure(4096));
+    TRY(c->part_r.ensure(4096));
+    pc.part_scores = static_cast<uint32_t*>(c->part_s.p);
+    pc.part_rows = static_cast<uint64_t*>(c->part_r.p);
+    pc.evict_first = 0;
+    TRY(launch_scan(c, pc, n_queries, 1, metric, nullptr, /*dry=*/false));
+    if (c->timing) CU(cudaEventRecord(c->ev1, st));
+    const size_t smem = (size_t)cap * 8;
+    TRY(allow_max_smem(collect_select_kernel, c->device));
+    collect_select_kernel<<<n_queries, kSelectThreads, smem, st>>>(pc.collect_keys, cnt, thr, cap, k, c->base_row, o_s,
+                                                                o_r, flags);
+    LAUNCHED();
+    int h = 0;
+    CU(cudaMemcpyAsync(&h, flags, sizeof h, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    if (h) {
+        CU(cudaMemsetAsync(flags, 0, sizeof(int), st));
+        return VL_OK;  // overflow / shortfall: let the exact multi-pass path answer
+    }
+    *done = true;
+    return VL_OK;
+}
+
+}  // namespace
