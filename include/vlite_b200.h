@@ -76,6 +76,8 @@ uint64_t vl_launch_count(void);
 /* ---- corpus residency: replaces the per-query rebuild of the (N, W) array
  * from the Python dict (vlite/main.py:143-146) and the dict appends of
  * VLite.add / set_batch (vlite/main.py:89-95, :264-268) ------------------- */
+/* capacity_rows: rows to back with memory up front (0 = grow on demand); a shard holds at most
+ * 2^31 - 1024 rows (local rows are 32-bit inside the kernels; global rows are 64-bit) */
 int vl_corpus_create(int device, int width_bytes, uint64_t capacity_rows, vl_corpus** out);
 int vl_corpus_destroy(vl_corpus* c);
 /* stream: a cudaStream_t (as void*); NULL = the legacy default stream */
