@@ -341,6 +341,34 @@ def run_ours(args):
 
     extra = {}
     cpu_baseline = None
+    if world > 1:
+        # HBM-bound leg of the sharded path: 1 and 2 queries over 16 GB per GPU (scan + all-gather + merge),
+        # i.e. BASELINE's "scanned corpus GB/s vs HBM roofline" at this GPU count; at 8 GPUs this is the
+        # north star's 1B-vector corpus (configs[3])
+        big = 125_000_000
+        with _capi.Corpus(w, device=local_rank, capacity_rows=big, base_row=rank * big) as cb:
+            cb.set_stream(torch.cuda.current_stream().cuda_stream)
+            cb.fill_synthetic(0, 0, big)
+            sb = ShardedSearcher(cb)
+            for q_small in (1, 2):
+                tt = []
+                for i in range(6):
+                    barrier()
+                    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    a.record()
+                    sb.search(dq[:q_small], k, _capi.HAMMING)
+                    b.record()
+                    b.synchronize()
+                    if i >= 2:
+                        tt.append(a.elapsed_time(b))
+                t_leg = torch.tensor([float(np.mean(tt))], dtype=torch.float64, device=dev)
+                dist.all_reduce(t_leg, op=dist.ReduceOp.MAX)
+                agg = world * big * w / (float(t_leg.item()) * 1e-3) / 1e9
+                extra[f"hbm_leg_q{q_small}"] = {
+                    "rows_total": big * world, "corpus_GB_total": world * big * w / 1e9,
+                    "step_ms_max_over_ranks": float(t_leg.item()), "aggregate_GBps": agg,
+                    "hbm_frac_of_aggregate": agg / (world * hbm_peak),
+                    "qps": q_small / (float(t_leg.item()) * 1e-3)}
     if world == 1:
         # HBM-bound leg of the same kernel: 1 and 2 queries over a corpus far larger than L2
         big = 32_000_000
