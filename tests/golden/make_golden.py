@@ -78,6 +78,7 @@ def golden_search(ref_model):
         ("u128", 128, 900, 10, 0, 12),
         ("dup128", 128, 600, 8, 37, 13),   # heavy ties (distribution D)
         ("kbig64", 64, 50, 80, 0, 14),     # top_k > N -> clamp (model.py:84)
+        ("u32", 32, 500, 7, 0, 15),        # 256-bit rows: the reference's search is width-agnostic
     ]
     for name, w, n, k, period, seed in cases:
         corpus = synth.corpus_rows(seed, 0, n, w, period)

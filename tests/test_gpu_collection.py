@@ -258,7 +258,7 @@ def test_embedding_model_search_is_the_reference_seam(gpu):
     from vlite_b200 import EmbeddingModel
     g = np.load(os.path.join(GOLD, "search_golden.npz"))
     m = EmbeddingModel(embedder=lambda t: None)
-    for name in ("u64", "u128", "dup128", "kbig64"):
+    for name in ("u64", "u128", "dup128", "kbig64", "u32"):
         corpus, queries, k = g[f"{name}_corpus_u8"], g[f"{name}_queries_u8"], int(g[f"{name}_k"])
         e_f32 = osearch.to_ref_encoding(corpus).astype(np.float32)     # what main.py:146 hands to search
         for qi, q in enumerate(queries):

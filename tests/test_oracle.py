@@ -10,7 +10,7 @@ from oracle import cscan, ctxfile, ref_port, search as osearch, synth
 
 GOLD = os.path.join(os.path.dirname(__file__), "golden")
 SG = np.load(os.path.join(GOLD, "search_golden.npz"))
-CASES = ["u64", "u128", "dup128", "kbig64"]
+CASES = ["u64", "u128", "dup128", "kbig64", "u32"]
 
 
 @pytest.mark.parametrize("name", CASES)
