@@ -581,9 +581,17 @@ class VLite:
 
     @_locked
     def close(self):
+        """Release the device memory of the collection (not part of the reference API; the files on
+        disk are untouched)."""
         if self._corpus is not None:
             self._corpus.close()
             self._corpus = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
 
 
 class ShardedVLite(VLite):
