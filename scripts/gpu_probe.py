@@ -3,9 +3,7 @@ Writes gpurun_out/probe.json.  Not the bench; numbers here guide tuning."""
 import json
 import os
 import sys
-import time
 
-import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)

@@ -1,6 +1,6 @@
 """2+ GPU probe: where does a sharded step spend its time (scan / all-gather / merge)?"""
 import os, sys, time
-import numpy as np
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import torch, torch.distributed as dist

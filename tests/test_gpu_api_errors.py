@@ -1,5 +1,4 @@
 """-m gpu: error behaviour of the C ABI (negative code + vl_last_error, no crash, no silent fallback)."""
-import ctypes
 
 import numpy as np
 import pytest

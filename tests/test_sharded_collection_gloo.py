@@ -12,7 +12,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from oracle import cscan, search as osearch, synth
+from oracle import search as osearch, synth
 from vlite_b200.sharded import ShardedCorpus
 
 
