@@ -204,6 +204,14 @@ int vl_set_timing(vl_corpus* c, int enabled);
 /* tuning knobs for experiments and tests (0 = automatic): row_splits = CTAs per query tile;
  * stages = depth of the TMA ring, or -1 to force the exact multi-pass path for k > 32 */
 int vl_set_tuning(vl_corpus* c, int row_splits, int stages);
+/* which scan kernel answers vl_search on this handle.  0 = automatic (default): HAMMING batches of
+ * at least 64 queries with k <= 16 (and the collect pass of k > 32) go to the tensor-core kernel
+ * (tcgen05.mma kind::i8 on rows expanded bit -> int8 in shared memory; exact int32 scores), the rest
+ * to the integer-pipe kernel (LOP3 + POPC / DP4A).  1 = integer-pipe kernel only; 2 / 3 = tensor-core
+ * kernel with one CTA / a CTA pair per query tile whenever the call is eligible (any batch size).
+ * Results are bit-identical on every path (tests/test_gpu_mma_scan.py).  Replaces the same reference
+ * lines as vl_search: vlite/model.py:71-74 + :84-85. */
+int vl_set_scan_path(vl_corpus* c, int path);
 
 /* ---- shard group: several shards searched as one corpus, in one process --- */
 /* The in-process twin of the one-process-per-GPU path (the reference has no

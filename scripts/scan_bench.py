@@ -31,6 +31,7 @@ for spec in sys.argv[1:]:
         cache[key] = c
     c = cache[key]
     c.set_tuning(splits, stages)
+    c.set_scan_path(int(os.environ.get("SCAN_PATH", "0")))
     q = synth.uniform_queries(1, nq, w)
     dq = torch.from_numpy(q).cuda()
     ds = torch.empty((nq, k), dtype=torch.int32, device="cuda")
@@ -46,7 +47,7 @@ for spec in sys.argv[1:]:
     t, s = float(np.median(ts)), float(np.median(ss))
     pairs = n * nq
     t_roof = max(n * w / HBM_PEAK, pairs * (w / 4) / POPC_PEAK)
-    print(json.dumps({"n": n, "w": w, "nq": nq, "k": k, "metric": metric, "splits": splits, "stages": stages,
+    print(json.dumps({"n": n, "w": w, "nq": nq, "k": k, "metric": metric, "splits": splits, "stages": stages, "path": int(os.environ.get("SCAN_PATH", "0")),
                       "total_ms": round(t, 4), "scan_ms": round(s, 4), "qps": round(nq / (t * 1e-3)),
                       "GBps": round(n * w / (s * 1e-3) / 1e9, 1),
                       "Tpopc": round(pairs * (w / 4) / (s * 1e-3) / 1e12, 3),

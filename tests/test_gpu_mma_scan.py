@@ -1,0 +1,134 @@
+"""-m gpu parity tests of the tensor-core scan (csrc/mmascan.cuh: tcgen05.mma kind::i8 on rows
+expanded bit -> int8 in shared memory) through the C ABI against the CPU oracle.
+
+Bar: bit-exact scores and row lists under the (score, row) tie-break, identical to the
+integer-pipe kernel on every shape.  vl_set_scan_path forces the kernel: 2 = one CTA per query
+tile, 3 = CTA pairs (cta_group::2)."""
+import numpy as np
+import pytest
+
+from oracle import cscan, synth
+
+pytestmark = pytest.mark.gpu
+
+HAMMING = 0
+PATHS = [2, 3]
+
+
+def _check(c, corpus, queries, k, mask_words=None, base_row=0):
+    s, r = c.search(queries, k, HAMMING, mask_words)
+    es, er = cscan.search(queries, corpus, k, HAMMING, mask_words, base_row)
+    np.testing.assert_array_equal(s, es)
+    np.testing.assert_array_equal(r, er)
+
+
+@pytest.mark.parametrize("path", PATHS)
+@pytest.mark.parametrize("width", [128, 64, 32])
+@pytest.mark.parametrize("nq", [1, 100, 128, 129, 300])
+def test_topk_query_tilings(gpu, path, width, nq):
+    n, k = 20011, 10   # ragged: not a multiple of the 128 / 256-row tile
+    corpus = synth.corpus_rows(5, 0, n, width)
+    queries = synth.uniform_queries(6, nq, width)
+    queries[0] = corpus[n - 1]            # exact hit on the last row
+    with gpu.Corpus(width) as c:
+        c.append(corpus)
+        c.set_scan_path(path)
+        _check(c, corpus, queries, k)
+
+
+@pytest.mark.parametrize("path", PATHS)
+@pytest.mark.parametrize("k", [1, 5, 16])
+@pytest.mark.parametrize("n", [1, 127, 128, 129, 255, 257, 5000])
+def test_k_and_tiny_corpora(gpu, path, k, n):
+    corpus = synth.corpus_rows(7, 0, n, 128)
+    queries = synth.uniform_queries(8, 70, 128)
+    with gpu.Corpus(128) as c:
+        c.append(corpus)
+        c.set_scan_path(path)
+        _check(c, corpus, queries, k)     # k > n: sentinel padded
+
+
+@pytest.mark.parametrize("path", PATHS)
+def test_duplicates_ties_break_on_row(gpu, path):
+    n = 60_000
+    corpus = synth.corpus_rows(9, 0, n, 128, period=500)   # every row 120 times: ties everywhere
+    queries = synth.uniform_queries(10, 140, 128)
+    queries[3] = corpus[17]
+    with gpu.Corpus(128) as c:
+        c.append(corpus)
+        c.set_scan_path(path)
+        _check(c, corpus, queries, 10)
+        _check(c, corpus, queries, 16)
+
+
+@pytest.mark.parametrize("path", PATHS)
+@pytest.mark.parametrize("sel", [0.01, 0.5])
+def test_filter_mask_and_tombstones(gpu, path, sel):
+    n, w = 150_003, 128
+    corpus = synth.corpus_rows(11, 0, n, w)
+    queries, src = synth.clustered_queries(12, 0, n, 200, w)
+    valid = synth.filter_valid(13, 0, n, sel)
+    dead = np.unique(np.concatenate([src[:50], np.arange(0, n, 977)])).astype(np.uint64)
+    live = np.ones(n, dtype=bool)
+    live[dead.astype(np.int64)] = False
+    with gpu.Corpus(w) as c:
+        c.append(corpus)
+        c.tombstone(dead)
+        c.set_scan_path(path)
+        s, r = c.search(queries, 10, HAMMING, synth.pack_mask(valid))
+        es, er = cscan.search(queries, corpus, 10, HAMMING, synth.pack_mask(valid & live))
+        np.testing.assert_array_equal(s, es)
+        np.testing.assert_array_equal(r, er)
+        s, r = c.search(queries, 10, HAMMING)
+        es, er = cscan.search(queries, corpus, 10, HAMMING, synth.pack_mask(live))
+        np.testing.assert_array_equal(s, es)
+        np.testing.assert_array_equal(r, er)
+
+
+@pytest.mark.parametrize("path", PATHS)
+def test_matches_integer_pipe_kernel_and_base_row(gpu, path):
+    n, w, nq = 300_000, 128, 1024
+    base = 5_000_000_000
+    queries = synth.uniform_queries(15, nq, w)
+    with gpu.Corpus(w, base_row=base) as c:
+        c.fill_synthetic(14, 0, n)
+        c.set_scan_path(1)
+        s1, r1 = c.search(queries, 10, HAMMING)
+        c.set_scan_path(path)
+        s2, r2 = c.search(queries, 10, HAMMING)
+        assert r1.min() >= base
+        np.testing.assert_array_equal(s1, s2)
+        np.testing.assert_array_equal(r1, r2)
+        for splits in (1, 3, 40):            # result must not depend on how rows are split over CTAs
+            c.set_tuning(row_splits=splits)
+            s3, r3 = c.search(queries[:200], 10, HAMMING)
+            np.testing.assert_array_equal(s3, s1[:200])
+            np.testing.assert_array_equal(r3, r1[:200])
+
+
+@pytest.mark.parametrize("path", PATHS)
+@pytest.mark.parametrize("k", [100, 1000])
+def test_large_k_collect_pass_on_tensor_cores(gpu, path, k):
+    n = 200_000
+    corpus = synth.corpus_rows(16, 0, n, 128)
+    queries = synth.uniform_queries(17, 130, 128)
+    with gpu.Corpus(128) as c:
+        c.append(corpus)
+        c.set_scan_path(path)
+        _check(c, corpus, queries, k)
+
+
+def test_automatic_dispatch_is_bit_identical(gpu):
+    """auto mode: Q >= 64 with k <= 16 goes to the tensor-core kernel, everything else to the
+    integer-pipe kernel; XORSUM never does."""
+    n = 50_000
+    corpus = synth.corpus_rows(18, 0, n, 64)
+    queries = synth.uniform_queries(19, 260, 64)
+    with gpu.Corpus(64) as c:
+        c.append(corpus)
+        for nq in (63, 64, 260):
+            _check(c, corpus, queries[:nq], 10)
+        s, r = c.search(queries, 10, 1)
+        es, er = cscan.search(queries, corpus, 10, 1)
+        np.testing.assert_array_equal(s, es)
+        np.testing.assert_array_equal(r, er)

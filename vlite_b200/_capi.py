@@ -98,6 +98,7 @@ def load():
         "vl_last_timing": (c_int, [c_void_p, P(ctypes.c_float), P(ctypes.c_float)]),
         "vl_set_timing": (c_int, [c_void_p, c_int]),
         "vl_set_tuning": (c_int, [c_void_p, c_int, c_int]),
+        "vl_set_scan_path": (c_int, [c_void_p, c_int]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)
@@ -312,6 +313,10 @@ class Corpus:
 
     def set_tuning(self, row_splits: int = 0, stages: int = 0):
         check(self._L.vl_set_tuning(self._h, row_splits, stages))
+
+    def set_scan_path(self, path: int = 0):
+        """0 auto, 1 integer-pipe kernel only, 2 / 3 tensor-core kernel (1 / 2 CTAs per query tile)."""
+        check(self._L.vl_set_scan_path(self._h, path))
 
 
 class ShardGroup:

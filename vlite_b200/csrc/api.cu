@@ -23,6 +23,7 @@
 #include "repack.cuh"
 #include "rescore.cuh"
 #include "scan.cuh"
+#include "mmascan.cuh"
 #include "synth.cuh"
 
 #include "host_util.cuh"
@@ -734,6 +735,13 @@ extern "C" int vl_set_tuning(vl_corpus* c, int row_splits, int stages) {
     if (stages < 0) stages = 0;
     c->tune_splits = row_splits;
     c->tune_stages = stages;
+    return VL_OK;
+}
+
+extern "C" int vl_set_scan_path(vl_corpus* c, int path) {
+    if (!c) return fail(VL_EINVAL, "corpus is NULL");
+    if (path < 0 || path > 3) return fail(VL_EINVAL, "scan path must be 0 (auto), 1 (integer pipes), 2 or 3 (tensor cores, 1 or 2 CTAs per tile)");
+    c->scan_path = path;
     return VL_OK;
 }
 

@@ -144,6 +144,7 @@ struct vl_corpus {
     bool timed = false;
     int tune_splits = 0;
     int tune_stages = 0;
+    int scan_path = 0;  // 0 auto, 1 integer-pipe kernel only, 2 / 3 tensor-core kernel with 1 / 2 CTAs per tile
 };
 
 namespace {
@@ -234,7 +235,7 @@ int check_err_flag(vl_corpus* c, const char* what) {
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-int make_corpus_tmap(const vl_corpus* c, CUtensorMap* out) {
+int make_corpus_tmap(const vl_corpus* c, CUtensorMap* out, int box_rows = kTileRows) {
     static std::atomic<EncodeTiledFn> cached{nullptr};
     EncodeTiledFn fn = cached.load();
     if (!fn) {
@@ -248,7 +249,7 @@ int make_corpus_tmap(const vl_corpus* c, CUtensorMap* out) {
     }
     const cuuint64_t dims[2] = {(cuuint64_t)c->w, (cuuint64_t)c->count};
     const cuuint64_t strides[1] = {(cuuint64_t)c->w};
-    const cuuint32_t box[2] = {(cuuint32_t)c->w, (cuuint32_t)kTileRows};
+    const cuuint32_t box[2] = {(cuuint32_t)c->w, (cuuint32_t)box_rows};
     const cuuint32_t estr[2] = {1, 1};
     const CUtensorMapSwizzle sw = c->w == 128  ? CU_TENSOR_MAP_SWIZZLE_128B
                                   : c->w == 64 ? CU_TENSOR_MAP_SWIZZLE_64B

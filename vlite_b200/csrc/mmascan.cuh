@@ -1,0 +1,515 @@
+// Kernel 1T: the scan for large query batches on the 5th-generation tensor cores (tcgen05 + TMEM).
+//
+// Same contract as scan_topk_kernel (scan.cuh): HAMMING scores of a batch of queries against the
+// packed corpus (reference: EmbeddingModel.hamming_distance, vlite/model.py:71-74, applied to
+// unpacked bits) + per-CTA top-k lists by (score, row) (vlite/model.py:85), bit-exact.
+//
+// Why a second kernel: for Q >= 64 the scan is a dense binary contraction,
+//     hamming(q, e) = (8W - <s(q), s(e)>) / 2,   s(bit) = +1 (bit 0) / -1 (bit 1),
+// and the LOP3/POPC kernel is bound by the integer pipes (16 POPC/clk/SM) at ~2e11 pairs/s while
+// the int8 tensor pipe (tcgen05.mma kind::i8, exact int32 accumulation) does 8192 MAC/clk/SM =
+// 1.5e12 pairs/s at W = 128.  The corpus stays PACKED in HBM (the format is the product); rows are
+// expanded bit -> int8 in shared memory only, once per 128 (or 256) queries.
+//
+//   grid    = (query tiles of 128, row splits); CG = 1: one CTA per tile, CG = 2: a CTA pair
+//             (cluster of 2, tcgen05 cta_group::2) shares every expanded row tile between its 256
+//             queries -- each CTA expands only half of the rows it scores.
+//   A (M)   = this CTA's 128 queries, expanded once into shared memory (K-major, 128 B swizzle).
+//   B (N)   = corpus rows: TMA streams packed 128-row boxes (hardware swizzle) into a 2-stage ring;
+//             8 "expander" warps turn each 16-byte chunk of a row into 128 int8 (one K slab of one
+//             row: SHL + PRMT sign-replicate + LOP3) and store it in the UMMA canonical layout
+//             into a 3-stage slab ring (generic-proxy stores -> fence.proxy.async -> mbarrier).
+//             The K order inside a slab is a fixed permutation applied to rows and queries alike.
+//             Masked rows (tombstones, filter, past the end) expand to zeros.
+//   D       = TMEM, 128 lanes (queries) x NT columns (rows of the tile) int32, double buffered:
+//             one elected thread issues W/4 tcgen05.mma (K = 32 each) per tile and commits to
+//             mbarriers; the epilogue of tile i overlaps the MMAs of tile i + 1.
+//   epilogue= 4 warps, one query per thread (its TMEM lane): tcgen05.ld 32 columns at a time, a
+//             max tree against the thread's own threshold, and -- rarely -- the insert of (score,
+//             row) into the thread's register-resident sorted k-list (k <= 16) or the append to
+//             the per-query collect buffer (large k).  tau[] shares thresholds between CTAs as in
+//             scan.cuh.  Output = one sorted list per (row split, query) for merge.cuh.
+#pragma once
+#include "scan.cuh"
+
+namespace vl {
+
+constexpr int kMmaQT = 128;          // queries per CTA = TMEM lanes = UMMA M per CTA
+constexpr int kMmaRows = 128;        // corpus rows one CTA expands per tile
+constexpr int kMmaBStages = 3;       // expanded K slabs in flight
+constexpr int kMmaPkStages = 2;      // packed row boxes in flight
+constexpr int kMmaThreads = 512;     // warps 0 TMA, 1 MMA, 2 TMEM alloc, 3 idle | 4-7 epilogue | 8-15 expanders
+constexpr int kMmaExpWarps = 8;
+constexpr int kMmaListCap = 16;      // k <= 16 per-thread register list
+constexpr int kMmaSlabBytes = 128 * 128;
+
+template <int W, int CG>
+struct MmaCfg {
+    static constexpr int K = W * 8;                 // int8 elements per row
+    static constexpr int SLABS = W / 16;            // K slabs of 128 elements (= one 16 B packed chunk)
+    static constexpr int NT = kMmaRows * CG;        // rows per tile = UMMA N
+    static constexpr int MW = NT / 32;              // mask words per tile
+    static constexpr int A_BYTES = SLABS * kMmaSlabBytes;
+    static constexpr int PK_BYTES = kMmaRows * W;
+    static constexpr int TMEM_COLS = 2 * NT;        // two accumulator buffers
+    static constexpr size_t SMEM =
+        (size_t)A_BYTES + (size_t)kMmaBStages * kMmaSlabBytes + (size_t)kMmaPkStages * PK_BYTES +
+        (size_t)kMmaPkStages * 2 * MW * 4 + 16 * 8 + 16 + 1024 /* alignment slack */;
+    static_assert(W == 32 || W == 64 || W == 128, "row width");
+    static_assert(CG == 1 || CG == 2, "cta group");
+};
+
+// ---- tcgen05 / cluster PTX wrappers ------------------------------------------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t mapa_shared(uint32_t saddr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank));
+    return r;
+}
+// arrive on a barrier of another CTA of the cluster.  Default semantics (release at CTA scope) on
+// purpose: the data the barrier guards never leaves the arriving CTA's own shared memory (it is read
+// by that SM's tensor core), only the signal crosses; a cluster-scope release would cost a
+// MEMBAR.ALL.GPU + L1 invalidate per slab.
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait_cluster(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
+    while (!mbar_try_wait_cluster(bar, parity)) {
+    }
+}
+// generic-proxy shared-memory writes -> visible to the async proxy (UMMA operand reads)
+__device__ __forceinline__ void fence_proxy_async_smem() {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+template <int CG>
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t cols) {   // one full warp
+    if constexpr (CG == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(cols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    } else {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(cols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+}
+template <int CG>
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
+    if constexpr (CG == 1)
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+    else
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+// D[tmem] (+)= A[smem desc] * B[smem desc], int8 x int8 -> int32, issued by ONE thread (SASS UTCIMMA)
+template <int CG>
+__device__ __forceinline__ void umma_i8(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    if constexpr (CG == 1)
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                     "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc),
+                     "r"(idesc), "r"(accumulate)
+                     : "memory");
+    else
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                     "tcgen05.mma.cta_group::2.kind::i8 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc),
+                     "r"(idesc), "r"(accumulate)
+                     : "memory");
+}
+// arrive on an mbarrier once every tcgen05 operation issued so far by this thread has completed;
+// CG = 2: the same barrier offset in both CTAs of the pair
+template <int CG>
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    if constexpr (CG == 1)
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+    else
+        asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                         smem_u32(bar)),
+                     "h"((uint16_t)3)
+                     : "memory");
+}
+// 32 lanes x 32 consecutive 32-bit columns of TMEM -> 32 registers per thread (lane = thread)
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+          "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+          "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// UMMA shared-memory descriptor of a K-major operand slab in the canonical 128 B-swizzle layout:
+// row r of the slab at r * 128 B, its 16 B chunk c stored at chunk position c ^ (r & 7); groups of 8
+// rows 1024 B apart (stride byte offset), slab base 1024 B aligned (base offset 0).
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
+    return (uint64_t)((saddr >> 4) & 0x3FFFu) | (1ull << 16) /* LBO (unused for swizzled K-major) */ |
+           (64ull << 32) /* SBO = 1024 B */ | (1ull << 46) /* descriptor version: sm_100 */ |
+           (2ull << 61) /* SWIZZLE_128B */;
+}
+// instruction descriptor: D = s32, A = B = signed 8 bit, both K-major, shape M x N (K = 32 implied)
+__host__ __device__ constexpr uint32_t umma_idesc_i8(int m, int n) {
+    return (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+
+// bit -> int8: byte i of the result is -1 (0xFF) if bit (8 i + 7 - s) of x is set, else +1 (0x01);
+// `keep` = 0 zeroes the word (masked row).  SHL + PRMT (sign replicate) + LOP3.
+template <int S>
+__device__ __forceinline__ uint32_t expand_pm1(uint32_t x, uint32_t keep) {
+    // prmt selector nibble 8 + i: replicate the sign bit of byte i (the __byte_perm intrinsic masks
+    // that mode bit off, hence inline PTX)
+    uint32_t m;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(m) : "r"(x << S), "r"(0u), "r"(0xBA98u));
+    return (m | 0x01010101u) & keep;
+}
+__device__ __forceinline__ void sts128(uint32_t saddr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+// one 16 B packed chunk (4 words) of a row -> K-slab chunks [C0, C0 + NC) of that row.  Element
+// (chunk c, word t, byte i) of the slab is bit (8 i + 7 - c) of packed word t: the same permutation
+// of K for corpus rows and queries, so the contraction is unchanged.
+template <int C0, int NC>
+__device__ __forceinline__ void expand_chunks(const uint4& x, uint32_t keep, uint32_t slab_row_saddr, uint32_t r7) {
+#pragma unroll
+    for (int cc = 0; cc < NC; ++cc) {
+        constexpr int kBase = C0;
+        const int c = kBase + cc;
+        uint32_t o0, o1, o2, o3;
+        switch (c) {   // c is a compile-time constant after unrolling
+            case 0: o0 = expand_pm1<0>(x.x, keep); o1 = expand_pm1<0>(x.y, keep); o2 = expand_pm1<0>(x.z, keep); o3 = expand_pm1<0>(x.w, keep); break;
+            case 1: o0 = expand_pm1<1>(x.x, keep); o1 = expand_pm1<1>(x.y, keep); o2 = expand_pm1<1>(x.z, keep); o3 = expand_pm1<1>(x.w, keep); break;
+            case 2: o0 = expand_pm1<2>(x.x, keep); o1 = expand_pm1<2>(x.y, keep); o2 = expand_pm1<2>(x.z, keep); o3 = expand_pm1<2>(x.w, keep); break;
+            case 3: o0 = expand_pm1<3>(x.x, keep); o1 = expand_pm1<3>(x.y, keep); o2 = expand_pm1<3>(x.z, keep); o3 = expand_pm1<3>(x.w, keep); break;
+            case 4: o0 = expand_pm1<4>(x.x, keep); o1 = expand_pm1<4>(x.y, keep); o2 = expand_pm1<4>(x.z, keep); o3 = expand_pm1<4>(x.w, keep); break;
+            case 5: o0 = expand_pm1<5>(x.x, keep); o1 = expand_pm1<5>(x.y, keep); o2 = expand_pm1<5>(x.z, keep); o3 = expand_pm1<5>(x.w, keep); break;
+            case 6: o0 = expand_pm1<6>(x.x, keep); o1 = expand_pm1<6>(x.y, keep); o2 = expand_pm1<6>(x.z, keep); o3 = expand_pm1<6>(x.w, keep); break;
+            default: o0 = expand_pm1<7>(x.x, keep); o1 = expand_pm1<7>(x.y, keep); o2 = expand_pm1<7>(x.z, keep); o3 = expand_pm1<7>(x.w, keep); break;
+        }
+        sts128(slab_row_saddr + (((uint32_t)c ^ r7) << 4), o0, o1, o2, o3);
+    }
+}
+
+template <int W, int CG, bool COLLECT>
+__global__ void __launch_bounds__(kMmaThreads, 1)
+mma_scan_kernel(const __grid_constant__ CUtensorMap tmap, const ScanParams p) {
+    using Cfg = MmaCfg<W, CG>;
+    constexpr int SLABS = Cfg::SLABS, NT = Cfg::NT, MW = Cfg::MW, K = Cfg::K;
+    constexpr int CHUNKS = W / 16;
+
+    extern __shared__ uint8_t smem_raw[];
+    // the dynamic shared window is only 16 B aligned by contract: swizzled operands want 1024 B
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* sA = smem;
+    uint8_t* sB = sA + Cfg::A_BYTES;
+    uint8_t* sPk = sB + kMmaBStages * kMmaSlabBytes;
+    uint32_t* sMask = reinterpret_cast<uint32_t*>(sPk + kMmaPkStages * Cfg::PK_BYTES);   // [stage][live | filter][MW]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sMask + kMmaPkStages * 2 * MW);
+    uint64_t* pk_full = bars;                    // [2]  TMA -> expanders
+    uint64_t* pk_empty = bars + 2;               // [2]  expanders -> TMA
+    uint64_t* b_full = bars + 4;                 // [3]  expanders (both CTAs) -> MMA thread of the leader
+    uint64_t* b_empty = bars + 7;                // [3]  tcgen05.commit -> expanders (each CTA its own copy)
+    uint64_t* acc_full = bars + 10;              // [2]  tcgen05.commit -> epilogue (each CTA its own copy)
+    uint64_t* acc_empty = bars + 12;             // [2]  epilogue warps (both CTAs) -> MMA thread of the leader
+    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 14);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const uint32_t rank = (CG == 2) ? cluster_ctarank() : 0u;
+    const int q0 = (int)blockIdx.x * kMmaQT;     // blockIdx.x = pair * CG + rank
+    const int split = blockIdx.y;
+    const int n_splits = gridDim.y;
+    const uint32_t tile_begin = (uint32_t)(((uint64_t)p.n_tiles * split) / n_splits);
+    const uint32_t tile_end = (uint32_t)(((uint64_t)p.n_tiles * (split + 1)) / n_splits);
+    const uint32_t my_tiles = tile_end - tile_begin;
+    const bool has_filter = p.filter != nullptr;
+
+    if (threadIdx.x == 0) {
+        tma_prefetch_desc(&tmap);
+        for (int s = 0; s < kMmaPkStages; ++s) {
+            mbar_init(&pk_full[s], 1);
+            mbar_init(&pk_empty[s], kMmaExpWarps);
+        }
+        for (int s = 0; s < kMmaBStages; ++s) {
+            mbar_init(&b_full[s], kMmaExpWarps * CG);
+            mbar_init(&b_empty[s], 1);
+        }
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(&acc_full[b], 1);
+            mbar_init(&acc_empty[b], 4 * CG);
+        }
+        mbar_fence_init();
+    }
+    if (warp == 2) tmem_alloc<CG>(s_tmem, (uint32_t)Cfg::TMEM_COLS);
+
+    // ---- A operand: expand this CTA's queries once (zeros past n_queries) ----
+    {
+        const uint32_t a_saddr = smem_u32(sA);
+        for (int it = threadIdx.x; it < kMmaQT * SLABS * 2; it += kMmaThreads) {
+            const int ql = it % kMmaQT;
+            const int j = (it / kMmaQT) % SLABS;
+            const int h = it / (kMmaQT * SLABS);
+            const int qg = q0 + ql;
+            uint4 x = make_uint4(0, 0, 0, 0);
+            uint32_t keep = 0;
+            if (qg < p.n_queries) {
+                x = *reinterpret_cast<const uint4*>(p.queries + (size_t)qg * W + j * 16);
+                keep = 0xFFFFFFFFu;
+            }
+            const uint32_t row_saddr = a_saddr + (uint32_t)j * kMmaSlabBytes + (uint32_t)ql * 128u;
+            if (h == 0)
+                expand_chunks<0, 4>(x, keep, row_saddr, (uint32_t)(ql & 7));
+            else
+                expand_chunks<4, 4>(x, keep, row_saddr, (uint32_t)(ql & 7));
+        }
+        fence_proxy_async_smem();
+    }
+    tc_fence_before();
+    if constexpr (CG == 2) cluster_sync_all(); else __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *s_tmem;
+
+    if (warp == 0) {
+        // ===================== TMA producer: packed row boxes + their mask words =====================
+        if (lane == 0) {
+            const uint64_t policy = p.evict_first ? l2_policy_evict_first() : l2_policy_evict_last();
+            for (uint32_t i = 0; i < my_tiles; ++i) {
+                const int s = i % kMmaPkStages;
+                if (i >= kMmaPkStages) mbar_wait(&pk_empty[s], ((i / kMmaPkStages) - 1) & 1);
+                const uint32_t t = (tile_begin + i) * p.tile_stride;
+                const uint32_t mask_bytes = MW * 4;
+                mbar_arrive_expect_tx(&pk_full[s], Cfg::PK_BYTES + mask_bytes + (has_filter ? mask_bytes : 0));
+                tma_load_2d(sPk + (size_t)s * Cfg::PK_BYTES, &tmap, 0, (int)(t * NT + rank * kMmaRows), &pk_full[s], policy);
+                uint32_t* m = sMask + s * 2 * MW;
+                bulk_g2s(m, p.live + (size_t)t * MW, mask_bytes, &pk_full[s]);
+                if (has_filter) bulk_g2s(m + MW, p.filter + (size_t)t * MW, mask_bytes, &pk_full[s]);
+            }
+        }
+        __syncwarp();   // reconverge: the teardown barrier / cluster barrier is warp-aligned
+    } else if (warp == 1) {
+        // ===================== MMA issuer: one thread of the leader CTA =====================
+        if (rank == 0 && lane == 0) {
+            constexpr uint32_t idesc = umma_idesc_i8(kMmaQT * CG, NT);
+            const uint32_t a_saddr = smem_u32(sA), b_saddr = smem_u32(sB);
+            uint32_t g = 0;   // slab counter
+            for (uint32_t i = 0; i < my_tiles; ++i) {
+                const uint32_t buf = i & 1;
+                if (i >= 2) {
+                    if constexpr (CG == 2) mbar_wait_cluster(&acc_empty[buf], ((i >> 1) - 1) & 1);
+                    else mbar_wait(&acc_empty[buf], ((i >> 1) - 1) & 1);
+                    tc_fence_after();
+                }
+                const uint32_t d_tmem = tmem_base + buf * NT;
+#pragma unroll 1
+                for (int j = 0; j < SLABS; ++j, ++g) {
+                    const uint32_t st = g % kMmaBStages;
+                    const uint32_t par = (g / kMmaBStages) & 1;
+                    if constexpr (CG == 2) mbar_wait_cluster(&b_full[st], par); else mbar_wait(&b_full[st], par);
+                    tc_fence_after();
+                    const uint64_t ad = umma_desc_sw128(a_saddr + (uint32_t)j * kMmaSlabBytes);
+                    const uint64_t bd = umma_desc_sw128(b_saddr + st * kMmaSlabBytes);
+#pragma unroll
+                    for (int kk = 0; kk < 4; ++kk)   // K = 32 int8 = 32 B per instruction: +2 in the address field
+                        umma_i8<CG>(d_tmem, ad + (uint64_t)(kk * 2), bd + (uint64_t)(kk * 2), idesc, (j | kk) != 0 ? 1u : 0u);
+                    umma_commit<CG>(&b_empty[st]);
+                }
+                umma_commit<CG>(&acc_full[buf]);
+            }
+        }
+        __syncwarp();
+    } else if (warp >= 4 && warp < 8) {
+        // ===================== epilogue: one query per thread =====================
+        const uint32_t lane_base = (uint32_t)(warp & 3) * 32u;
+        const int ql = (int)lane_base + lane;
+        const int qg = q0 + ql;
+        const bool q_ok = qg < p.n_queries;
+        const int k = p.k;
+        // descending list: kk[0] = k-th best (worst kept), kk[k-1] = best; slots >= k stay 0
+        uint64_t kk[kMmaListCap];
+#pragma unroll
+        for (int e = 0; e < kMmaListCap; ++e) kk[e] = (!COLLECT && e < k) ? ~0ull : 0ull;
+        uint32_t thr = kSentinelScore;      // admit rows with score < thr
+        if constexpr (COLLECT) {
+            if (q_ok) {
+                const uint32_t v = p.collect_thr[qg];
+                thr = (v == kSentinelScore) ? v : v + 1;
+            }
+        }
+        constexpr int kNever = 1 << 30;
+        auto to_dot = [&](uint32_t th) -> int {   // score < th  <=>  dot > K - 2 th
+            if (!q_ok) return kNever;
+            return (th > (uint32_t)K) ? -kNever : K - 2 * (int)th;
+        };
+        int thrd = to_dot(thr);
+        const bool use_tau = !COLLECT && q_ok;
+        uint32_t* tau_ptr = p.tau + (q_ok ? qg : 0);
+        uint32_t tau_pref = kSentinelScore;
+        bool dirty = false;
+        const uint32_t acc_empty_remote = (CG == 2) ? mapa_shared(smem_u32(&acc_empty[0]), 0) : 0u;
+
+        for (uint32_t i = 0; i < my_tiles; ++i) {
+            const uint32_t buf = i & 1;
+            const uint32_t t = (tile_begin + i) * p.tile_stride;
+            if (use_tau) {
+                const uint32_t gth = (tau_pref == kSentinelScore) ? tau_pref : tau_pref + 1;
+                if (gth < thr) {
+                    thr = gth;
+                    thrd = to_dot(thr);
+                }
+                tau_pref = __ldcg(tau_ptr);
+            }
+            mbar_wait(&acc_full[buf], (i >> 1) & 1);
+            tc_fence_after();
+#pragma unroll 1
+            for (int ch = 0; ch < NT / 32; ++ch) {
+                uint32_t vu[32];
+                __syncwarp();   // tcgen05.ld is warp-aligned: reconverge after a divergent insert
+                tmem_ld32(tmem_base + (lane_base << 16) + buf * NT + (uint32_t)ch * 32u, vu);
+                tmem_ld_wait();
+                if (ch == NT / 32 - 1) {
+                    // the accumulator buffer is in registers now: hand it back to the MMA thread
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) {
+                        if constexpr (CG == 2) mbar_arrive_cluster(acc_empty_remote + buf * 8u);
+                        else mbar_arrive(&acc_empty[buf]);
+                    }
+                }
+                int v[32];
+#pragma unroll
+                for (int c = 0; c < 32; ++c) v[c] = (int)vu[c];
+                int m = v[0];
+#pragma unroll
+                for (int c = 1; c < 32; c += 2) m = max(m, max(v[c], (c + 1 < 32) ? v[c + 1] : v[c]));
+                if (!__any_sync(kFullMask, m > thrd)) continue;
+                // ---- rare: some thread of the warp has a candidate among these 32 rows ----
+                int limit = -1;
+                while (true) {
+                    int pc = 64, pv = 0;
+#pragma unroll
+                    for (int c = 31; c >= 0; --c)
+                        if (c > limit && v[c] > thrd) {
+                            pc = c;
+                            pv = v[c];
+                        }
+                    if (!__any_sync(kFullMask, pc < 64)) break;
+                    if (pc < 64) {
+                        limit = pc;
+                        const uint32_t rit = (uint32_t)ch * 32u + (uint32_t)pc;      // row in tile
+                        uint32_t wv = __ldg(p.live + (size_t)t * MW + (rit >> 5));
+                        if (has_filter) wv &= __ldg(p.filter + (size_t)t * MW + (rit >> 5));
+                        if ((wv >> (rit & 31)) & 1u) {
+                            const uint32_t score = (uint32_t)(K - pv) >> 1;
+                            const uint32_t lrow = t * (uint32_t)NT + rit;
+                            const uint64_t key = ((uint64_t)score << 32) | lrow;
+                            if constexpr (COLLECT) {
+                                const uint32_t slot = atomicAdd(p.collect_count + qg, 1u);
+                                if (slot < p.collect_cap) p.collect_keys[(size_t)qg * p.collect_cap + slot] = key;
+                            } else {
+                                // drop kk[0] (the worst), slide `key` into the descending list
+#pragma unroll
+                                for (int e = 0; e < kMmaListCap; ++e) {
+                                    const uint64_t nxt = (e + 1 < kMmaListCap) ? kk[e + 1] : 0ull;
+                                    kk[e] = (nxt > key) ? nxt : ((kk[e] > key) ? key : kk[e]);
+                                }
+                                thr = (uint32_t)(kk[0] >> 32);
+                                thrd = to_dot(thr);
+                                dirty = true;
+                            }
+                        }
+                    }
+                }
+            }
+            if (!COLLECT && dirty) {
+                dirty = false;
+                if (use_tau && thr != kSentinelScore && thr < tau_pref) atomicMin(tau_ptr, thr);
+            }
+        }
+        if constexpr (!COLLECT) {
+            if (q_ok) {
+                const size_t o = ((size_t)split * p.n_queries + qg) * k;
+#pragma unroll
+                for (int e = 0; e < kMmaListCap; ++e)
+                    if (e < k) {
+                        const uint64_t key = kk[e];
+                        const bool none = key == ~0ull;
+                        p.part_scores[o + (k - 1 - e)] = none ? kSentinelScore : (uint32_t)(key >> 32);
+                        p.part_rows[o + (k - 1 - e)] = none ? kSentinelRow : p.base_row + (uint32_t)key;
+                    }
+            }
+        }
+    } else if (warp >= 8) {
+        // ===================== expanders: packed rows -> int8 K slabs =====================
+        const int ew = warp - 8;
+        const int rgrp = ew & 3;            // 32 rows of the CTA's 128
+        const int half = ew >> 2;           // chunks [4 half, 4 half + 4) of every slab
+        const int r = rgrp * 32 + lane;
+        // TMA swizzle of the packed box: logical chunk j of row r at chunk j ^ rot(r)
+        constexpr int LANES_PER_128B = (W >= 128) ? 1 : 128 / W;
+        constexpr int ROT_MASK = (CHUNKS < 8 ? CHUNKS : 8) - 1;
+        const uint32_t rot = (uint32_t)((r / LANES_PER_128B) & ROT_MASK);
+        const uint32_t pk_saddr = smem_u32(sPk) + (uint32_t)r * W;
+        const uint32_t b_saddr = smem_u32(sB) + (uint32_t)r * 128u;
+        const uint32_t r7 = (uint32_t)(r & 7);
+        const uint32_t b_full_remote = (CG == 2) ? mapa_shared(smem_u32(&b_full[0]), 0) : 0u;
+        const int mword = (int)rank * 4 + rgrp;   // this row group's word of the tile's mask
+        uint32_t g = 0;
+        for (uint32_t i = 0; i < my_tiles; ++i) {
+            const int s = i % kMmaPkStages;
+            mbar_wait(&pk_full[s], (i / kMmaPkStages) & 1);
+            const uint32_t* m = sMask + s * 2 * MW;
+            uint32_t wv = m[mword];
+            if (has_filter) wv &= m[MW + mword];
+            const uint32_t keep = ((wv >> lane) & 1u) ? 0xFFFFFFFFu : 0u;
+#pragma unroll
+            for (int j = 0; j < SLABS; ++j, ++g) {
+                const uint32_t st = g % kMmaBStages;
+                const uint4 x = lds128(pk_saddr + (uint32_t)s * Cfg::PK_BYTES + (((uint32_t)j ^ rot) << 4));
+                if (g >= (uint32_t)kMmaBStages) mbar_wait(&b_empty[st], ((g / kMmaBStages) - 1) & 1);
+                const uint32_t row_saddr = b_saddr + st * kMmaSlabBytes;
+                if (half == 0)
+                    expand_chunks<0, 4>(x, keep, row_saddr, r7);
+                else
+                    expand_chunks<4, 4>(x, keep, row_saddr, r7);
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) {
+                    if constexpr (CG == 2) mbar_arrive_cluster(b_full_remote + st * 8u);
+                    else mbar_arrive(&b_full[st]);
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&pk_empty[s]);
+        }
+    }
+
+    // ---- teardown: every tcgen05 operation has completed once the epilogues are through ----
+    tc_fence_before();
+    if constexpr (CG == 2) cluster_sync_all(); else __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc<CG>(tmem_base, (uint32_t)Cfg::TMEM_COLS);
+    }
+}
+
+}  // namespace vl

@@ -103,7 +103,84 @@ int launch_scan_wm(vl_corpus* c, ScanParams& p, int nq, int k, ScanPlan* plan, b
     return launch_scan_cfg<W, METRIC, 8, 8, 1>(c, p, nq, k, plan, dry);
 }
 
+// ---- tensor-core scan (mmascan.cuh) ----------------------------------------------
+
+// smallest batch the tensor-core scan takes in automatic mode (tuning override: VLITE_B200_MMA_MINQ;
+// a value <= 0 disables the path)
+int mma_min_q() {
+    static int v = [] {
+        const char* e = getenv("VLITE_B200_MMA_MINQ");
+        return e ? atoi(e) : 64;
+    }();
+    return v;
+}
+
+// 0 = not eligible, 1 = one CTA per query tile, 2 = CTA pairs (cta_group::2)
+int mma_path_for(const vl_corpus* c, const ScanParams& p, int nq, int k, int metric) {
+    if (metric != VL_METRIC_HAMMING || p.cur_score != nullptr) return 0;
+    const bool collect = p.collect_thr != nullptr;
+    if (!collect && k > kMmaListCap) return 0;
+    if (c->scan_path == 1) return 0;
+    if (c->scan_path == 2) return 1;
+    if (c->scan_path == 3) return 2;
+    const int mq = mma_min_q();
+    if (mq <= 0 || nq < mq) return 0;
+    return nq > kMmaQT ? 2 : 1;
+}
+
+template <int W, int CG, bool COLLECT>
+int launch_mma_cfg(vl_corpus* c, ScanParams& p, int nq, int k, ScanPlan* plan_out, bool dry) {
+    using Cfg = MmaCfg<W, CG>;
+    auto kern = mma_scan_kernel<W, CG, COLLECT>;
+    const uint32_t all_tiles = (uint32_t)((p.n_rows + Cfg::NT - 1) / Cfg::NT);
+    p.n_tiles = (all_tiles + p.tile_stride - 1) / p.tile_stride;
+    const int T = (nq + kMmaQT * CG - 1) / (kMmaQT * CG);   // clusters along the queries
+    const long slots = std::max(1, c->sms / CG);             // clusters resident at once (one CTA per SM)
+    long S = c->tune_splits > 0 ? c->tune_splits : std::max<long>(1, slots / T);
+    S = std::min<long>(S, std::max<long>(1, p.n_tiles));
+    S = std::min<long>(S, 65535);
+    const size_t smem = Cfg::SMEM;
+    if (plan_out) *plan_out = ScanPlan{0, 0, 1, kMmaQT * CG, T, (int)S, kMmaBStages, 1, smem};
+    if (dry) return VL_OK;
+    TRY(allow_max_smem(kern, c->device));
+    CUtensorMap tmap;
+    TRY(make_corpus_tmap(c, &tmap, kMmaRows));
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)(T * CG), (unsigned)S);
+    cfg.blockDim = dim3(kMmaThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = c->stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = CG;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = CG == 2 ? 1 : 0;
+    CU(cudaLaunchKernelEx(&cfg, kern, tmap, p));
+    LAUNCHED();
+    return VL_OK;
+}
+
+template <int W>
+int launch_mma_w(vl_corpus* c, ScanParams& p, int nq, int k, int cg, ScanPlan* plan, bool dry) {
+    const bool collect = p.collect_thr != nullptr;
+    if (cg == 2)
+        return collect ? launch_mma_cfg<W, 2, true>(c, p, nq, k, plan, dry)
+                       : launch_mma_cfg<W, 2, false>(c, p, nq, k, plan, dry);
+    return collect ? launch_mma_cfg<W, 1, true>(c, p, nq, k, plan, dry)
+                   : launch_mma_cfg<W, 1, false>(c, p, nq, k, plan, dry);
+}
+
 int launch_scan(vl_corpus* c, ScanParams& p, int nq, int k, int metric, ScanPlan* plan, bool dry) {
+    if (const int cg = mma_path_for(c, p, nq, k, metric)) {
+        switch (c->w) {
+            case 32: return launch_mma_w<32>(c, p, nq, k, cg, plan, dry);
+            case 64: return launch_mma_w<64>(c, p, nq, k, cg, plan, dry);
+            case 128: return launch_mma_w<128>(c, p, nq, k, cg, plan, dry);
+            default: break;
+        }
+    }
 #define VL_W(Wv)                                                                          \
     case Wv:                                                                              \
         return metric == VL_METRIC_HAMMING ? launch_scan_wm<Wv, kHamming>(c, p, nq, k, plan, dry) \
