@@ -378,6 +378,13 @@ mma_scan_kernel(const __grid_constant__ CUtensorMap tmap, const ScanParams p) {
                 }
                 tau_pref = __ldcg(tau_ptr);
             }
+            // this tile's eligibility bits (live & filter), one word per lane: fetched before the wait so
+            // that the rare path below never touches memory
+            uint32_t vw = 0;
+            if (lane < MW) {
+                vw = __ldg(p.live + (size_t)t * MW + lane);
+                if (has_filter) vw &= __ldg(p.filter + (size_t)t * MW + lane);
+            }
             mbar_wait(&acc_full[buf], (i >> 1) & 1);
             tc_fence_after();
 #pragma unroll 1
@@ -402,40 +409,46 @@ mma_scan_kernel(const __grid_constant__ CUtensorMap tmap, const ScanParams p) {
 #pragma unroll
                 for (int c = 1; c < 32; c += 2) m = max(m, max(v[c], (c + 1 < 32) ? v[c + 1] : v[c]));
                 if (!__any_sync(kFullMask, m > thrd)) continue;
-                // ---- rare: some thread of the warp has a candidate among these 32 rows ----
-                int limit = -1;
-                while (true) {
-                    int pc = 64, pv = 0;
+                // ---- rare: some thread of the warp has a candidate among these 32 rows.  Candidates
+                // are taken in ascending row order (so an equal score never displaces an earlier row);
+                // every thread works on its own query, the warp only votes on "anything left". ----
+                uint32_t hm = 0;
 #pragma unroll
-                    for (int c = 31; c >= 0; --c)
-                        if (c > limit && v[c] > thrd) {
-                            pc = c;
-                            pv = v[c];
-                        }
-                    if (!__any_sync(kFullMask, pc < 64)) break;
-                    if (pc < 64) {
-                        limit = pc;
-                        const uint32_t rit = (uint32_t)ch * 32u + (uint32_t)pc;      // row in tile
-                        uint32_t wv = __ldg(p.live + (size_t)t * MW + (rit >> 5));
-                        if (has_filter) wv &= __ldg(p.filter + (size_t)t * MW + (rit >> 5));
-                        if ((wv >> (rit & 31)) & 1u) {
-                            const uint32_t score = (uint32_t)(K - pv) >> 1;
-                            const uint32_t lrow = t * (uint32_t)NT + rit;
-                            const uint64_t key = ((uint64_t)score << 32) | lrow;
-                            if constexpr (COLLECT) {
-                                const uint32_t slot = atomicAdd(p.collect_count + qg, 1u);
-                                if (slot < p.collect_cap) p.collect_keys[(size_t)qg * p.collect_cap + slot] = key;
-                            } else {
-                                // drop kk[0] (the worst), slide `key` into the descending list
+                for (int c = 0; c < 32; ++c) hm |= (v[c] > thrd) ? (1u << c) : 0u;
+                while (__any_sync(kFullMask, hm != 0u)) {
+                    const bool mine = hm != 0u;
+                    const int pc = mine ? __ffs(hm) - 1 : 0;
+                    hm &= hm - 1u;
+                    // v[pc] without dynamic register indexing: a 5-level select tree
+                    int s16[16], s8[8], s4[4], s2[2];
 #pragma unroll
-                                for (int e = 0; e < kMmaListCap; ++e) {
-                                    const uint64_t nxt = (e + 1 < kMmaListCap) ? kk[e + 1] : 0ull;
-                                    kk[e] = (nxt > key) ? nxt : ((kk[e] > key) ? key : kk[e]);
-                                }
-                                thr = (uint32_t)(kk[0] >> 32);
-                                thrd = to_dot(thr);
-                                dirty = true;
+                    for (int e = 0; e < 16; ++e) s16[e] = (pc & 16) ? v[e + 16] : v[e];
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) s8[e] = (pc & 8) ? s16[e + 8] : s16[e];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) s4[e] = (pc & 4) ? s8[e + 4] : s8[e];
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) s2[e] = (pc & 2) ? s4[e + 2] : s4[e];
+                    const int pv = (pc & 1) ? s2[1] : s2[0];
+                    const uint32_t rit = (uint32_t)ch * 32u + (uint32_t)pc;      // row in tile
+                    const uint32_t wv = __shfl_sync(kFullMask, vw, (int)(rit >> 5));
+                    if (mine && pv > thrd && ((wv >> (rit & 31)) & 1u)) {
+                        const uint32_t score = (uint32_t)(K - pv) >> 1;
+                        const uint32_t lrow = t * (uint32_t)NT + rit;
+                        const uint64_t key = ((uint64_t)score << 32) | lrow;
+                        if constexpr (COLLECT) {
+                            const uint32_t slot = atomicAdd(p.collect_count + qg, 1u);
+                            if (slot < p.collect_cap) p.collect_keys[(size_t)qg * p.collect_cap + slot] = key;
+                        } else {
+                            // drop kk[0] (the worst), slide `key` into the descending list
+#pragma unroll
+                            for (int e = 0; e < kMmaListCap; ++e) {
+                                const uint64_t nxt = (e + 1 < kMmaListCap) ? kk[e + 1] : 0ull;
+                                kk[e] = (nxt > key) ? nxt : ((kk[e] > key) ? key : kk[e]);
                             }
+                            thr = (uint32_t)(kk[0] >> 32);
+                            thrd = to_dot(thr);
+                            dirty = true;
                         }
                     }
                 }

@@ -276,8 +276,10 @@ int search_lists(vl_corpus* c, ScanParams p, int n_queries, int k, int metric, u
     // tau[Q] | cursor score[Q] | cursor row[Q] | histogram[Q][1056] (k <= 32, not for huge batches)
     // (the histogram is read only by the one-warp-per-query configuration, Q > 32; the shared bound
     // tau only by query tiles of more than two queries: small batches skip both memsets)
-    const bool want_hist = k <= 32 && n_queries > 32 && n_queries <= 16384;
-    const bool want_tau = n_queries > 2;
+    // the tensor-core kernel shares tau at every batch size and never reads the histogram
+    const bool mma = mma_path_for(c, p, n_queries, std::min(k, kWarpListMaxK), metric) != 0;
+    const bool want_hist = !mma && k <= 32 && n_queries > 32 && n_queries <= 16384;
+    const bool want_tau = mma || n_queries > 2;
     const size_t hist_bytes = want_hist ? (size_t)n_queries * kHistWords * 4 : 0;
     TRY(c->cand_buf.ensure((size_t)n_queries * 12 + hist_bytes));
     p.tau = static_cast<uint32_t*>(c->cand_buf.p);
