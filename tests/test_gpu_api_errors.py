@@ -119,3 +119,30 @@ def test_independent_handles_on_concurrent_threads(gpu):
     for t in threads:
         t.join()
     assert not errors, errors
+
+
+def test_rejected_f32_append_leaves_tombstones_alone(gpu):
+    """A vl_corpus_append_f32 that fails validation (VL_ERANGE) appends nothing and must not bring
+    deleted rows back: count, live count and the live mask stay as they were."""
+    from oracle import cscan, search as osearch, synth
+    n, w = 3000, 64
+    rows = synth.corpus_rows(33, 0, n, w)
+    q = synth.uniform_queries(34, 4, w)
+    dead = np.arange(0, n, 7).astype(np.uint64)
+    live = np.ones(n, dtype=bool)
+    live[dead.astype(np.int64)] = False
+    with gpu.Corpus(w) as c:
+        c.append_f32(osearch.to_ref_encoding(rows).astype(np.float32), gpu.SRC_F32_OFFSET)
+        c.tombstone(dead)
+        bad = osearch.to_ref_encoding(rows[:10]).astype(np.float32)
+        bad[3, 5] = 1e6
+        with pytest.raises(gpu.VliteB200Error) as e:
+            c.append_f32(bad, gpu.SRC_F32_OFFSET)
+        assert e.value.code == gpu.ERANGE
+        assert c.rows == n and c.live_rows == n - len(dead)
+        s, r = c.search(q, 10, 0)
+        es, er = cscan.search(q, rows, 10, 0, synth.pack_mask(live))
+        np.testing.assert_array_equal(s, es)
+        np.testing.assert_array_equal(r, er)
+        first = c.append_f32(osearch.to_ref_encoding(rows[:10]).astype(np.float32), gpu.SRC_F32_OFFSET)
+        assert first == n and c.live_rows == n - len(dead) + 10

@@ -439,3 +439,73 @@ def test_other_row_widths_round_trip_through_ctx(gpu, tmp_path, width):
     assert [[int(g[3]) for g in one] for one in got] == [list(map(int, x)) for x in es]
     v.close()
     v2.close()
+
+
+def test_shared_metadata_dict_follows_update_like_reference(gpu, tmp_path):
+    """set_batch without metadatas stores ONE dict for every row (vlite/main.py:249); update() of one
+    id mutates it in place (vlite/main.py:178), so every row matches the new term -- in the
+    in-scan filter as well as in reference filter mode -- until a save/reload separates the dicts."""
+    from vlite_b200 import VLite
+    rows = synth.corpus_rows(90, 0, 40, 64)
+    emb = lambda texts: np.unpackbits(rows[: len(texts)], axis=1).astype(np.float32) * 2 - 1
+    for mode in ("prefilter", "reference"):
+        d = tmp_path / mode
+        v = VLite("shared", ctx_dir=str(d), embedder=emb, filter_mode=mode)
+        v.set_batch([f"t{i}" for i in range(40)], osearch.to_ref_encoding(rows))
+        one = list(v.index.keys())[7][:-2]
+        assert v.update(one, metadata={"tag": "x"})
+        assert all(md == {"tag": "x"} for md in v._metas.values())
+        hits = v.retrieve("q", top_k=40, metadata={"tag": "x"}, top_k_multiplier=40)
+        assert len(hits) == 40                                       # every row carries the term
+        assert len(v.get(where={"tag": "x"})) == 40
+        v.close()
+        v2 = VLite("shared", ctx_dir=str(d), embedder=emb, filter_mode=mode)   # reload: separate dicts,
+        assert len(v2.retrieve("q", top_k=40, metadata={"tag": "x"}, top_k_multiplier=40)) == 40  # same answer
+        assert v2.update(one, metadata={"tag": "y"})
+        assert len(v2.retrieve("q", top_k=40, metadata={"tag": "y"}, top_k_multiplier=40)) == 1
+        v2.close()
+    # a caller-owned dict reused across add() items behaves the same way
+    v = VLite("reuse", ctx_dir=str(tmp_path / "reuse"), embedder=emb)
+    md = {"src": "a"}
+    v.add([{"text": "one", "metadata": md}], item_id="i1")
+    v.add([{"text": "two", "metadata": md}], item_id="i2")
+    v.update("i1", metadata={"src": "b"})
+    assert {h[0] for h in v.retrieve("q", top_k=5, metadata={"src": "b"})} == {"i1_0", "i2_0"}
+    v.close()
+
+
+@pytest.mark.parametrize("width", [32, 128])
+def test_reopen_without_width_adopts_the_files_width(gpu, tmp_path, width):
+    """A width-32/128 collection reopened WITHOUT width=: the row width comes from the CTX header
+    and queries / later add() calls are embedded at that width."""
+    from vlite_b200 import VLite
+    rows = synth.corpus_rows(91, 0, 300, width)
+    full = lambda texts: np.unpackbits(rows[: len(texts)], axis=1).astype(np.float32) * 2 - 1
+    v = VLite("w", ctx_dir=str(tmp_path), embedder=full, width=width, metric="hamming")
+    v.set_batch([f"t{i}" for i in range(300)], osearch.to_ref_encoding(rows))
+    v.close()
+    v2 = VLite("w", ctx_dir=str(tmp_path), embedder=full, metric="hamming")      # no width=
+    assert v2._corpus.width == width and v2.model.binary_dims == width * 8
+    got = v2.retrieve(["a", "b", "c"], top_k=3, return_scores=True)
+    assert [(g[1], int(g[3])) for g in got] == [("t0", 0), ("t1", 0), ("t2", 0)]
+    v2.add("extra", item_id="new")                                                # same width: accepted
+    assert v2.count() == 301
+    v2.close()
+
+
+def test_save_writes_a_zero_row_for_keys_without_a_vector(gpu, golden, tmp_path):
+    """Keys past the stored rows are kept with np.zeros (vlite/main.py:50) and written back as a
+    zero row by the reference's save (vlite/main.py:289-293); so here, instead of refusing."""
+    from vlite_b200 import VLite
+    v = _build(gpu, golden, tmp_path)
+    v._register("ghost_0", "no vector", {"tag": "ghost"}, None)
+    n = v.count()
+    v.save()
+    header, emb_f32, contexts, metadata, _ = octx.read_ctx(str(tmp_path / "contexts" / "golden.ctx"))
+    assert emb_f32.shape[0] == n == len(metadata) == len(contexts)
+    pos = list(metadata.keys()).index("ghost_0")
+    assert not emb_f32[pos].any() and emb_f32[pos - 1].any()
+    v2 = VLite("golden", ctx_dir=str(tmp_path / "contexts"), embedder=bits_embedder(golden["queries"]))
+    assert v2.count() == n and "ghost_0" in v2.index
+    v.close()
+    v2.close()

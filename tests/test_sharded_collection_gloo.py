@@ -130,6 +130,16 @@ def _worker(rank, world, port, tmp, q):
         out["vlite"] = ([(h[1], int(h[3])) for h in hits], [(h[1], int(h[3])) for h in filt_hits], n_del,
                         [(h[1], int(h[3])) for h in after], v.count(),
                         os.path.exists(os.path.join(tmp, "ctx", "shardcol.ctx")))
+        # rank 0 alone writes the file: when that fails, EVERY rank must raise (none may sit in a barrier)
+        if rank == 0:
+            def boom(name):
+                raise OSError("disk full")
+            v.ctx.create = boom
+        try:
+            v.save()
+            out["save_err"] = None
+        except Exception as e:          # noqa: BLE001
+            out["save_err"] = f"{type(e).__name__}: {e}"
         q.put((rank, out, full, valid, filt, queries, qv))
     finally:
         dist.destroy_process_group()
@@ -166,3 +176,5 @@ def test_sharded_collection_matches_single_shard(world, tmp_path):
     assert [h[1] for h in hits] == [m[0] for m in merged]
     assert all(t.startswith("u") for t, _ in filt_hits) and len(filt_hits) == 4
     assert n_del == 1 and count == 299 and saved
+    for rank, out, *_ in got:
+        assert out["save_err"] is not None and "disk full" in out["save_err"], (rank, out["save_err"])

@@ -168,19 +168,10 @@ extern "C" int vl_corpus_append_f32(vl_corpus* c, const float* vals_any, uint64_
             TRY(repack_rows(c, static_cast<const float*>(sb.p), first + done, m, src_kind));
         }
     }
+    // validate BEFORE the rows go live (like vl_corpus_load_file): on a bad value nothing was
+    // appended -- count, live mask and every tombstone stay exactly as they were
+    TRY(check_err_flag(c, "vl_corpus_append_f32"));
     TRY(mark_appended(c, first, n));
-    int rc = check_err_flag(c, "vl_corpus_append_f32");
-    if (rc != VL_OK) {  // roll the append back
-        c->count = first;
-        c->live_count -= n;
-        cudaMemsetAsync(c->live, 0, c->capacity / 8, c->stream);  // conservative: rebuild below
-        if (first) {
-            live_set_range_kernel<<<grid_for(first / 32 + 1, 256, c->sms), 256, 0, c->stream>>>(c->live, 0, first);
-            g_launches.fetch_add(1);
-        }
-        cudaStreamSynchronize(c->stream);
-        return fail(VL_ERANGE, "vl_corpus_append_f32: a stored value is outside the encoding (tombstones were reset)");
-    }
     return VL_OK;
 }
 

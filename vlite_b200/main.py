@@ -160,9 +160,17 @@ class VLite:
         """fresh item ids (uuid4 like vlite/main.py:76, :261)"""
         return [str(uuid4()) for _ in range(n)]
 
+    def _adopt_width(self, width: int):
+        """The collection's row width is fixed by its first vectors (or its file): queries and later
+        add() calls must be embedded at the same width (the reference hard-codes 512 bits,
+        vlite/model.py:39; here width=32/128 collections reopen without repeating ``width=``)."""
+        self._width = self._width or width
+        if getattr(self.model, "binary_dims", None) != self._width * 8:
+            self.model.binary_dims = self._width * 8
+
     def _ensure_corpus(self, width: int):
         if self._corpus is None:
-            self._width = self._width or width
+            self._adopt_width(width)
             if self.gpus and len(self.gpus) > 1:
                 from .sharded import LocalShardedCorpus
                 self._corpus = LocalShardedCorpus(self._width, self.gpus)
@@ -319,7 +327,9 @@ class VLite:
     def _search(self, queries_u8, k, mask=None):
         if self._corpus is None or self._corpus.live_rows == 0 or queries_u8.shape[1] != self._corpus.width:
             raise ValueError("No valid binary vectors found for comparison.")     # main.py:149
-        k = max(1, min(int(k), _capi.MAX_K))
+        k = max(1, min(int(k), int(self._corpus.live_rows)))          # vlite/model.py:84
+        if k > _capi.MAX_K:
+            raise ValueError(f"top_k={k} exceeds the device top-k limit VL_MAX_K={_capi.MAX_K}")
         scores, rows = self._corpus.search(queries_u8, k, self.metric, mask)
         return scores, rows
 
@@ -414,8 +424,14 @@ class VLite:
         if not chunk_ids:
             return False
         if metadata is not None:
-            # chunks of one add() share a metadata dict: read every old value before changing any
-            for cid in chunk_ids:
+            # Metadata dicts can be SHARED: by the chunks of one add() (vlite/main.py:83), by every
+            # row of a set_batch without metadatas (``[{}] * n``, vlite/main.py:249) or by a caller
+            # that reuses one dict.  The reference mutates the shared object in place
+            # (vlite/main.py:178), so every chunk holding it changes: the bitmap index must follow all
+            # of them, not only this id's rows.  Read every old value before changing any.
+            touched = [self._metas[cid] for cid in chunk_ids]      # (`id` is a parameter here)
+            sharers = [cid for cid, md in self._metas.items() if any(md is t for t in touched)]
+            for cid in sharers:
                 row = self._row_of[cid]
                 if row is not None:
                     replaced = {k: self._metas[cid][k] for k in metadata if k in self._metas[cid]}
@@ -489,7 +505,7 @@ class VLite:
         if not isinstance(texts, list):
             texts = [texts]
         if metadatas is None:
-            metadatas = [{}] * len(texts)
+            metadatas = [{}] * len(texts)      # ONE shared dict, like vlite/main.py:249 (see update())
         elif not isinstance(metadatas, list):
             metadatas = [metadatas]
         if len(texts) != len(embeddings):
@@ -518,12 +534,13 @@ class VLite:
         width = self._width or 64
         keys = list(self._row_of.keys())
         rows = [self._row_of[k] for k in keys]
-        if keys and any(r is None for r in rows):
-            raise ValueError("cannot save: some chunks have no stored vector")
+        # a key without a stored vector (the file held fewer rows than keys) is kept by the reference
+        # as np.zeros(dimension) (vlite/main.py:50) and saved as such (:289-293): write a zero row
+        no_vec = [r is None for r in rows]
         compact = self.ctx_dtype == "ubinary"
         per_file = max(1, min(self.max_rows_per_file, ((1 << 32) - 1) // (width * (1 if compact else 4))))
         n_parts = max(1, -(-len(keys) // per_file))
-        if _all_rows is None and keys:
+        if _all_rows is None and keys and self._corpus is not None and self._corpus.rows:
             _all_rows = self._corpus.read()                                  # one D2H copy
         all_rows = _all_rows
         for part in range(n_parts):
@@ -536,11 +553,20 @@ class VLite:
                 cf.header["part"] = part
             lo, hi = part * per_file, min(len(keys), (part + 1) * per_file)
             if hi > lo:
-                sel = np.asarray(rows[lo:hi])
-                if compact:
-                    cf.set_embeddings_array(all_rows[sel])
+                missing = np.asarray(no_vec[lo:hi])
+                sel = np.asarray([0 if r is None else r for r in rows[lo:hi]], dtype=np.int64)
+                if all_rows is None:                                         # no row has a vector
+                    block = np.zeros((hi - lo, width), dtype=np.uint8)
                 else:
-                    cf.set_embeddings_array(to_reference_encoding(all_rows[sel]).astype(np.float32))
+                    block = all_rows[sel]
+                if compact:
+                    block = block.copy() if missing.any() else block
+                    block[missing] = 0
+                    cf.set_embeddings_array(block)
+                else:
+                    vals = to_reference_encoding(block).astype(np.float32)
+                    vals[missing] = 0.0
+                    cf.set_embeddings_array(vals)
             for k in keys[lo:hi]:
                 cf.add_context(self._texts[k])
                 cf.add_metadata(k, self._metas[k])
@@ -621,7 +647,7 @@ class ShardedVLite(VLite):
     def _ensure_corpus(self, width: int):
         if self._corpus is None:
             from .sharded import ShardedCorpus
-            self._width = self._width or width
+            self._adopt_width(width)
             backend = self._backend_factory(self._width) if self._backend_factory else None
             self._corpus = ShardedCorpus(self._width, device=self.gpu_index, group=self._group, backend=backend)
         return self._corpus
@@ -630,21 +656,34 @@ class ShardedVLite(VLite):
         import torch.distributed as dist
         rows = self._corpus.read() if (self._corpus is not None and self._row_of) else None   # collective
         rank = dist.get_rank(self._group) if dist.is_initialized() else 0
+        self._rank0_then_all(lambda: VLite.save(self, _all_rows=rows), rank)
+
+    def _rank0_then_all(self, fn, rank):
+        """Run ``fn`` on rank 0 only; its outcome is broadcast so that a failure (I/O error, bad
+        value) raises on EVERY rank instead of leaving the others waiting in a barrier."""
+        import torch.distributed as dist
+        err = None
         if rank == 0:
-            super().save(_all_rows=rows)
-        if dist.is_initialized():
-            dist.barrier(group=self._group)
+            try:
+                fn()
+            except Exception as e:            # noqa: BLE001 -- re-raised below on every rank
+                err = e
+        if dist.is_initialized() and dist.get_world_size(self._group) > 1:
+            box = [None if err is None else f"{type(err).__name__}: {err}"]
+            dist.broadcast_object_list(box, src=dist.get_global_rank(self._group, 0) if self._group else 0,
+                                       group=self._group)
+            if box[0] is not None and err is None:
+                err = RuntimeError(f"rank 0 failed: {box[0]}")
+        if err is not None:
+            raise err
 
     def clear(self):
         import torch.distributed as dist
         rank = dist.get_rank(self._group) if dist.is_initialized() else 0
-        if rank == 0:
-            super().clear()
-        else:
+        if rank != 0:
             if self._corpus is not None:
                 self._corpus.clear()
             for d in (self._row_of, self._texts, self._metas, self._extra, self._meta_index, self._by_prefix):
                 d.clear()
             self._ids.clear()
-        if dist.is_initialized():
-            dist.barrier(group=self._group)
+        self._rank0_then_all(lambda: VLite.clear(self), rank)

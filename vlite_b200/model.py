@@ -147,6 +147,8 @@ class EmbeddingModel:
         k = min(int(top_k), n)                                  # vlite/model.py:84
         if k <= 0:
             return np.zeros(0, dtype=np.int64), np.zeros(0, dtype=np.int64)
+        if k > _capi.MAX_K:
+            raise ValueError(f"top_k={k} exceeds the device top-k limit VL_MAX_K={_capi.MAX_K}")
         with _capi.Corpus(w, device=self.gpu_index, capacity_rows=n) as c:
             if e.dtype == np.uint8:
                 c.append(e)
