@@ -19,10 +19,9 @@
  *     the same contract the reference's single mutable VLite object has
  *     (vlite/server.py:14).  When every pointer passed to a call is device
  *     memory the call only ENQUEUES work on the handle's stream and returns
- *     without synchronising (exception: vl_search with k > 32 waits for its
- *     own kernels, because it checks a device flag to decide whether the exact
- *     fallback pass is needed); with any host pointer it returns after the
- *     data has landed.
+ *     without synchronising -- for every k: the exact fallback pass of k > 32
+ *     is enqueued behind a device-side gate instead of being decided by a host
+ *     read-back; with any host pointer it returns after the data has landed.
  *   - results are ordered ascending by (score, global row); slots past the
  *     number of eligible rows hold VL_SENTINEL_SCORE / VL_SENTINEL_ROW.
  *   - there is NO CPU fallback: without a usable sm_100 device every compute

@@ -321,3 +321,42 @@ def test_very_large_query_batch(gpu):
         c.append(corpus)
         for metric, k in ((HAMMING, 5), (XORSUM, 32)):
             _check(c, corpus, queries, k, metric)
+
+
+@pytest.mark.parametrize("period", [0, 700])
+@pytest.mark.parametrize("nq,path", [(5, 0), (130, 0), (130, 1)])
+def test_large_k_is_enqueue_only_graph_capturable(gpu, period, nq, path):
+    """k > 32 with device pointers only never synchronises with the host: the whole search --
+    sampled pass, collect pass, select, and the exact multi-pass fallback behind its device-side gate
+    (opened here by period=700: mass ties overflow the candidate buffers) -- is captured into a CUDA
+    graph and replayed.  A host read-back inside vl_search would make the capture fail."""
+    import torch
+    n, k, w = 200_000, 100, 128
+    corpus = synth.corpus_rows(11, 0, n, w, period=period)
+    queries = synth.uniform_queries(12, nq, w)
+    es, er = cscan.search(queries, corpus, k, HAMMING)
+    stream = torch.cuda.Stream()
+    with gpu.Corpus(w) as c:
+        c.append(corpus)
+        c.set_scan_path(path)
+        c.set_stream(stream.cuda_stream)
+        dq = torch.from_numpy(queries).cuda()
+        ds = torch.zeros((nq, k), dtype=torch.int32, device="cuda")
+        dr = torch.zeros((nq, k), dtype=torch.int64, device="cuda")
+        torch.cuda.synchronize()
+        c.search(dq, k, HAMMING, None, ds, dr)            # warm-up: scratch buffers get allocated here
+        stream.synchronize()
+        np.testing.assert_array_equal(ds.cpu().numpy().view(np.uint32), es)
+        ds.zero_()
+        dr.zero_()
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=stream, capture_error_mode="thread_local"):
+            c.search(dq, k, HAMMING, None, ds, dr)
+        for _ in range(2):
+            g.replay()
+        torch.cuda.synchronize()
+        np.testing.assert_array_equal(ds.cpu().numpy().view(np.uint32), es)
+        np.testing.assert_array_equal(dr.cpu().numpy().view(np.uint64), er)
+        c.set_stream(None)
+        del g

@@ -67,9 +67,9 @@ extern "C" int vl_corpus_create(int device, int width_bytes, uint64_t capacity_r
         vl_corpus_destroy(c);
         return rc;
     };
-    if (cudaMalloc(&c->d_err, sizeof(int)) != cudaSuccess || cudaMalloc(&c->d_counter, 8) != cudaSuccess)
+    if (cudaMalloc(&c->d_err, 2 * sizeof(int)) != cudaSuccess || cudaMalloc(&c->d_counter, 8) != cudaSuccess)
         return bail(fail(VL_ENOMEM, "cudaMalloc failed"));
-    cudaMemset(c->d_err, 0, sizeof(int));
+    cudaMemset(c->d_err, 0, 2 * sizeof(int));
     cudaMemset(c->d_counter, 0, 8);
     cudaEventCreate(&c->ev0);
     cudaEventCreate(&c->ev1);

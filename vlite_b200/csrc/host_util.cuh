@@ -50,25 +50,34 @@ struct DeviceGuard {
     }
 };
 
+// Grow-only device scratch.  Growing never frees the old block while work that uses it may still
+// be in flight on the handle's stream (cudaFree would synchronise the device -- a latency cliff when
+// a batch grows -- and enqueue-only calls must stay enqueue-only): the old block is retired and
+// freed with the handle.  Growth is geometric below 64 MB, exact above, so retired blocks add up
+// to less than the live one.
 struct DevBuf {
     void* p = nullptr;
     size_t cap = 0;
+    std::vector<void*> retired;
     int ensure(size_t bytes) {
         if (bytes <= cap) return VL_OK;
-        if (p) cudaFree(p);
-        p = nullptr;
-        cap = 0;
         size_t want = std::max(bytes, (size_t)4096);
-        cudaError_t e = cudaMalloc(&p, want);
+        if (want < ((size_t)64 << 20)) want = std::max(want, cap * 2);
+        void* q = nullptr;
+        cudaError_t e = cudaMalloc(&q, want);
         if (e != cudaSuccess) {
             cudaGetLastError();
             return fail(VL_ENOMEM, "cudaMalloc(%zu) failed: %s", want, cudaGetErrorString(e));
         }
+        if (p) retired.push_back(p);
+        p = q;
         cap = want;
         return VL_OK;
     }
     void release() {
         if (p) cudaFree(p);
+        for (void* r : retired) cudaFree(r);
+        retired.clear();
         p = nullptr;
         cap = 0;
     }

@@ -25,7 +25,8 @@ __global__ void extract_thr_kernel(const uint32_t* __restrict__ sample_scores, c
 }
 
 // flags: bit 0 = some buffer overflowed, bit 1 = some buffer holds fewer than k rows although its
-// threshold was finite
+// threshold was finite.  A non-zero *flags opens the gate of the exact multi-pass pass that the host
+// has already enqueued behind this kernel (ScanParams::gate): no host round trip decides it.
 __global__ void __launch_bounds__(kSelectThreads)
 collect_select_kernel(const unsigned long long* __restrict__ keys, const uint32_t* __restrict__ count,
                       const uint32_t* __restrict__ thr, uint32_t cap, int k, uint64_t base_row,

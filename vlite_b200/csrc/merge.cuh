@@ -28,7 +28,8 @@ __global__ void __launch_bounds__(kMergeWarps * 32)
 merge_topk_kernel(const uint32_t* __restrict__ scores, const uint64_t* __restrict__ rows, int n_lists,
                   int n_queries, int k_in, int k_out, uint32_t* __restrict__ out_scores,
                   uint64_t* __restrict__ out_rows, int out_stride, int out_offset, size_t score_list_stride,
-                  size_t row_list_stride, size_t out_group_stride) {
+                  size_t row_list_stride, size_t out_group_stride, const int* __restrict__ gate = nullptr) {
+    if (gate != nullptr && *gate == 0) return;   // device-side gate, see ScanParams::gate
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int q = blockIdx.x * kMergeWarps + warp;
     if (q >= n_queries) return;
@@ -116,7 +117,9 @@ __global__ void map_rows_kernel(uint64_t* __restrict__ rows, uint64_t n, const u
 // cursor for the next pass of a multi-pass (large k) search: the last key already emitted
 __global__ void cursor_update_kernel(const uint32_t* __restrict__ out_scores, const uint64_t* __restrict__ out_rows,
                                      int n_queries, int out_stride, int last_pos, uint64_t base_row,
-                                     uint32_t* __restrict__ cur_score, uint32_t* __restrict__ cur_row) {
+                                     uint32_t* __restrict__ cur_score, uint32_t* __restrict__ cur_row,
+                                     const int* __restrict__ gate = nullptr) {
+    if (gate != nullptr && *gate == 0) return;
     const int q = blockIdx.x * blockDim.x + threadIdx.x;
     if (q >= n_queries) return;
     const uint64_t r = out_rows[(size_t)q * out_stride + last_pos];

@@ -214,6 +214,7 @@ template <int W, int CG, bool COLLECT>
 __global__ void __launch_bounds__(kMmaThreads, 1)
 mma_scan_kernel(const __grid_constant__ CUtensorMap tmap, const ScanParams p) {
     using Cfg = MmaCfg<W, CG>;
+    if (p.gate != nullptr && *p.gate == 0) return;   // uniform over the grid (and over a cluster)
     constexpr int SLABS = Cfg::SLABS, NT = Cfg::NT, MW = Cfg::MW, K = Cfg::K;
     constexpr int CHUNKS = W / 16;
 

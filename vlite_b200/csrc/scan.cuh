@@ -79,6 +79,9 @@ struct ScanParams {
     uint32_t* collect_count;
     uint32_t collect_cap;
     uint32_t one;  // == 1, opaque to ptxas: keeps "acc += popc" on IMAD (FMA pipe) instead of IADD3 (ALU pipe)
+    // optional device-side gate: when set and *gate == 0 the whole launch is a no-op.  Lets the host
+    // ENQUEUE a fallback pass whose need is only known on the device (large k: search_host.cuh).
+    const int* gate;
 };
 
 // ---- warp-wide selection network for k <= 32: keys are (score << 32 | local row), unique per row ----
@@ -244,6 +247,7 @@ template <int W, int METRIC, int C, int WQ, int TPS>
 __global__ void __launch_bounds__(kScanThreads, VL_MINBLOCKS)
 scan_topk_kernel(const __grid_constant__ CUtensorMap tmap, const ScanParams p) {
     using Cfg = ScanCfg<W, C, WQ, TPS>;
+    if (p.gate != nullptr && *p.gate == 0) return;   // uniform over the grid
     constexpr int WR = Cfg::WR, RPW = Cfg::RPW, R = Cfg::R, STEPS = Cfg::STEPS, QT = Cfg::QT;
     constexpr int CHUNKS = Cfg::CHUNKS, TILE_BYTES = Cfg::TILE_BYTES, TR = Cfg::TR, MASKW = Cfg::MASKW;
     static_assert(CHUNKS % 2 == 0, "rows are scored two 16 B chunks at a time");

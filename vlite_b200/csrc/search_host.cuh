@@ -240,7 +240,7 @@ size_t merge_tmp_lists(size_t n_lists) {
 
 int merge_levels(cudaStream_t st, const uint32_t* in_s, const uint64_t* in_r, size_t n_lists, size_t s_stride,
                  size_t r_stride, int n_queries, int k_in, int k_out, uint32_t* out_s, uint64_t* out_r,
-                 int out_stride, int out_offset, uint32_t* tmp_s, uint64_t* tmp_r) {
+                 int out_stride, int out_offset, uint32_t* tmp_s, uint64_t* tmp_r, const int* gate = nullptr) {
     const unsigned gx = (unsigned)((n_queries + kMergeWarps - 1) / kMergeWarps);
     const size_t dense = (size_t)n_queries * k_out;
     while (true) {
@@ -248,12 +248,12 @@ int merge_levels(cudaStream_t st, const uint32_t* in_s, const uint64_t* in_r, si
         if (groups <= 1) {
             merge_topk_kernel<<<dim3(gx, 1), kMergeWarps * 32, 0, st>>>(in_s, in_r, (int)n_lists, n_queries, k_in, k_out,
                                                                       out_s, out_r, out_stride, out_offset, s_stride,
-                                                                      r_stride, 0);
+                                                                      r_stride, 0, gate);
             LAUNCHED();
             return VL_OK;
         }
         merge_topk_kernel<<<dim3(gx, (unsigned)groups), kMergeWarps * 32, 0, st>>>(
-            in_s, in_r, (int)n_lists, n_queries, k_in, k_out, tmp_s, tmp_r, k_out, 0, s_stride, r_stride, dense);
+            in_s, in_r, (int)n_lists, n_queries, k_in, k_out, tmp_s, tmp_r, k_out, 0, s_stride, r_stride, dense, gate);
         LAUNCHED();
         in_s = tmp_s;
         in_r = tmp_r;
@@ -269,7 +269,8 @@ int merge_levels(cudaStream_t st, const uint32_t* in_s, const uint64_t* in_r, si
 // a per-query cursor (exact and deterministic for any tie pattern).  `p` arrives with the corpus,
 // queries and masks filled in.
 int search_lists(vl_corpus* c, ScanParams p, int n_queries, int k, int metric, uint32_t* o_s, uint64_t* o_r,
-                 int out_stride = 0) {
+                 int out_stride = 0, const int* gate = nullptr) {
+    p.gate = gate;
     cudaStream_t st = c->stream;
     if (out_stride == 0) out_stride = k;
     const int n_pass = (k + kWarpListMaxK - 1) / kWarpListMaxK;
@@ -312,13 +313,13 @@ int search_lists(vl_corpus* c, ScanParams p, int n_queries, int k, int metric, u
         if (want_tau) CU(cudaMemsetAsync(p.tau, 0xFF, (size_t)n_queries * 4, st));
         if (p.hist) CU(cudaMemsetAsync(p.hist, 0, hist_bytes, st));
         TRY(launch_scan(c, p, n_queries, k_pass, metric, nullptr, /*dry=*/false));
-        if (c->timing && pass == 0 && p.tile_stride == 1) CU(cudaEventRecord(c->ev1, st));
+        if (c->timing && pass == 0 && p.tile_stride == 1 && gate == nullptr) CU(cudaEventRecord(c->ev1, st));
         TRY(merge_levels(st, p.part_scores, p.part_rows, n_lists, dense, dense, n_queries, k_pass, k_pass, o_s, o_r,
                          out_stride, pass * kWarpListMaxK, p.part_scores + n_lists * dense,
-                         p.part_rows + n_lists * dense));
+                         p.part_rows + n_lists * dense, gate));
         if (pass + 1 < n_pass) {
             cursor_update_kernel<<<(n_queries + 127) / 128, 128, 0, st>>>(
-                o_s, o_r, n_queries, out_stride, pass * kWarpListMaxK + k_pass - 1, c->base_row, cur_s, cur_r);
+                o_s, o_r, n_queries, out_stride, pass * kWarpListMaxK + k_pass - 1, c->base_row, cur_s, cur_r, gate);
             LAUNCHED();
         }
     }
@@ -349,7 +350,9 @@ int search_large_k(vl_corpus* c, ScanParams p, int n_queries, int k, int metric,
     // it visit few tiles; the threshold's relative spread is 1/sqrt(ks) <= 25 %, far inside the margin
     // between the ~3k rows expected at or below it and both failure modes (fewer than k: fallback;
     // more than cap >= 6k: fallback)
-    const int ks = std::min(kLargeKSample, std::max(16, k / 4));
+    // (16 whenever the tensor-core kernel can take the sampled pass: its register lists hold 16)
+    const int ks = mma_path_for(c, p, n_queries, kMmaListCap, metric) ? kMmaListCap
+                                                                     : std::min(kLargeKSample, std::max(16, k / 4));
     // sample every `stride`-th tile: at least 3k expected candidates, and never more than 5 % of a scan
     const uint32_t stride = std::max<uint32_t>(20u, (3u * (uint32_t)k) / (uint32_t)ks);
     TRY(c->lk_keys.ensure(key_bytes));
@@ -358,7 +361,7 @@ int search_large_k(vl_corpus* c, ScanParams p, int n_queries, int k, int metric,
     uint32_t* cnt = thr + n_queries;
     uint64_t* smp_r = reinterpret_cast<uint64_t*>(cnt + n_queries);  // 8*Q bytes in: 8-byte aligned
     uint32_t* smp_s = reinterpret_cast<uint32_t*>(smp_r + (size_t)n_queries * kLargeKSample);
-    int* flags = c->d_err;
+    int* flags = c->d_err + 1;   // the fallback gate (d_err[0] is the repack error flag)
     if (c->count <= cap) {
         // the whole shard fits a buffer: no sampling, collect every eligible row
         CU(cudaMemsetAsync(thr, 0xFF, (size_t)n_queries * 4, st));
@@ -390,13 +393,12 @@ int search_large_k(vl_corpus* c, ScanParams p, int n_queries, int k, int metric,
     collect_select_kernel<<<n_queries, kSelectThreads, smem, st>>>(pc.collect_keys, cnt, thr, cap, k, c->base_row, o_s,
                                                                 o_r, flags);
     LAUNCHED();
-    int h = 0;
-    CU(cudaMemcpyAsync(&h, flags, sizeof h, cudaMemcpyDeviceToHost, st));
-    CU(cudaStreamSynchronize(st));
-    if (h) {
-        CU(cudaMemsetAsync(flags, 0, sizeof(int), st));
-        return VL_OK;  // overflow / shortfall: let the exact multi-pass path answer
-    }
+    // Overflow (mass ties at the threshold) or shortfall is only known on the device: the exact
+    // multi-pass path is ENQUEUED behind the select kernel with its launches gated on the flag word
+    // (every gated kernel returns at once when the flag is 0), then the flag is cleared.  No host
+    // round trip: k > 32 is enqueue-only like k <= 32, so it pipelines and can be graph-captured.
+    TRY(search_lists(c, p, n_queries, k, metric, o_s, o_r, 0, flags));
+    CU(cudaMemsetAsync(flags, 0, sizeof(int), st));
     *done = true;
     return VL_OK;
 }
