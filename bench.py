@@ -1,21 +1,31 @@
 #!/usr/bin/env python
 """bench.py -- the retrieval hot path on N B200s of one node (contract in the task prompt).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--legs a,b,...]
 
-Workload (BASELINE.json configs[1]): a 500k x 128 B synthetic ubinary corpus per GPU shard,
-a batch of 1024 queries, top_k = 10, HAMMING.  A "step" = one vl_search over the shard (N > 1:
-+ the all-gather of the per-shard top-k and the merge).  Row-sharded WEAK scaling: every rank
-holds its own 500k-row shard of an N x 500k corpus, all ranks scan all queries.
+Headline step (BASELINE.json configs[1]): a 500k x 128 B synthetic ubinary corpus per GPU shard, a
+batch of 1024 queries, top_k = 10, HAMMING.  A "step" = one vl_search over the shard (N > 1: + the
+all-gather of the per-shard top-k and the merge).  Row-sharded WEAK scaling: every rank holds its
+own 500k-row shard of an N x 500k corpus, all ranks scan all queries.
 
-``value``  queries/s in 500k-row-corpus equivalents (Q x total_rows / 500k per step), inputs
-           resident in HBM, CUDA events, max over ranks.  At N = 1 this is plain queries/s.
-``e2e``    same metric through the C ABI with HOST buffers (pinned queries in, results out).
-``roofline`` of the scan kernel as north_star defines it: the slower of corpus bytes at HBM
-           bandwidth and popcount work at the INT-pipe (POPC) peak; POPC peak measured live by
-           the library's micro-benchmark, HBM peak from MEASURED_PEAKS.json.
+``value``   queries/s in 500k-row-corpus equivalents (Q x total_rows / 500k per step / time; plain
+            queries/s at N = 1), inputs resident in HBM, CUDA events, max over ranks.  The reference
+            arm reports the SAME unit, so the driver's ratio compares like with like at every N;
+            ``qps_over_whole_corpus`` is the plain queries/s over the N x 500k corpus.
+``e2e``     the same metric through the C ABI with HOST buffers (pinned queries in, results out).
+``roofline`` of the dominant kernel.  Batches of >= 64 queries run on the tensor-core scan
+            (tcgen05.mma kind::i8 on rows expanded bit -> int8 in shared memory): bound "tensor",
+            achieved = 2 N Q 8W int8 ops / kernel time, peak = 2 x the measured bf16 cuBLAS rate of
+            MEASURED_PEAKS.json (int8 issues at twice the bf16 rate on B200).  The north star's own
+            roofline (popcount work at the INT-pipe peak, corpus bytes at HBM bandwidth) is kept
+            beside it as ``north_star_view``; the HBM-bound regime (1-2 queries) is ``roofline_hbm``.
 ``cpu_baseline`` the oracle's torch-op port of the reference's EmbeddingModel.search
-           (vlite/model.py:76-90) timed on this box's host cores on a bounded sample.
+            (vlite/model.py:76-90) timed on ALL of this box's host cores on a bounded sample.
+``legs``    every other BASELINE config as a parity-gated measurement (bench_legs.py): N = 1:
+            cfg1 (VLite.retrieve latency), hbm (1-2 queries over 4 GB), cfg3 (100M rows, 4096 queries,
+            top-1000 -> int8 rescore), cfg5 (filters, streaming add, 4 GiB CTX load); N > 1: hbm (16 GB
+            per GPU: the 1B-vector corpus at 8 GPUs), strong (500k rows split N ways), group (the
+            in-process shard group over the N GPUs, driven by rank 0).
 """
 from __future__ import annotations
 
@@ -32,19 +42,27 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+import bench_legs as legs_mod  # noqa: E402
+
 ROWS_PER_GPU = 500_000
 WIDTH = 128
 N_QUERIES = 1024
 TOP_K = 10
 HBM_FALLBACK_GBS = 6650.0
+BF16_FALLBACK_TFLOPS = 1590.0
+VALUE_DEFINITION = ("Q x total_rows / 500k per step / time: queries/s in 500k-row-corpus equivalents "
+                    "(plain queries/s at N = 1); both arms use this unit")
 
 
 def load_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
         d = json.load(open(path))
-        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
-    return HBM_FALLBACK_GBS, "fallback (B200_PROFILING.md)"
+        return {"hbm": float(d["hbm_gbs"]), "bf16": float(d["bf16_tflops"]),
+                "bf16_sustained": float(d.get("bf16_tflops_sustained", d["bf16_tflops"])),
+                "src": "measured (MEASURED_PEAKS.json)"}
+    return {"hbm": HBM_FALLBACK_GBS, "bf16": BF16_FALLBACK_TFLOPS, "bf16_sustained": 1400.0,
+            "src": "fallback (B200_PROFILING.md)"}
 
 
 class ClockSampler:
@@ -129,8 +147,8 @@ def make_queries(n_rows_total: int, nq: int, width: int):
 # ------------------------------------------------------------------------------------------
 def time_reference(steps, warmup: int, budget_s: float = 150.0, target_s: float = 15.0):
     """steps=None: as many one-query calls as fit ~target_s seconds of CPU work (6..1024)."""
-    import torch
     from oracle import ref_port, synth
+    cores = legs_mod.use_all_host_cores()        # torchrun sets OMP_NUM_THREADS=1: undo it for the CPU arm
     rows = ROWS_PER_GPU
     queries = make_queries(rows, 8, WIDTH)
     # probe on 50k rows to size the per-step sample so that steps+warmup fit the budget
@@ -158,8 +176,9 @@ def time_reference(steps, warmup: int, budget_s: float = 150.0, target_s: float 
     qps = (1.0 / dt) * (n_sample / rows)                  # search cost is linear in N
     sample = (f"{steps} sequential EmbeddingModel.search calls (1 query, k={TOP_K}) over "
               f"{n_sample} of the {rows} x {WIDTH} B rows held as float32"
-              + ("" if n_sample == rows else "; q/s scaled linearly to the full corpus"))
-    return qps, dt * 1e3, torch.get_num_threads(), sample
+              + ("" if n_sample == rows else "; q/s scaled linearly to the full corpus")
+              + "; q/s per 500k rows (= 500k-row-corpus equivalents at any shard count: the search is linear in rows)")
+    return qps, dt * 1e3, cores, sample
 
 
 def run_reference(args):
@@ -172,20 +191,27 @@ def run_reference(args):
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32 (via float32 storage)",
         "data": "synthetic",
-        "config": workload_config(args.gpus),
+        "config": workload_config(args.gpus, reference=True),
         "cpu_baseline": {"value": qps, "unit": "queries/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": qps, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
+        "value_definition": VALUE_DEFINITION,
+        "qps_over_whole_corpus": qps / max(1, args.gpus),
     }
+    if not args.no_legs:
+        # BASELINE configs[0] as the reference pays for it: dict rebuild + search, reported separately
+        line["cfg1_reference_port"] = legs_mod.cfg1_reference_port()
     print(json.dumps(line), flush=True)
 
 
-def workload_config(n_gpus: int):
+def workload_config(n_gpus: int, reference: bool = False):
     return {
         "workload": (f"BASELINE configs[1]: {ROWS_PER_GPU} x {WIDTH} B ubinary rows per GPU shard "
                      f"({n_gpus} shard(s), row-sharded), batch of {N_QUERIES} queries, top_k={TOP_K}, HAMMING"),
         "rows_per_gpu": ROWS_PER_GPU, "width_bytes": WIDTH, "queries": N_QUERIES, "top_k": TOP_K,
-        "metric_fn": "hamming", "parallelism": f"row-shard x{n_gpus}",
+        # the reference's live score is the XOR-sum of byte values (vlite/model.py:82); ours is timed on
+        # true Hamming, the north-star metric (same memory traffic; our XOR-sum time is under extra)
+        "metric_fn": "xorsum" if reference else "hamming", "parallelism": f"row-shard x{n_gpus}",
         "l2": "corpus (64 MB) fits L2: a 256 MB buffer is overwritten between timed iterations (L2 flush)",
     }
 
@@ -207,15 +233,18 @@ def run_ours(args):
         raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    cpu_group = None
     if world > 1:
         # keep stdout to the one JSON line: NCCL_DEBUG=VERSION (set in some images) prints a banner
         if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
             os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=dev)
+        cpu_group = dist.new_group(backend="gloo")      # host-side waits that put no kernel on the GPUs
     _capi.load()
     if _capi.device_count() < 1:
         raise SystemExit("no sm_100 device: vlite_b200 has no CPU fallback")
-    hbm_peak, hbm_src = load_peaks()
+    peaks = load_peaks()
+    hbm_peak = peaks["hbm"]
 
     rows, w, nq, k = ROWS_PER_GPU, WIDTH, N_QUERIES, TOP_K
     total_rows = rows * world
@@ -232,7 +261,7 @@ def run_ours(args):
     got_s = out_s.cpu().numpy().view(np.uint32)
     got_r = out_r.cpu().numpy().view(np.uint64)
     if rank == 0:
-        sub = np.r_[0:8, nq - 8:nq]
+        sub = np.r_[0:16, nq - 16:nq]
         host_rows = np.concatenate([synth.corpus_rows(0, g * rows, rows, w) for g in range(world)])
         es, er = cscan.search(queries[sub], host_rows, k, _capi.HAMMING)
         if not (np.array_equal(got_s[sub], es) and np.array_equal(got_r[sub], er)):
@@ -311,127 +340,162 @@ def run_ours(args):
     e2e_ms = float(e2e_total.item()) / args.steps * 1e3
     e2e_value = nq * world / (e2e_ms * 1e-3)
 
-    # ---- roofline of the scan kernel ----
+    # ---- roofline of the dominant kernel (the tensor-core scan at this batch size) ----
     scan_avg_ms = float(np.mean(scan_ms))
     popc_peak, _ = _capi.microbench(0, 8192, device=local_rank)           # lane-POPC/s, measured live
     alg_bytes = rows * w + rows / 8 + nq * w + nq * k * 12
     alg_popc = rows * nq * (w / 4)
+    alg_int8_ops = 2.0 * rows * nq * (w * 8)
     t_hbm = alg_bytes / (hbm_peak * 1e9)
     t_int = alg_popc / popc_peak
-    t_roof = max(t_hbm, t_int)
-    traffic, pipes = None, None
+    int8_peak = 2.0 * peaks["bf16"]                                        # TOP/s
+    traffic, traffic_src, pipes = None, None, None
     tpath = os.path.join(ROOT, "profiles", "traffic_cfg2.json")
-    if os.path.exists(tpath):       # from the committed ncu --set full capture of this same kernel and workload
+    if os.path.exists(tpath):       # a STATIC number: read from the committed ncu --set full capture of this kernel + workload
         tj = json.load(open(tpath))
         traffic = tj.get("dram_bytes_per_launch")
-        pipes = {k: tj[k] for k in ("alu_pipe_pct", "xu_pipe_pct", "fma_pipe_pct", "issue_slots_pct") if k in tj}
+        traffic_src = f"not measured in this run: committed ncu capture profiles/{tj.get('source', '?')} of the same kernel and workload"
+        pipes = {kk: tj[kk] for kk in ("tensor_pipe_pct", "alu_pipe_pct", "xu_pipe_pct", "fma_pipe_pct", "issue_slots_pct") if kk in tj}
+    achieved_tops = alg_int8_ops / (scan_avg_ms * 1e-3) / 1e12
     roofline = {
-        "bound": "int_pipe" if t_int >= t_hbm else "hbm",
-        "achieved": alg_popc / (scan_avg_ms * 1e-3) / 1e12, "peak": popc_peak / 1e12, "unit": "TPOPC/s",
-        "frac": t_roof / (scan_avg_ms * 1e-3), "traffic": traffic, "int_pipe_utilisation_ncu": pipes,
-        "kernel": "scan_topk_kernel<128,HAMMING,8,8>", "kernel_ms": scan_avg_ms,
-        "algorithmic": {"bytes_per_launch": alg_bytes, "popc_per_launch": alg_popc,
-                        "per_unit": "W bytes and W/4 32-bit POPC per (query,row) pair; W=128"},
-        "peak_source": "POPC: vl_microbench live in this run; HBM: " + hbm_src,
-        "note": ("frac > 1 is expected: carry-save adders turn 32 algorithmic POPC per pair into 16 issued "
-                 "POPC + 64 LOP3, so the kernel beats the plain-POPC pipe bound"),
+        "bound": "tensor", "achieved": achieved_tops, "peak": int8_peak, "unit": "TFLOP/s",
+        "frac": achieved_tops / int8_peak, "traffic": traffic, "traffic_source": traffic_src,
+        "pipe_utilisation_ncu": pipes,
+        "kernel": "mma_scan_kernel<W=128, CG=2, lists> (tcgen05.mma.cta_group::2.kind::i8, TMEM accumulators)",
+        "kernel_ms": scan_avg_ms,
+        "algorithmic": {"int8_ops_per_launch": alg_int8_ops, "bytes_per_launch": alg_bytes, "popc_per_launch": alg_popc,
+                        "per_unit": "per (query,row) pair at W=128: 1024 int8 MAC = 2048 ops (tensor view), "
+                                    "32 32-bit POPC (north-star INT view), W = 128 corpus bytes per row once per batch"},
+        "peak_source": ("int8 dense = 2 x bf16: 2 x " + f"{peaks['bf16']:.1f}" + " TFLOP/s cuBLAS bf16 burst, " + peaks["src"] +
+                        "; the unit is int8 TOP/s (integer ops, exact s32 accumulation)"),
+        "north_star_view": {"bound": "int_pipe" if t_int >= t_hbm else "hbm",
+                            "achieved": alg_popc / (scan_avg_ms * 1e-3) / 1e12, "peak": popc_peak / 1e12, "unit": "TPOPC/s",
+                            "frac": max(t_hbm, t_int) / (scan_avg_ms * 1e-3),
+                            "note": "north_star's roofline = slower of corpus bytes at HBM bandwidth and popcount work at "
+                                    "the INT-pipe peak (POPC peak: vl_microbench live in this run).  frac >> 1 because the "
+                                    "popcount work runs on the tensor pipe as an exact int8 contraction instead"},
         "hbm_view": {"achieved": rows * w / (scan_avg_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
                      "frac": rows * w / (scan_avg_ms * 1e-3) / 1e9 / hbm_peak},
     }
 
+    ctx = {"torch": torch, "dist": dist, "capi": _capi, "world": world, "rank": rank, "local_rank": local_rank,
+           "dev": dev, "hbm_peak": hbm_peak, "barrier": barrier, "flush": flush, "no_cpu": args.no_cpu}
+    default_legs = ["extra", "hbm", "cfg1", "cfg3", "cfg5"] if world == 1 else ["hbm", "strong", "group"]
+    want = default_legs if args.legs == "default" else [x for x in args.legs.split(",") if x]
+    if args.no_legs:
+        want = []
+    legs, failed = {}, []
+
+    def run_leg(name, fn, collective=True):
+        """collective legs run on every rank; a gate failure anywhere fails the leg everywhere"""
+        t0 = time.perf_counter()
+        err = None
+        try:
+            res = fn()
+        except legs_mod.GateError as e:
+            res, err = None, f"GATE FAILED: {e}"
+        except Exception as e:            # noqa: BLE001 -- a broken leg must not take the headline down with it
+            res, err = None, f"{type(e).__name__}: {e}"
+        if world > 1 and collective:
+            flag = torch.tensor([1 if err else 0], dtype=torch.int32, device=dev)
+            dist.all_reduce(flag, op=dist.ReduceOp.MAX)
+            if int(flag.item()) and not err:
+                err = "failed on another rank"
+        if err:
+            failed.append(name)
+            legs[name] = {"error": err}
+        else:
+            legs[name] = res
+        legs[name]["leg_seconds"] = time.perf_counter() - t0
+        torch.cuda.empty_cache()
+
     extra = {}
-    cpu_baseline = None
-    if world > 1:
-        # HBM-bound leg of the sharded path: 1 and 2 queries over 16 GB per GPU (scan + all-gather + merge),
-        # i.e. BASELINE's "scanned corpus GB/s vs HBM roofline" at this GPU count; at 8 GPUs this is the
-        # north star's 1B-vector corpus (configs[3])
-        big = 125_000_000
-        with _capi.Corpus(w, device=local_rank, capacity_rows=big, base_row=rank * big) as cb:
-            cb.set_stream(torch.cuda.current_stream().cuda_stream)
-            cb.fill_synthetic(0, 0, big)
-            sb = ShardedSearcher(cb)
-            for q_small in (1, 2):
-                tt = []
-                for i in range(6):
-                    barrier()
-                    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                    a.record()
-                    sb.search(dq[:q_small], k, _capi.HAMMING)
-                    b.record()
-                    b.synchronize()
-                    if i >= 2:
-                        tt.append(a.elapsed_time(b))
-                t_leg = torch.tensor([float(np.mean(tt))], dtype=torch.float64, device=dev)
-                dist.all_reduce(t_leg, op=dist.ReduceOp.MAX)
-                agg = world * big * w / (float(t_leg.item()) * 1e-3) / 1e9
-                extra[f"hbm_leg_q{q_small}"] = {
-                    "rows_total": big * world, "corpus_GB_total": world * big * w / 1e9,
-                    "step_ms_max_over_ranks": float(t_leg.item()), "aggregate_GBps": agg,
-                    "hbm_frac_of_aggregate": agg / (world * hbm_peak),
-                    "qps": q_small / (float(t_leg.item()) * 1e-3)}
-    if world == 1:
-        # HBM-bound leg of the same kernel: 1 and 2 queries over a corpus far larger than L2
-        big = 32_000_000
-        with _capi.Corpus(w, device=local_rank, capacity_rows=big) as cb:
-            cb.set_stream(torch.cuda.current_stream().cuda_stream)
-            cb.fill_synthetic(0, 0, big)
-            cb.set_timing(True)
-            for q_small in (1, 2):
-                ds = torch.empty((q_small, k), dtype=torch.int32, device=dev)
-                dr = torch.empty((q_small, k), dtype=torch.int64, device=dev)
-                ts, tt = [], []
-                for i in range(6):
-                    cb.search(dq[:q_small], k, _capi.HAMMING, None, ds, dr)
-                    t_all, t_scan = cb.last_timing()
-                    if i >= 2:
-                        ts.append(t_scan)
-                        tt.append(t_all)
-                gbs = big * w / (float(np.mean(ts)) * 1e-3) / 1e9
-                extra[f"hbm_leg_q{q_small}"] = {
-                    "rows": big, "corpus_GB": big * w / 1e9, "scan_ms": float(np.mean(ts)),
-                    "total_ms": float(np.mean(tt)), "GBps": gbs, "hbm_frac": gbs / hbm_peak,
-                    "qps": q_small / (float(np.mean(tt)) * 1e-3)}
-        # the reference's LIVE score (XOR-sum of byte values, vlite/model.py:82) on the same workload
+    if "extra" in want and world == 1:
+        # the reference's LIVE score (XOR-sum of byte values, vlite/model.py:82) on the same workload, and
+        # the integer-pipe kernel (LOP3 + POPC, the north-star-literal scan) on the same workload
         ds = torch.empty((nq, k), dtype=torch.int32, device=dev)
         dr = torch.empty((nq, k), dtype=torch.int64, device=dev)
         corpus.set_timing(True)
-        tt = []
-        for i in range(6):
-            flush.zero_()
-            corpus.search(dq, k, _capi.XORSUM, None, ds, dr)
-            if i >= 2:
-                tt.append(corpus.last_timing()[0])
+
+        def timed(metric, path, flush_l2=True):
+            corpus.set_scan_path(path)
+            tt, ts = [], []
+            for i in range(8):
+                if flush_l2:
+                    flush.zero_()
+                corpus.search(dq, k, metric, None, ds, dr)
+                if i >= 3:
+                    tt.append(corpus.last_timing()[0])
+                    ts.append(corpus.last_timing()[1])
+            corpus.set_scan_path(0)
+            return float(np.mean(tt)), float(np.mean(ts))
+        t, s_ = timed(_capi.XORSUM, 0)
+        extra["xorsum_same_workload"] = {"ms_per_step": t, "qps": nq / (t * 1e-3), "kernel": "scan_topk_kernel (LOP3 + IDP4A)"}
+        t, s_ = timed(_capi.HAMMING, 1)
+        extra["integer_pipe_kernel_same_workload"] = {
+            "ms_per_step": t, "scan_ms": s_, "qps": nq / (t * 1e-3), "kernel": "scan_topk_kernel<128,HAMMING,8,8> (LOP3 carry-save + POPC)",
+            "north_star_frac": max(t_hbm, t_int) / (s_ * 1e-3)}
         # SURVEY 8(d): the 64 MB corpus fits L2 -- the headline is timed with L2 flushed between
         # iterations; this is the same step with the corpus left resident
-        tt_res = []
-        for i in range(6):
-            corpus.search(dq, k, _capi.HAMMING, None, ds, dr)
-            if i >= 2:
-                tt_res.append(corpus.last_timing()[0])
-        extra["l2_resident_same_workload"] = {"ms_per_step": float(np.mean(tt_res)),
-                                              "qps": nq / (float(np.mean(tt_res)) * 1e-3)}
-        extra["xorsum_same_workload"] = {"ms_per_step": float(np.mean(tt)), "qps": nq / (float(np.mean(tt)) * 1e-3)}
-        if rank == 0 and not args.no_cpu:
-            qps, ms, cores, sample = time_reference(None, 2, budget_s=40.0, target_s=15.0)
-            cpu_baseline = {"value": qps, "unit": "queries/s", "cores": cores, "kind": "port", "sample": sample}
+        t, s_ = timed(_capi.HAMMING, 0, flush_l2=False)
+        extra["l2_resident_same_workload"] = {"ms_per_step": t, "qps": nq / (t * 1e-3)}
+        corpus.set_timing(False)
+    if "hbm" in want:
+        run_leg("hbm", lambda: legs_mod.leg_hbm(ctx, 32_000_000 if world == 1 else 125_000_000))
+    if "strong" in want and world > 1:
+        run_leg("strong", lambda: legs_mod.leg_strong(ctx, queries))
+    if "group" in want and world > 1:
+        # rank 0 drives every GPU from one process; the other ranks wait on the HOST (gloo), so no
+        # collective kernel spins on the GPUs meanwhile
+        torch.cuda.synchronize()
+        dist.barrier(group=cpu_group)
+        if rank == 0:
+            run_leg("group", lambda: legs_mod.leg_group(ctx, queries), collective=False)
+        dist.barrier(group=cpu_group)
+    if "cfg1" in want and rank == 0:
+        run_leg("cfg1", lambda: legs_mod.leg_cfg1(ctx), collective=False)
+    if "cfg5" in want and world == 1:
+        run_leg("cfg5", lambda: legs_mod.leg_cfg5(ctx))
+    if "cfg3" in want and world == 1:
+        corpus.close()
+        corpus = None
+        del flush
+        ctx["flush"] = None
+        torch.cuda.empty_cache()
+        run_leg("cfg3", lambda: legs_mod.leg_cfg3(ctx))
+
+    cpu_baseline = None
+    if rank == 0 and not args.no_cpu:
+        # N = 1: ~15 s of CPU work; N > 1: a shorter sample so that the scaling runs stay short
+        qps, ms, cores, sample = time_reference(None, 2, budget_s=40.0 if world == 1 else 12.0,
+                                                target_s=15.0 if world == 1 else 5.0)
+        cpu_baseline = {"value": qps, "unit": "queries/s", "cores": cores, "kind": "port", "sample": sample}
 
     if rank == 0:
+        roofline_hbm = None
+        if "hbm" in legs and "q1" in legs["hbm"]:
+            roofline_hbm = dict(legs["hbm"]["q1"], traffic=None, gate=legs["hbm"].get("gate"),
+                                rows_total=legs["hbm"]["rows_total"], gpus=world, kernel=legs["hbm"]["kernel"],
+                                q2=legs["hbm"].get("q2"))
         line = {
             "metric": "queries_per_sec", "value": value, "unit": "queries/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32 (XOR/POPC on packed bits)",
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "s8 x s8 -> s32 (packed bits expanded to +-1 int8 in shared memory; exact)",
             "data": "synthetic", "config": workload_config(world),
             "e2e": {"value": e2e_value, "unit": "queries/s", "h2d_bytes_per_step": nq * w,
                     "d2h_bytes_per_step": nq * k * 12, "ms_per_step": e2e_ms},
             "gpu_launches": int(launches),
-            "roofline": roofline, "cpu_baseline": cpu_baseline, "clocks": clocks,
+            "roofline": roofline, "roofline_hbm": roofline_hbm, "cpu_baseline": cpu_baseline, "clocks": clocks,
             "scan_GBps_aggregate": rows * w * world / (scan_avg_ms * 1e-3) / 1e9,
             "qps_over_whole_corpus": nq / (ms_per_step * 1e-3),
-            "value_definition": "Q x total_rows / 500k per step / time: queries/s in 500k-row-corpus equivalents",
-            "extra": extra,
+            "value_definition": VALUE_DEFINITION,
+            "parity_gate": "32 of the 1024 queries bit-exact (scores and rows) vs the C oracle over the whole corpus, before timing",
+            "legs": legs, "legs_failed": failed, "extra": extra,
         }
         print(json.dumps(line), flush=True)
-    corpus.close()
+    if corpus is not None:
+        corpus.close()
     if world > 1:
         dist.destroy_process_group()
 
@@ -443,6 +507,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
+    ap.add_argument("--no-legs", action="store_true", help="headline step only (profiling runs)")
+    ap.add_argument("--legs", default="default",
+                    help="comma list of extra,hbm,cfg1,cfg3,cfg5 (N=1) / hbm,strong,group (N>1); default = all of them")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
