@@ -238,8 +238,21 @@ def run_ours(args):
         # keep stdout to the one JSON line: NCCL_DEBUG=VERSION (set in some images) prints a banner
         if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
             os.environ["NCCL_DEBUG"] = "WARN"
-        dist.init_process_group("nccl", device_id=dev)
-        cpu_group = dist.new_group(backend="gloo")      # host-side waits that put no kernel on the GPUs
+        # ... and NCCL can still print its version line from a config file: stdout carries ONE JSON line,
+        # so fd 1 points at /dev/null while the communicators come up
+        sys.stdout.flush()
+        saved_fd, null_fd = os.dup(1), os.open(os.devnull, os.O_WRONLY)
+        os.dup2(null_fd, 1)
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            dist.barrier()
+            torch.cuda.synchronize()
+            cpu_group = dist.new_group(backend="gloo")  # host-side waits that put no kernel on the GPUs
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_fd, 1)
+            os.close(saved_fd)
+            os.close(null_fd)
     _capi.load()
     if _capi.device_count() < 1:
         raise SystemExit("no sm_100 device: vlite_b200 has no CPU fallback")

@@ -54,7 +54,7 @@ struct MmaCfg {
     static constexpr int TMEM_COLS = 2 * NT;        // two accumulator buffers
     static constexpr size_t SMEM =
         (size_t)A_BYTES + (size_t)kMmaBStages * kMmaSlabBytes + (size_t)kMmaPkStages * PK_BYTES +
-        (size_t)kMmaPkStages * 2 * MW * 4 + 16 * 8 + 16 + 1024 /* alignment slack */;
+        (size_t)kMmaPkStages * 2 * MW * 4 + 16 * 8 + 16 + kMmaQT * 4 + 1024 /* alignment slack */;
     static_assert(W == 32 || W == 64 || W == 128, "row width");
     static_assert(CG == 1 || CG == 2, "cta group");
 };
@@ -233,6 +233,8 @@ mma_scan_kernel(const __grid_constant__ CUtensorMap tmap, const ScanParams p) {
     uint64_t* acc_full = bars + 10;              // [2]  tcgen05.commit -> epilogue (each CTA its own copy)
     uint64_t* acc_empty = bars + 12;             // [2]  epilogue warps (both CTAs) -> MMA thread of the leader
     uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 14);
+    uint32_t* s_done = s_tmem + 1;                // epilogue warps that have finished (stops the helper warps)
+    uint32_t* s_bound = s_tmem + 4;              // [128] per-query admission bound from the device-wide histogram
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -260,7 +262,9 @@ mma_scan_kernel(const __grid_constant__ CUtensorMap tmap, const ScanParams p) {
             mbar_init(&acc_empty[b], 4 * CG);
         }
         mbar_fence_init();
+        *s_done = 0;
     }
+    if (threadIdx.x < kMmaQT) s_bound[threadIdx.x] = kSentinelScore;
     if (warp == 2) tmem_alloc<CG>(s_tmem, (uint32_t)Cfg::TMEM_COLS);
 
     // ---- A operand: expand this CTA's queries once (zeros past n_queries) ----
@@ -366,6 +370,8 @@ mma_scan_kernel(const __grid_constant__ CUtensorMap tmap, const ScanParams p) {
         uint32_t* tau_ptr = p.tau + (q_ok ? qg : 0);
         uint32_t tau_pref = kSentinelScore;
         bool dirty = false;
+        const bool use_hist = !COLLECT && q_ok && p.hist != nullptr;
+        uint32_t* hq = p.hist + (size_t)(q_ok ? qg : 0) * kHistWords;
         const uint32_t acc_empty_remote = (CG == 2) ? mapa_shared(smem_u32(&acc_empty[0]), 0) : 0u;
 
         for (uint32_t i = 0; i < my_tiles; ++i) {
@@ -378,6 +384,14 @@ mma_scan_kernel(const __grid_constant__ CUtensorMap tmap, const ScanParams p) {
                     thrd = to_dot(thr);
                 }
                 tau_pref = __ldcg(tau_ptr);
+            }
+            // device-wide bound, kept fresh by the helper warps (below): one shared-memory read per tile
+            if (use_hist) {
+                const uint32_t hb = *reinterpret_cast<volatile uint32_t*>(&s_bound[ql]);
+                if (hb < thr) {
+                    thr = hb;
+                    thrd = to_dot(thr);
+                }
             }
             // this tile's eligibility bits (live & filter), one word per lane: fetched before the wait so
             // that the rare path below never touches memory
@@ -447,9 +461,14 @@ mma_scan_kernel(const __grid_constant__ CUtensorMap tmap, const ScanParams p) {
                                 const uint64_t nxt = (e + 1 < kMmaListCap) ? kk[e + 1] : 0ull;
                                 kk[e] = (nxt > key) ? nxt : ((kk[e] > key) ? key : kk[e]);
                             }
-                            thr = (uint32_t)(kk[0] >> 32);
+                            thr = min(thr, (uint32_t)(kk[0] >> 32));   // never looser than a shared bound
                             thrd = to_dot(thr);
                             dirty = true;
+                            if (use_hist) {
+                                const uint32_t b = min(score, (uint32_t)(kHistFine - 1));
+                                atomicAdd(hq + b, 1u);
+                                atomicAdd(hq + kHistFine + (b >> 5), 1u);
+                            }
                         }
                     }
                 }
@@ -459,6 +478,8 @@ mma_scan_kernel(const __grid_constant__ CUtensorMap tmap, const ScanParams p) {
                 if (use_tau && thr != kSentinelScore && thr < tau_pref) atomicMin(tau_ptr, thr);
             }
         }
+        __syncwarp();
+        if (lane == 0) atomicAdd(s_done, 1u);
         if constexpr (!COLLECT) {
             if (q_ok) {
                 const size_t o = ((size_t)split * p.n_queries + qg) * k;
@@ -472,6 +493,65 @@ mma_scan_kernel(const __grid_constant__ CUtensorMap tmap, const ScanParams p) {
                     }
             }
         }
+    } else if (warp == 2 || warp == 3) {
+        // ===================== helpers: device-wide admission bounds =====================
+        // Every row that entered ANY CTA's list of a query was counted in that query's histogram
+        // (fine[1024] | coarse[32], ScanParams::hist), so the score x at which the running count reaches
+        // k caps the final k-th best.  A list's own k-th best only reflects its own row split -- with ~20
+        // statistically alike splits per query that leaves ~half of all 32-row chunks with a candidate;
+        // the histogram reflects all splits and makes the insert path rare.  Two otherwise idle warps poll
+        // it (two L2 round trips per query) and publish bound + 1 to shared memory, off the epilogue's path.
+        if (!COLLECT && p.hist != nullptr) {
+            const int h = (warp - 2) * 32 + lane;
+            const int k = p.k;
+            // the bound tightens like 1 / (rows seen): poll at geometrically growing intervals (1 us ..
+            // 64 us) so that a long scan does not keep two warps hammering L2
+            uint32_t nap = 1000;
+            while (*reinterpret_cast<volatile uint32_t*>(s_done) < 4u) {
+                for (int qq = h; qq < kMmaQT; qq += 64) {
+                    const int qg = q0 + qq;
+                    if (qg >= p.n_queries) continue;
+                    const uint32_t* hq = p.hist + (size_t)qg * kHistWords;
+                    const uint4* coarse = reinterpret_cast<const uint4*>(hq + kHistFine);
+                    uint32_t cum = 0, before = 0;
+                    int cb = -1;
+#pragma unroll
+                    for (int j = 0; j < kHistCoarse / 4; ++j) {
+                        const uint4 c4 = __ldcg(coarse + j);
+                        const uint32_t cw[4] = {c4.x, c4.y, c4.z, c4.w};
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            if (cb < 0 && cum + cw[e] >= (uint32_t)k) {
+                                cb = j * 4 + e;
+                                before = cum;
+                            }
+                            cum += cw[e];
+                        }
+                    }
+                    if (cb < 0) continue;
+                    const uint4* fine = reinterpret_cast<const uint4*>(hq + cb * 32);
+                    uint32_t cf = before;
+                    int x = -1;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const uint4 f4 = __ldcg(fine + j);
+                        const uint32_t fw[4] = {f4.x, f4.y, f4.z, f4.w};
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            if (x < 0 && cf + fw[e] >= (uint32_t)k) x = cb * 32 + j * 4 + e;
+                            cf += fw[e];
+                        }
+                    }
+                    // (the fine bins can lag the coarse ones: x < 0 then; the last bucket is open-ended)
+                    if (x >= 0 && x < kHistFine - 1) s_bound[qq] = (uint32_t)x + 1u;
+                }
+                // sleep in slices so that the end of the scan is noticed within ~2 us
+                for (uint32_t slept = 0; slept < nap && *reinterpret_cast<volatile uint32_t*>(s_done) < 4u; slept += 2000)
+                    __nanosleep(min(nap - slept, 2000u));
+                nap = min(nap + nap / 2, 64000u);
+            }
+        }
+        __syncwarp();
     } else if (warp >= 8) {
         // ===================== expanders: packed rows -> int8 K slabs =====================
         const int ew = warp - 8;

@@ -277,16 +277,17 @@ int search_lists(vl_corpus* c, ScanParams p, int n_queries, int k, int metric, u
     // tau[Q] | cursor score[Q] | cursor row[Q] | histogram[Q][1056] (k <= 32, not for huge batches)
     // (the histogram is read only by the one-warp-per-query configuration, Q > 32; the shared bound
     // tau only by query tiles of more than two queries: small batches skip both memsets)
-    // the tensor-core kernel shares tau at every batch size and never reads the histogram
+    // the tensor-core kernel shares tau AND the histogram at every batch size
     const bool mma = mma_path_for(c, p, n_queries, std::min(k, kWarpListMaxK), metric) != 0;
-    const bool want_hist = !mma && k <= 32 && n_queries > 32 && n_queries <= 16384;
+    const bool want_hist = (mma || (k <= 32 && n_queries > 32)) && n_queries <= 16384;
     const bool want_tau = mma || n_queries > 2;
     const size_t hist_bytes = want_hist ? (size_t)n_queries * kHistWords * 4 : 0;
-    TRY(c->cand_buf.ensure((size_t)n_queries * 12 + hist_bytes));
+    const size_t head_bytes = ((size_t)n_queries * 12 + 15) & ~(size_t)15;   // the histogram is read 16 B at a time
+    TRY(c->cand_buf.ensure(head_bytes + hist_bytes));
     p.tau = static_cast<uint32_t*>(c->cand_buf.p);
     uint32_t* cur_s = p.tau + n_queries;
     uint32_t* cur_r = cur_s + n_queries;
-    p.hist = want_hist ? cur_r + n_queries : nullptr;
+    p.hist = want_hist ? reinterpret_cast<uint32_t*>(static_cast<uint8_t*>(c->cand_buf.p) + head_bytes) : nullptr;
     {
         const uint32_t max_score = metric == VL_METRIC_HAMMING ? 8u * c->w : 255u * c->w;
         p.hist_shift = 0;
