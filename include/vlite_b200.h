@@ -137,6 +137,13 @@ int vl_synth_filter_mask(vl_corpus* c, uint64_t seed, uint64_t threshold, uint32
 #define VL_MAX_K 2048
 int vl_search(vl_corpus* c, const uint8_t* queries_any, int n_queries, int k, int metric,
               const uint32_t* filter_mask_any, uint32_t* out_score_any, uint64_t* out_row_any);
+/* the same search for queries given as FLOAT embeddings (n_queries x dims float32, host or device):
+ * the quantisation tail of EmbeddingModel.embed (vlite/model.py:39-42: first 8*W features, x > 0,
+ * np.packbits MSB-first) runs on the device in front of the scan, so VLite.retrieve
+ * (vlite/main.py:113-117) is ONE call with one copy in and one copy out.  dims >= 8 * W. */
+int vl_search_embeddings(vl_corpus* c, const float* x_any, int n_queries, int dims, int k, int metric,
+                         const uint32_t* filter_mask_any, uint32_t* out_score_any,
+                         uint64_t* out_row_any);
 /* full score vector of ONE query over rows [first, first+n) (parity tests) */
 int vl_scores(vl_corpus* c, const uint8_t* query_any, int metric, uint64_t first, uint64_t n,
               uint32_t* out_any);

@@ -360,3 +360,67 @@ def test_large_k_is_enqueue_only_graph_capturable(gpu, period, nq, path):
         np.testing.assert_array_equal(dr.cpu().numpy().view(np.uint64), er)
         c.set_stream(None)
         del g
+
+
+@pytest.mark.parametrize("width", [32, 64, 128])
+def test_search_embeddings_quantises_like_packbits(gpu, width):
+    """vl_search_embeddings = sign-quantise (first 8W features, x > 0, MSB-first: vlite/model.py:39-42)
+    + vl_search, for host and device float inputs, with more features than the rows hold bits."""
+    import torch
+    n, nq, dims = 30_000, 9, width * 8 + 64
+    corpus = synth.corpus_rows(21, 0, n, width)
+    x = np.random.default_rng(5).standard_normal((nq, dims)).astype(np.float32)
+    x[0, : width * 8] = np.unpackbits(corpus[123]).astype(np.float32) * 2 - 1      # an exact hit
+    x[1, 3] = 0.0                                                                  # 0 is not > 0
+    q = np.packbits(x[:, : width * 8] > 0, axis=1)
+    with gpu.Corpus(width) as c:
+        c.append(corpus)
+        for metric in (HAMMING, XORSUM):
+            es, er = cscan.search(q, corpus, 7, metric)
+            s, r = c.search_embeddings(x, 7, metric)
+            np.testing.assert_array_equal(s, es)
+            np.testing.assert_array_equal(r, er)
+            ds = torch.empty((nq, 7), dtype=torch.int32, device="cuda")
+            dr = torch.empty((nq, 7), dtype=torch.int64, device="cuda")
+            c.search_embeddings(torch.from_numpy(x).cuda(), 7, metric, None, ds, dr)
+            torch.cuda.synchronize()
+            np.testing.assert_array_equal(ds.cpu().numpy().view(np.uint32), es)
+            np.testing.assert_array_equal(dr.cpu().numpy().view(np.uint64), er)
+        assert r[0, 0] == 123 and s[0, 0] == 0
+        valid = synth.filter_valid(22, 0, n, 0.2)
+        s, r = c.search_embeddings(x[:1], 5, HAMMING, synth.pack_mask(valid))
+        es, er = cscan.search(q[:1], corpus, 5, HAMMING, synth.pack_mask(valid))
+        np.testing.assert_array_equal(s, es)
+        np.testing.assert_array_equal(r, er)
+        with pytest.raises(gpu.VliteB200Error):
+            c.search_embeddings(x[:, : width * 8 - 32], 5, HAMMING)                 # fewer features than bits
+
+
+@pytest.mark.parametrize("nq", [1, 2])
+@pytest.mark.parametrize("n", [300, 5000, 200_000])
+def test_fused_merge_matches_separate_merge_kernels(gpu, nq, n):
+    """1-2 queries on a small corpus finish inside the scan launch (last-CTA-done ticket); the result
+    is identical to the scan + merge-kernel path and to the oracle, call after call (the ticket resets)."""
+    corpus = synth.corpus_rows(23, 0, n, 128, period=97 if n == 5000 else 0)
+    q = synth.uniform_queries(24, nq, 128)
+    q[0] = corpus[n - 1]
+    with gpu.Corpus(128) as c:
+        c.append(corpus)
+        for k in (1, 10, 32):
+            es, er = cscan.search(q, corpus, k, HAMMING)
+            for rep in range(3):
+                s, r = c.search(q, k, HAMMING)
+                np.testing.assert_array_equal(s, es)
+                np.testing.assert_array_equal(r, er)
+            c.set_tuning(stages=-2)                       # separate merge kernels
+            s, r = c.search(q, k, HAMMING)
+            np.testing.assert_array_equal(s, es)
+            np.testing.assert_array_equal(r, er)
+            c.set_tuning()
+            for splits in (1, 7, 300):
+                c.set_tuning(row_splits=splits)
+                s, r = c.search(q, k, XORSUM)
+                es2, er2 = cscan.search(q, corpus, k, XORSUM)
+                np.testing.assert_array_equal(s, es2)
+                np.testing.assert_array_equal(r, er2)
+            c.set_tuning()

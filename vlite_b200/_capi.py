@@ -99,6 +99,7 @@ def load():
         "vl_set_timing": (c_int, [c_void_p, c_int]),
         "vl_set_tuning": (c_int, [c_void_p, c_int, c_int]),
         "vl_set_scan_path": (c_int, [c_void_p, c_int]),
+        "vl_search_embeddings": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)
@@ -271,6 +272,26 @@ class Corpus:
         if out_rows is None:
             out_rows = np.empty((nq, k), dtype=np.uint64)
         check(self._L.vl_search(self._h, ptr(queries), nq, k, metric, ptr(filter_mask), ptr(out_scores), ptr(out_rows)))
+        return out_scores, out_rows
+
+    def search_embeddings(self, x, k: int, metric: int = HAMMING, filter_mask=None, out_scores=None, out_rows=None):
+        """x (Q, D) float32 embeddings (numpy or a CUDA tensor), D >= 8 * width: sign-quantised on
+        the device (first 8 * width features, MSB-first like np.packbits) and searched in one call."""
+        if isinstance(x, np.ndarray):
+            x = np.ascontiguousarray(np.atleast_2d(x), dtype=np.float32)
+        nq, dims = int(x.shape[0]), int(x.shape[1])
+        if isinstance(filter_mask, np.ndarray):
+            filter_mask = np.ascontiguousarray(filter_mask, dtype=np.uint32)
+            if filter_mask.shape[0] * 32 < self.rows:
+                raise ValueError("filter mask is shorter than the corpus")
+        if k < 1:
+            raise VliteB200Error(EINVAL, f"k must be in [1, {MAX_K}]")
+        if out_scores is None:
+            out_scores = np.empty((nq, k), dtype=np.uint32)
+        if out_rows is None:
+            out_rows = np.empty((nq, k), dtype=np.uint64)
+        check(self._L.vl_search_embeddings(self._h, ptr(x), nq, dims, k, metric, ptr(filter_mask), ptr(out_scores),
+                                           ptr(out_rows)))
         return out_scores, out_rows
 
     def scores(self, query, metric: int = HAMMING, first: int = 0, n: int | None = None) -> np.ndarray:

@@ -67,9 +67,9 @@ extern "C" int vl_corpus_create(int device, int width_bytes, uint64_t capacity_r
         vl_corpus_destroy(c);
         return rc;
     };
-    if (cudaMalloc(&c->d_err, 2 * sizeof(int)) != cudaSuccess || cudaMalloc(&c->d_counter, 8) != cudaSuccess)
+    if (cudaMalloc(&c->d_err, 4 * sizeof(int)) != cudaSuccess || cudaMalloc(&c->d_counter, 8) != cudaSuccess)
         return bail(fail(VL_ENOMEM, "cudaMalloc failed"));
-    cudaMemset(c->d_err, 0, 2 * sizeof(int));
+    cudaMemset(c->d_err, 0, 4 * sizeof(int));   // [0] repack error, [1] large-k gate, [2] fused-merge ticket
     cudaMemset(c->d_counter, 0, 8);
     cudaEventCreate(&c->ev0);
     cudaEventCreate(&c->ev1);
@@ -96,12 +96,13 @@ extern "C" int vl_corpus_destroy(vl_corpus* c) {
     c->rows_arena.destroy();
     c->live_arena.destroy();
     for (DevBuf* b : {&c->q_buf, &c->filt_buf, &c->part_s, &c->part_r, &c->out_s, &c->out_r, &c->stage[0],
-                      &c->stage[1], &c->cand_buf, &c->misc, &c->lk_keys, &c->lk_misc})
+                      &c->stage[1], &c->cand_buf, &c->misc, &c->lk_keys, &c->lk_misc, &c->qx_buf})
         b->release();
     for (int i = 0; i < 2; ++i) {
         if (c->pinned[i]) cudaFreeHost(c->pinned[i]);
         if (c->stage_ev[i]) cudaEventDestroy(c->stage_ev[i]);
     }
+    if (c->io_pinned) cudaFreeHost(c->io_pinned);
     if (c->d_err) cudaFree(c->d_err);
     if (c->d_counter) cudaFree(c->d_counter);
     if (c->ev0) cudaEventDestroy(c->ev0);
@@ -385,8 +386,8 @@ extern "C" int vl_search(vl_corpus* c, const uint8_t* queries_any, int n_queries
     if (metric != VL_METRIC_HAMMING && metric != VL_METRIC_XORSUM) return fail(VL_EINVAL, "bad metric %d", metric);
     DeviceGuard g(c->device);
     cudaStream_t st = c->stream;
-    const bool q_dev = is_device_ptr(queries_any);
-    const bool s_dev = is_device_ptr(out_score_any), r_dev = is_device_ptr(out_row_any);
+    const int q_kind = ptr_kind(queries_any), s_kind = ptr_kind(out_score_any), r_kind = ptr_kind(out_row_any);
+    const bool q_dev = q_kind == 2, s_dev = s_kind == 2, r_dev = r_kind == 2;
     const size_t n_out = (size_t)n_queries * k;
     c->timed = false;
     if (c->count == 0 || c->live_count == 0) {
@@ -394,11 +395,24 @@ extern "C" int vl_search(vl_corpus* c, const uint8_t* queries_any, int n_queries
         return VL_OK;
     }
 
+    // Pageable host buffers of a small call go through the handle's pinned staging block: one memcpy
+    // on the host, truly asynchronous copies on the stream, and ONE device -> host copy for
+    // [rows | scores] instead of two staged driver copies (the latency path: 1 query, k = 5).
+    const size_t q_bytes = (size_t)n_queries * c->w;
+    const bool stage_q = q_kind == 0 && q_bytes <= (4u << 20);
+    const bool stage_o = s_kind == 0 && r_kind == 0 && n_out * 12 <= (4u << 20);
+    const size_t q_slot = (q_bytes + 63) & ~(size_t)63;
+    if (stage_q || stage_o) TRY(ensure_io_pinned(c, q_slot + n_out * 12));
+
     const uint8_t* q_ptr = queries_any;
     if (!q_dev || (reinterpret_cast<uintptr_t>(queries_any) & 15)) {
-        TRY(c->q_buf.ensure((size_t)n_queries * c->w));
-        CU(cudaMemcpyAsync(c->q_buf.p, queries_any, (size_t)n_queries * c->w,
-                           q_dev ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, st));
+        TRY(c->q_buf.ensure(q_bytes));
+        const void* src = queries_any;
+        if (stage_q) {
+            memcpy(c->io_pinned, queries_any, q_bytes);
+            src = c->io_pinned;
+        }
+        CU(cudaMemcpyAsync(c->q_buf.p, src, q_bytes, q_dev ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, st));
         q_ptr = static_cast<const uint8_t*>(c->q_buf.p);
     }
     const uint32_t* filt = nullptr;
@@ -406,13 +420,19 @@ extern "C" int vl_search(vl_corpus* c, const uint8_t* queries_any, int n_queries
 
     uint32_t* o_s = out_score_any;
     uint64_t* o_r = out_row_any;
-    if (!s_dev) {
-        TRY(c->out_s.ensure(n_out * 4));
-        o_s = static_cast<uint32_t*>(c->out_s.p);
-    }
-    if (!r_dev) {
-        TRY(c->out_r.ensure(n_out * 8));
+    if (stage_o) {
+        TRY(c->out_r.ensure(n_out * 12));            // [rows u64 | scores u32]: contiguous for the single copy back
         o_r = static_cast<uint64_t*>(c->out_r.p);
+        o_s = reinterpret_cast<uint32_t*>(o_r + n_out);
+    } else {
+        if (!s_dev) {
+            TRY(c->out_s.ensure(n_out * 4));
+            o_s = static_cast<uint32_t*>(c->out_s.p);
+        }
+        if (!r_dev) {
+            TRY(c->out_r.ensure(n_out * 8));
+            o_r = static_cast<uint64_t*>(c->out_r.p);
+        }
     }
 
     if (c->timing) CU(cudaEventRecord(c->ev0, st));
@@ -436,10 +456,53 @@ extern "C" int vl_search(vl_corpus* c, const uint8_t* queries_any, int n_queries
         CU(cudaEventRecord(c->ev2, st));
         c->timed = true;
     }
+    if (stage_o) {
+        uint8_t* host = static_cast<uint8_t*>(c->io_pinned) + q_slot;
+        CU(cudaMemcpyAsync(host, o_r, n_out * 12, cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        memcpy(out_row_any, host, n_out * 8);
+        memcpy(out_score_any, host + n_out * 8, n_out * 4);
+        return VL_OK;
+    }
     if (!s_dev) CU(cudaMemcpyAsync(out_score_any, o_s, n_out * 4, cudaMemcpyDeviceToHost, st));
     if (!r_dev) CU(cudaMemcpyAsync(out_row_any, o_r, n_out * 8, cudaMemcpyDeviceToHost, st));
     if (!s_dev || !r_dev || !q_dev) CU(cudaStreamSynchronize(st));
     return VL_OK;
+}
+
+// float embeddings in, top-k out: quantise on the device, then the ordinary search -- one call, one
+// host -> device copy, one copy back (the whole of VLite.retrieve's device work for a query batch)
+extern "C" int vl_search_embeddings(vl_corpus* c, const float* x_any, int n_queries, int dims, int k, int metric,
+                                    const uint32_t* filter_mask_any, uint32_t* out_score_any, uint64_t* out_row_any) {
+    if (!c) return fail(VL_EINVAL, "corpus is NULL");
+    if (!x_any) return fail(VL_EINVAL, "NULL argument");
+    if (n_queries < 1) return fail(VL_EINVAL, "n_queries must be >= 1");
+    if (dims < c->w * 8) return fail(VL_EINVAL, "embeddings have %d features, the corpus rows %d bits", dims, c->w * 8);
+    DeviceGuard g(c->device);
+    cudaStream_t st = c->stream;
+    const size_t x_bytes = (size_t)n_queries * dims * 4;
+    const int x_kind = ptr_kind(x_any);
+    const float* x_dev = x_any;
+    if (x_kind != 2) {
+        TRY(c->stage[0].ensure(x_bytes));
+        const void* src = x_any;
+        if (x_kind == 0 && x_bytes <= (4u << 20)) {
+            // (the pinned block is shared with vl_search's result staging: stream order makes that safe --
+            // the copy back is enqueued behind the kernels, which are behind this copy in)
+            TRY(ensure_io_pinned(c, x_bytes));
+            memcpy(c->io_pinned, x_any, x_bytes);
+            src = c->io_pinned;
+        }
+        CU(cudaMemcpyAsync(c->stage[0].p, src, x_bytes, cudaMemcpyHostToDevice, st));
+        x_dev = static_cast<const float*>(c->stage[0].p);
+    }
+    TRY(c->qx_buf.ensure((size_t)n_queries * c->w));
+    const int words = c->w / 4;
+    sign_pack_rows_kernel<<<grid_for((uint64_t)n_queries * words, 128, c->sms), 128, 0, st>>>(
+        x_dev, (uint64_t)n_queries, dims, words, static_cast<uint32_t*>(c->qx_buf.p));
+    LAUNCHED();
+    return vl_search(c, static_cast<const uint8_t*>(c->qx_buf.p), n_queries, k, metric, filter_mask_any, out_score_any,
+                     out_row_any);
 }
 
 extern "C" int vl_scores(vl_corpus* c, const uint8_t* query_any, int metric, uint64_t first, uint64_t n,
@@ -722,7 +785,8 @@ extern "C" int vl_last_timing(vl_corpus* c, float* total_ms, float* scan_ms) {
 
 extern "C" int vl_set_tuning(vl_corpus* c, int row_splits, int stages) {
     if (!c) return fail(VL_EINVAL, "corpus is NULL");
-    c->force_multipass = stages < 0 ? 1 : 0;  // stages = -1: force the exact multi-pass path for large k
+    c->force_multipass = stages == -1 ? 1 : 0;  // stages = -1: force the exact multi-pass path for large k
+    c->fuse_merge = stages == -2 ? 0 : 1;       // stages = -2: separate merge kernels for 1-2 queries (A/B runs)
     if (stages < 0) stages = 0;
     c->tune_splits = row_splits;
     c->tune_stages = stages;

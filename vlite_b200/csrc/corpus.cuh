@@ -132,10 +132,12 @@ struct vl_corpus {
     uint64_t count = 0;
     uint64_t live_count = 0;
     uint64_t base_row = 0;
-    DevBuf q_buf, filt_buf, part_s, part_r, out_s, out_r, stage[2], cand_buf, misc, lk_keys, lk_misc;
+    DevBuf q_buf, qx_buf, filt_buf, part_s, part_r, out_s, out_r, stage[2], cand_buf, misc, lk_keys, lk_misc;
     int force_multipass = 0;  // tuning/testing: disable the sampled large-k path
     void* pinned[2] = {nullptr, nullptr};
     size_t pinned_bytes = 0;
+    void* io_pinned = nullptr;   // small pinned staging for pageable host queries / results of vl_search
+    size_t io_pinned_bytes = 0;
     cudaEvent_t stage_ev[2] = {nullptr, nullptr};
     int* d_err = nullptr;
     unsigned long long* d_counter = nullptr;
@@ -144,6 +146,7 @@ struct vl_corpus {
     bool timed = false;
     int tune_splits = 0;
     int tune_stages = 0;
+    int fuse_merge = 1;  // 1-2 queries: final merge inside the scan launch (0 = separate merge kernels, for A/B runs)
     int scan_path = 0;  // 0 auto, 1 integer-pipe kernel only, 2 / 3 tensor-core kernel with 1 / 2 CTAs per tile
 };
 
@@ -199,6 +202,20 @@ int ensure_pinned(vl_corpus* c, size_t bytes) {
     c->pinned_bytes = 0;
     for (int i = 0; i < 2; ++i) CU(cudaMallocHost(&c->pinned[i], bytes));
     c->pinned_bytes = bytes;
+    return VL_OK;
+}
+
+int ensure_io_pinned(vl_corpus* c, size_t bytes) {
+    if (bytes <= c->io_pinned_bytes) return VL_OK;
+    if (c->io_pinned) {
+        CU(cudaStreamSynchronize(c->stream));
+        cudaFreeHost(c->io_pinned);
+    }
+    c->io_pinned = nullptr;
+    c->io_pinned_bytes = 0;
+    const size_t want = std::max<size_t>(bytes, 256 << 10);
+    CU(cudaMallocHost(&c->io_pinned, want));
+    c->io_pinned_bytes = want;
     return VL_OK;
 }
 

@@ -83,6 +83,17 @@ struct DevBuf {
     }
 };
 
+// 0 = pageable host memory, 1 = pinned / registered host memory, 2 = device (or managed) memory
+int ptr_kind(const void* p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    if (a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged) return 2;
+    return a.type == cudaMemoryTypeHost ? 1 : 0;
+}
+
 bool is_device_ptr(const void* p) {
     cudaPointerAttributes a;
     if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {

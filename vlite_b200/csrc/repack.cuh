@@ -65,6 +65,24 @@ __global__ void repack_f32_bits_kernel(const float* __restrict__ src, uint64_t n
     }
 }
 
+// The quantisation tail of EmbeddingModel.embed for queries (vlite/model.py:39-42: MRL cut to the
+// first `words * 32` features, x > 0, np.packbits MSB-first), row stride `dims` floats: one thread
+// per output word.  L2 normalisation (model.py:35) does not change a sign, so it is skipped here.
+__global__ void sign_pack_rows_kernel(const float* __restrict__ x, uint64_t n_rows, int dims, int words,
+                                      uint32_t* __restrict__ dst) {
+    const uint64_t total = n_rows * (uint64_t)words;
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < total; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t r = i / words;
+        const int j = (int)(i % words);
+        const float* s = x + r * (uint64_t)dims + (uint64_t)j * 32;
+        uint32_t out = 0;
+#pragma unroll
+        for (int b = 0; b < 32; ++b)
+            if (s[b] > 0.f) out |= 1u << (8 * (b >> 3) + (7 - (b & 7)));
+        dst[i] = out;
+    }
+}
+
 // int8 embeddings -> sign bits packed MSB-first (the binary twin of an int8 document store):
 // one thread turns 32 int8 values into one 32-bit word of the row.
 __global__ void sign_i8_kernel(const int8_t* __restrict__ src, uint64_t n_words, uint32_t* __restrict__ dst) {

@@ -82,7 +82,52 @@ struct ScanParams {
     // optional device-side gate: when set and *gate == 0 the whole launch is a no-op.  Lets the host
     // ENQUEUE a fallback pass whose need is only known on the device (large k: search_host.cuh).
     const int* gate;
+    // fused final merge (1-2 queries, the latency path): every CTA merges its warps' lists, stores one
+    // list of keys per query in fuse_keys[split][q][k], takes a ticket; the LAST CTA to finish merges all
+    // splits and writes the final top-k -- one launch instead of scan + two merge levels.
+    unsigned long long* fuse_keys;   // nullptr = off
+    unsigned int* fuse_ticket;       // zero before the launch; the last CTA resets it
+    uint32_t* out_scores;            // final [q * out_stride + e]
+    uint64_t* out_rows;
+    int out_stride;
 };
+
+// Warp-level k-way merge of sorted key lists (ascending, unique keys, ~0 = exhausted): lane l owns
+// lists l, l + 32, ... (LPL of them) with their heads in registers; every round the warp's smallest
+// head is emitted through put(o, key) on lane 0 and its owner advances.  get(list, pos) fetches.
+template <int LPL, class Get, class Put>
+__device__ __forceinline__ void warp_merge_keys(int n_lists, int k, int lane, Get get, Put put) {
+    unsigned long long head[LPL];
+    int hd[LPL];
+#pragma unroll
+    for (int j = 0; j < LPL; ++j) {
+        hd[j] = 0;
+        const int l = lane + 32 * j;
+        head[j] = (l < n_lists) ? get(l, 0) : ~0ull;
+    }
+    for (int o = 0; o < k; ++o) {
+        unsigned long long best = head[0];
+        int bj = 0;
+#pragma unroll
+        for (int j = 1; j < LPL; ++j)
+            if (head[j] < best) {
+                best = head[j];
+                bj = j;
+            }
+        unsigned long long w = best;
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) w = min(w, __shfl_xor_sync(kFullMask, w, off));
+        if (best == w && w != ~0ull) {   // keys are unique: exactly one lane owns the winner
+#pragma unroll
+            for (int j = 0; j < LPL; ++j)
+                if (j == bj) {
+                    hd[j] += 1;
+                    head[j] = (hd[j] < k) ? get(lane + 32 * j, hd[j]) : ~0ull;
+                }
+        }
+        if (lane == 0) put(o, w);
+    }
+}
 
 // ---- warp-wide selection network for k <= 32: keys are (score << 32 | local row), unique per row ----
 __device__ __forceinline__ uint64_t warp_sort32(uint64_t key, int lane) {
@@ -615,6 +660,74 @@ scan_topk_kernel(const __grid_constant__ CUtensorMap tmap, const ScanParams p) {
 
     // -------- write this warp's lists to the partial buffer --------
     if (collect) return;
+    if constexpr (WQ == 1 && C <= 2) {
+        if (p.fuse_keys != nullptr) {
+            // ---- latency path: CTA-level merge, ticket, final merge by the last CTA ----
+            __syncthreads();                       // every warp's k-list is final (shared memory)
+            // the tile ring is drained (every issued tile was consumed): reuse it as scratch
+            unsigned long long (*s_l1)[32] = reinterpret_cast<unsigned long long (*)[32]>(s_tiles);
+            volatile uint32_t& s_last = *reinterpret_cast<volatile uint32_t*>(s_thr);
+            if (warp < C) {
+                const int c = warp;                // query c of this CTA: its 8 row-slice lists
+                warp_merge_keys<1>(
+                    kScanWarps, k, lane,
+                    [&](int l, int e) -> unsigned long long {
+                        const uint32_t sc = s_lscore[(size_t)l * C * k + c * k + e];
+                        const uint32_t ix = s_lidx[(size_t)l * C * k + c * k + e];
+                        return ix == 0xFFFFFFFFu ? ~0ull : (((unsigned long long)sc << 32) | ix);
+                    },
+                    [&](int o, unsigned long long key) {
+                        const int q = qtile * QT + c;
+                        if (q < p.n_queries) p.fuse_keys[((size_t)split * p.n_queries + q) * k + o] = key;
+                    });
+            }
+            __threadfence();
+            __syncthreads();
+            if (threadIdx.x == 0) s_last = (atomicAdd(p.fuse_ticket, 1u) == gridDim.x * gridDim.y - 1) ? 1u : 0u;
+            __syncthreads();
+            if (s_last == 0u) return;
+            __threadfence();
+            const int per = (n_splits + kScanWarps - 1) / kScanWarps;   // <= 128 (host caps the splits at 1024)
+            // staging area behind s_l1: each warp's lists are fetched from L2 in ONE batch of independent
+            // loads (one latency) instead of k dependent rounds; 8 warps x 1024 keys = 64 KB of the ring
+            unsigned long long* s_stage = reinterpret_cast<unsigned long long*>(s_tiles) + kScanWarps * 32 + (size_t)warp * 1024;
+            const bool staged = per * k <= 1024 && (size_t)stages * TILE_BYTES >= (size_t)(kScanWarps * 32 + kScanWarps * 1024) * 8;
+            for (int q = 0; q < p.n_queries; ++q) {
+                // level 1: warp w merges splits [w * per, (w + 1) * per)
+                const int l0 = warp * per;
+                const int nl = max(0, min(per, n_splits - l0));
+                if (staged) {
+                    for (int e = lane; e < nl * k; e += 32)
+                        s_stage[e] = __ldcg(p.fuse_keys + ((size_t)(l0 + e / k) * p.n_queries + q) * k + (e % k));
+                    __syncwarp();
+                    warp_merge_keys<4>(
+                        nl, k, lane, [&](int l, int e) -> unsigned long long { return s_stage[l * k + e]; },
+                        [&](int o, unsigned long long key) { s_l1[warp][o] = key; });
+                } else {
+                    warp_merge_keys<4>(
+                        nl, k, lane,
+                        [&](int l, int e) -> unsigned long long {
+                            return __ldcg(p.fuse_keys + ((size_t)(l0 + l) * p.n_queries + q) * k + e);
+                        },
+                        [&](int o, unsigned long long key) { s_l1[warp][o] = key; });
+                }
+                __syncthreads();
+                // level 2: warp 0 merges the 8 partial lists and writes the result
+                if (warp == 0) {
+                    warp_merge_keys<1>(
+                        kScanWarps, k, lane, [&](int l, int e) -> unsigned long long { return s_l1[l][e]; },
+                        [&](int o, unsigned long long key) {
+                            const bool none = key == ~0ull;
+                            p.out_scores[(size_t)q * p.out_stride + o] = none ? kSentinelScore : (uint32_t)(key >> 32);
+                            p.out_rows[(size_t)q * p.out_stride + o] = none ? kSentinelRow : p.base_row + (uint32_t)key;
+                        });
+                }
+                __syncthreads();
+            }
+            if (threadIdx.x == 0) *p.fuse_ticket = 0u;   // ready for the next launch on this stream
+            return;
+        }
+    }
     const int list_id = split * WR + wr;
 #pragma unroll
     for (int c = 0; c < C; ++c) {

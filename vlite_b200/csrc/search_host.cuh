@@ -301,6 +301,25 @@ int search_lists(vl_corpus* c, ScanParams p, int n_queries, int k, int metric, u
         p.cur_row = pass ? cur_r : nullptr;
         ScanPlan plan{};
         TRY(launch_scan(c, p, n_queries, k_pass, metric, &plan, /*dry=*/true));
+        // latency path (1-2 queries, k <= 32): the scan's last CTA does the whole merge -- one launch
+        const bool fuse = n_pass == 1 && n_queries <= 2 && k <= 32 && plan.C <= 2 && plan.WQ == 1 && plan.S <= 1024 &&
+                          p.tile_stride == 1 && gate == nullptr && c->fuse_merge &&
+                          c->count * (uint64_t)c->w <= (1ull << 30);   // (beyond ~1 GB the serial tail costs more than two launches)
+        if (fuse) {
+            TRY(c->part_r.ensure((size_t)plan.S * n_queries * k * 8));
+            p.fuse_keys = static_cast<unsigned long long*>(c->part_r.p);
+            p.fuse_ticket = reinterpret_cast<unsigned int*>(c->d_err + 2);
+            p.out_scores = o_s;
+            p.out_rows = o_r;
+            p.out_stride = out_stride;
+            p.part_scores = nullptr;
+            p.part_rows = nullptr;
+            p.evict_first = (c->count * (uint64_t)c->w > (96ull << 20)) ? 1 : 0;
+            TRY(launch_scan(c, p, n_queries, k_pass, metric, nullptr, /*dry=*/false));
+            if (c->timing) CU(cudaEventRecord(c->ev1, st));
+            return VL_OK;
+        }
+        p.fuse_keys = nullptr;
         const size_t n_lists = (size_t)plan.S * plan.WR;
         const size_t dense = (size_t)n_queries * k_pass;
         const size_t n_part = (n_lists + merge_tmp_lists(n_lists)) * dense;

@@ -324,14 +324,16 @@ class VLite:
             words = np.packbits(bits.reshape(-1, 32), axis=1, bitorder="little").view(np.uint32).reshape(-1)
         return words
 
-    def _search(self, queries_u8, k, mask=None):
-        if self._corpus is None or self._corpus.live_rows == 0 or queries_u8.shape[1] != self._corpus.width:
+    def _search(self, queries_u8, k, mask=None, floats=None):
+        live = self._corpus.live_rows if self._corpus is not None else 0
+        if live == 0 or (floats is None and queries_u8.shape[1] != self._corpus.width):
             raise ValueError("No valid binary vectors found for comparison.")     # main.py:149
-        k = max(1, min(int(k), int(self._corpus.live_rows)))          # vlite/model.py:84
+        k = max(1, min(int(k), int(live)))                            # vlite/model.py:84
         if k > _capi.MAX_K:
             raise ValueError(f"top_k={k} exceeds the device top-k limit VL_MAX_K={_capi.MAX_K}")
-        scores, rows = self._corpus.search(queries_u8, k, self.metric, mask)
-        return scores, rows
+        if floats is not None:
+            return self._corpus.search_embeddings(floats, k, self.metric, mask)
+        return self._corpus.search(queries_u8, k, self.metric, mask)
 
     # ------------------------------------------------------------------ API
     @_locked
@@ -367,9 +369,8 @@ class VLite:
         score and cut to top_k -- a list of Q texts yields ONE list.  Falsy text returns None."""
         if not text:
             return None
-        queries = self.model.embed(text, precision="binary")
         results = []
-        for chunk_results in self._rank_batch(np.atleast_2d(queries), top_k, metadata, top_k_multiplier):
+        for chunk_results in self._rank_texts(text, top_k, metadata, top_k_multiplier):
             results.extend(chunk_results)
         results.sort(key=lambda x: x[1])                 # stable, by score only (main.py:120)
         results = results[:top_k]
@@ -380,21 +381,32 @@ class VLite:
     @_locked
     def retrieve_batch(self, texts, top_k=5, metadata=None, return_scores=False, top_k_multiplier=4):
         """One result list PER query (the reference merges them, main.py:116-121).  One batched scan."""
-        queries = self.model.embed(texts, precision="binary")
         out = []
-        for chunk_results in self._rank_batch(np.atleast_2d(queries), top_k, metadata, top_k_multiplier):
+        for chunk_results in self._rank_texts(texts, top_k, metadata, top_k_multiplier):
             if return_scores:
                 out.append([(cid, self._texts[cid], self._metas[cid], s) for cid, s in chunk_results])
             else:
                 out.append([(cid, self._texts[cid], self._metas[cid]) for cid, _ in chunk_results])
         return out
 
-    def _rank_batch(self, queries, top_k, metadata, top_k_multiplier):
+    def _rank_texts(self, text, top_k, metadata, top_k_multiplier):
+        """embed + rank.  On a single-GPU collection the float embeddings go straight to
+        ``vl_search_embeddings``: quantisation (vlite/model.py:39-42) and scan are ONE native call
+        with one copy in and one copy out, instead of a device round trip for the packed query."""
+        c = self._corpus
+        if isinstance(c, _capi.Corpus) and c.live_rows and self.model.binary_dims == c.width * 8:
+            x = self.model.embed_float(text)
+            if x.shape[1] >= c.width * 8:
+                return self._rank_batch(None, top_k, metadata, top_k_multiplier, floats=x)
+        queries = self.model.embed(text, precision="binary")
+        return self._rank_batch(np.atleast_2d(queries), top_k, metadata, top_k_multiplier)
+
+    def _rank_batch(self, queries, top_k, metadata, top_k_multiplier, floats=None):
         if self._corpus is None or self._corpus.live_rows == 0:
             raise ValueError("No valid binary vectors found for comparison.")     # main.py:149
-        q = from_reference_encoding(queries)
+        q = from_reference_encoding(queries) if floats is None else None
         if metadata and self.filter_mode == "reference":
-            scores, rows = self._search(q, top_k * top_k_multiplier)           # main.py:134-137
+            scores, rows = self._search(q, top_k * top_k_multiplier, floats=floats)   # main.py:134-137
             out = []
             for s_row, r_row in zip(scores, rows):
                 ids = [self._ids[int(r)] for r in r_row if r != _capi.SENTINEL_ROW]
@@ -404,7 +416,7 @@ class VLite:
                 out.append(list(zip(kept, [np.int64(s) for s in s_row[:len(kept)]])))
             return out
         mask = self._filter_mask(metadata) if metadata else None
-        scores, rows = self._search(q, top_k, mask)
+        scores, rows = self._search(q, top_k, mask, floats=floats)
         out = []
         for s_row, r_row in zip(scores, rows):
             keep = r_row != _capi.SENTINEL_ROW

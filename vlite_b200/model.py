@@ -91,6 +91,16 @@ class EmbeddingModel:
             raise ValueError(f"Unsupported precision: {precision}")
         return to_reference_encoding(self.embed_ubinary(texts))
 
+    def embed_float(self, texts):
+        """The float embeddings of ``texts`` before quantisation, (B, D): numpy or a CUDA tensor.
+        ``VLite.retrieve`` hands them to ``vl_search_embeddings`` (quantise + scan in one call)."""
+        if isinstance(texts, str):
+            texts = [texts]
+        x = self._forward(texts)
+        if isinstance(x, np.ndarray):
+            return np.ascontiguousarray(np.atleast_2d(x), dtype=np.float32)
+        return x.float().contiguous()
+
     def embed_device(self, texts, int8=False, float32=False, i8_scale=127.0):
         """The quantisation tail fused on the device (``vl_quantize_embeddings``): returns a dict of
         CUDA tensors -- ``"ubinary"`` (B, binary_dims/8) uint8 for the scan and, on request,
