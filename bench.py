@@ -212,7 +212,8 @@ def workload_config(n_gpus: int, reference: bool = False):
         # the reference's live score is the XOR-sum of byte values (vlite/model.py:82); ours is timed on
         # true Hamming, the north-star metric (same memory traffic; our XOR-sum time is under extra)
         "metric_fn": "xorsum" if reference else "hamming", "parallelism": f"row-shard x{n_gpus}",
-        "l2": "corpus (64 MB) fits L2: a 256 MB buffer is overwritten between timed iterations (L2 flush)",
+        "l2": ("corpus (64 MB) fits L2: a 256 MB buffer is overwritten between timed iterations (L2 flush); at N > 1 an "
+               "untimed one-element all-reduce re-aligns the GPUs after each flush, before the step's first event"),
     }
 
 
@@ -302,8 +303,18 @@ def run_ours(args):
     launches0 = _capi.launch_count()
     scan_ms = []
     barrier()
+    tick = torch.zeros(1, dtype=torch.int32, device=dev)
+
+    def align():
+        """the 256 MB flush finishes at slightly different times on every GPU: an (untimed) one-element
+        all-reduce lines the GPUs up again before the timed events, so a step's time is scan + exchange,
+        not scan + exchange + how far the flush let the ranks drift apart"""
+        if world > 1:
+            dist.all_reduce(tick)
+
     for i in range(args.steps):
         flush.zero_()                              # L2 flush, outside the timed events
+        align()
         ev0[i].record()
         searcher.search(dq, k, _capi.HAMMING)
         ev1[i].record()
@@ -392,7 +403,7 @@ def run_ours(args):
     }
 
     ctx = {"torch": torch, "dist": dist, "capi": _capi, "world": world, "rank": rank, "local_rank": local_rank,
-           "dev": dev, "hbm_peak": hbm_peak, "barrier": barrier, "flush": flush, "no_cpu": args.no_cpu}
+           "dev": dev, "hbm_peak": hbm_peak, "barrier": barrier, "flush": flush, "no_cpu": args.no_cpu, "align": align}
     default_legs = ["extra", "hbm", "cfg1", "cfg3", "cfg5"] if world == 1 else ["hbm", "strong", "group"]
     want = default_legs if args.legs == "default" else [x for x in args.legs.split(",") if x]
     if args.no_legs:

@@ -194,6 +194,7 @@ def leg_hbm(ctx, rows_per_gpu):
             cb.set_timing(True)
             for i in range(7):
                 ctx["barrier"]()
+                ctx["align"]()
                 a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 a.record()
                 sb.search(dq[:q_small], k, _capi.HAMMING)
@@ -246,7 +247,7 @@ def leg_strong(ctx, queries, steps=20):
         tt = []
         for i in range(steps + 3):
             flush.zero_()
-            ctx["barrier"]()
+            ctx["align"]()
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record()
             s.search(dq, k, _capi.HAMMING)

@@ -245,6 +245,24 @@ int vl_shard_group_search(vl_shard_group* g, const uint8_t* queries_host, int n_
                           const uint32_t* const* filter_masks_or_null, uint32_t* out_score_host,
                           uint64_t* out_row_host);
 
+/* ---- exchange: the one exchange step of the row-sharded path for ONE PROCESS PER GPU -------- */
+/* (the reference has no multi-GPU path, so this replaces nothing there.)  Every rank
+ * stores its k candidates per query straight into every peer's gather buffer over NVLink (CUDA IPC
+ * mappings opened once) and raises a flag; the merge kernel of each rank acquires all flags and merges by
+ * (score, global row).  Same result as an all-gather + vl_merge_topk, without a collective library call
+ * on the critical path.  Setup: every rank creates its exchange, publishes its 64-byte handle
+ * (e.g. torch.distributed.all_gather_object) and attaches every peer's. */
+typedef struct vl_exchange vl_exchange;
+int vl_exchange_create(int device, int world, int rank, uint64_t slot_bytes, vl_exchange** out);
+int vl_exchange_handle(vl_exchange* x, void* handle_out_64);
+int vl_exchange_attach(vl_exchange* x, int peer_rank, const void* handle_64);
+/* local_block_dev = [Q*k uint32 scores | Q*k uint64 GLOBAL rows] (Q*k even, 16 B aligned), block_bytes =
+ * 12*Q*k <= slot_bytes.  Enqueues push + merge on cuda_stream; out_* get the merged top-k of all ranks. */
+int vl_exchange_gather_merge(vl_exchange* x, void* cuda_stream, const void* local_block_dev,
+                             uint64_t block_bytes, int n_queries, int k, uint32_t* out_score_dev,
+                             uint64_t* out_row_dev);
+int vl_exchange_destroy(vl_exchange* x);
+
 #ifdef __cplusplus
 }
 #endif

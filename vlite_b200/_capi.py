@@ -99,6 +99,11 @@ def load():
         "vl_set_timing": (c_int, [c_void_p, c_int]),
         "vl_set_tuning": (c_int, [c_void_p, c_int, c_int]),
         "vl_set_scan_path": (c_int, [c_void_p, c_int]),
+        "vl_exchange_create": (c_int, [c_int, c_int, c_int, c_u64, P(c_void_p)]),
+        "vl_exchange_handle": (c_int, [c_void_p, c_void_p]),
+        "vl_exchange_attach": (c_int, [c_void_p, c_int, c_void_p]),
+        "vl_exchange_gather_merge": (c_int, [c_void_p, c_void_p, c_void_p, c_u64, c_int, c_int, c_void_p, c_void_p]),
+        "vl_exchange_destroy": (c_int, [c_void_p]),
         "vl_search_embeddings": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     }
     for name, (res, args) in sig.items():
@@ -415,6 +420,40 @@ class ShardGroup:
                 masks[i] = m.ctypes.data
         check(self._L.vl_shard_group_search(self._h, ptr(q), nq, int(k), int(metric), masks, ptr(scores), ptr(rows)))
         return scores, rows
+
+
+class Exchange:
+    """``vl_exchange_*``: the peer-store exchange of the one-process-per-GPU path.  ``handle()`` is
+    published to every rank, ``attach(rank, handle)`` maps a peer's buffer (CUDA IPC)."""
+
+    def __init__(self, device: int, world: int, rank: int, slot_bytes: int):
+        self._L = load()
+        self._h = ctypes.c_void_p()
+        self.world, self.rank, self.slot_bytes = world, rank, slot_bytes
+        check(self._L.vl_exchange_create(device, world, rank, slot_bytes, ctypes.byref(self._h)))
+
+    def handle(self) -> bytes:
+        buf = ctypes.create_string_buffer(64)
+        check(self._L.vl_exchange_handle(self._h, buf))
+        return buf.raw
+
+    def attach(self, peer_rank: int, handle: bytes):
+        check(self._L.vl_exchange_attach(self._h, peer_rank, ctypes.c_char_p(handle)))
+
+    def gather_merge(self, stream, local_block_dev, block_bytes: int, n_queries: int, k: int, out_scores, out_rows):
+        check(self._L.vl_exchange_gather_merge(self._h, ctypes.c_void_p(stream or 0), ptr(local_block_dev), block_bytes,
+                                               n_queries, k, ptr(out_scores), ptr(out_rows)))
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            self._L.vl_exchange_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 def merge_topk(scores_dev, rows_dev, n_lists: int, n_queries: int, k_in: int, k_out: int,

@@ -17,7 +17,7 @@ LIB_DIR = os.path.join(PKG, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "libvlite_b200.so")
 SOURCES = [os.path.join(CSRC, "api.cu")]
 HEADERS = [os.path.join(CSRC, f) for f in ("common.cuh", "scan.cuh", "mmascan.cuh", "merge.cuh", "rescore.cuh",
-                                            "repack.cuh", "synth.cuh", "largek.cuh", "host_util.cuh",
+                                            "repack.cuh", "synth.cuh", "exchange.cuh", "largek.cuh", "host_util.cuh",
                                             "corpus.cuh", "search_host.cuh", "group.cuh")]
 HEADERS.append(os.path.join(os.path.dirname(PKG), "include", "vlite_b200.h"))
 

@@ -25,6 +25,7 @@
 #include "scan.cuh"
 #include "mmascan.cuh"
 #include "synth.cuh"
+#include "exchange.cuh"
 
 #include "host_util.cuh"
 #include "corpus.cuh"
@@ -801,3 +802,119 @@ extern "C" int vl_set_scan_path(vl_corpus* c, int path) {
 }
 
 #include "group.cuh"
+
+// =============================== exchange (one process per GPU) ===============================
+struct vl_exchange {
+    int device = 0, world = 0, rank = 0;
+    size_t slot_bytes = 0, flags_off = 0, total = 0;
+    uint8_t* local = nullptr;
+    uint8_t* peer[vl::kExchangeMaxWorld] = {};
+    bool opened[vl::kExchangeMaxWorld] = {};
+    uint32_t epoch = 0;
+    int* timeout_host = nullptr;   // pinned, mapped: the merge kernel reports a peer that never arrived
+    int* timeout_dev = nullptr;
+};
+
+extern "C" int vl_exchange_create(int device, int world, int rank, uint64_t slot_bytes, vl_exchange** out) {
+    if (!out) return fail(VL_EINVAL, "out is NULL");
+    *out = nullptr;
+    if (world < 2 || world > vl::kExchangeMaxWorld || rank < 0 || rank >= world)
+        return fail(VL_EINVAL, "need 2 <= world <= %d and 0 <= rank < world", vl::kExchangeMaxWorld);
+    if (slot_bytes == 0) return fail(VL_EINVAL, "slot_bytes is 0");
+    TRY(check_device(device, nullptr));
+    DeviceGuard g(device);
+    vl_exchange* x = new vl_exchange();
+    x->device = device;
+    x->world = world;
+    x->rank = rank;
+    x->slot_bytes = (slot_bytes + 255) & ~(size_t)255;
+    x->flags_off = 2 * (size_t)world * x->slot_bytes;
+    x->total = x->flags_off + 2 * (size_t)world * 4 + 256;
+    if (cudaMalloc(&x->local, x->total) != cudaSuccess) {
+        cudaGetLastError();
+        delete x;
+        return fail(VL_ENOMEM, "cudaMalloc(%zu) failed", x->total);
+    }
+    cudaMemset(x->local, 0, x->total);
+    cudaDeviceSynchronize();
+    if (cudaHostAlloc(&x->timeout_host, sizeof(int), cudaHostAllocMapped) != cudaSuccess ||
+        cudaHostGetDevicePointer(&x->timeout_dev, x->timeout_host, 0) != cudaSuccess) {
+        cudaGetLastError();
+        cudaFree(x->local);
+        delete x;
+        return fail(VL_ECUDA, "cannot allocate the mapped status word");
+    }
+    *x->timeout_host = 0;
+    x->peer[rank] = x->local;
+    *out = x;
+    return VL_OK;
+}
+
+extern "C" int vl_exchange_handle(vl_exchange* x, void* handle_out_64) {
+    if (!x || !handle_out_64) return fail(VL_EINVAL, "NULL argument");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    DeviceGuard g(x->device);
+    cudaIpcMemHandle_t h;
+    CU(cudaIpcGetMemHandle(&h, x->local));
+    memcpy(handle_out_64, &h, sizeof h);
+    return VL_OK;
+}
+
+extern "C" int vl_exchange_attach(vl_exchange* x, int peer_rank, const void* handle_64) {
+    if (!x || !handle_64) return fail(VL_EINVAL, "NULL argument");
+    if (peer_rank < 0 || peer_rank >= x->world) return fail(VL_EINVAL, "peer rank out of range");
+    if (peer_rank == x->rank) return VL_OK;
+    DeviceGuard g(x->device);
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle_64, sizeof h);
+    void* p = nullptr;
+    CU(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+    x->peer[peer_rank] = static_cast<uint8_t*>(p);
+    x->opened[peer_rank] = true;
+    return VL_OK;
+}
+
+extern "C" int vl_exchange_gather_merge(vl_exchange* x, void* cuda_stream, const void* local_block_dev,
+                                        uint64_t block_bytes, int n_queries, int k, uint32_t* out_score_dev,
+                                        uint64_t* out_row_dev) {
+    if (!x || !local_block_dev || !out_score_dev || !out_row_dev) return fail(VL_EINVAL, "NULL argument");
+    const size_t nb = (size_t)n_queries * k;
+    if (n_queries < 1 || k < 1 || (nb * 4) % 8 || block_bytes != nb * 12 || block_bytes > x->slot_bytes)
+        return fail(VL_EINVAL, "block must be [Q*k u32 | Q*k u64] with Q*k even, at most the slot size");
+    if (reinterpret_cast<uintptr_t>(local_block_dev) & 15) return fail(VL_EINVAL, "block must be 16 B aligned");
+    for (int r = 0; r < x->world; ++r)
+        if (!x->peer[r]) return fail(VL_EINVAL, "rank %d is not attached", r);
+    if (*x->timeout_host) return fail(VL_ECUDA, "an earlier exchange timed out waiting for a peer rank");
+    DeviceGuard g(x->device);
+    cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+    const uint32_t epoch = ++x->epoch;
+    const size_t parity = epoch & 1u;
+    vl::PeerPtrs peers{};
+    for (int r = 0; r < x->world; ++r) peers.p[r] = x->peer[r];
+    const uint64_t slot_off = (parity * x->world + x->rank) * x->slot_bytes;
+    const uint64_t flag_off = x->flags_off + (parity * x->world + x->rank) * 4;
+    const uint64_t n16 = (block_bytes + 15) / 16;          // (the slot is padded to 256 B: a ragged tail is harmless)
+    vl::exchange_push_kernel<<<x->world, vl::kPushThreads, 0, st>>>(static_cast<const uint4*>(local_block_dev), n16,
+                                                                   peers, slot_off, flag_off, epoch);
+    LAUNCHED();
+    const uint8_t* slots = x->local + parity * x->world * x->slot_bytes;
+    const uint32_t* flags = reinterpret_cast<const uint32_t*>(x->local + x->flags_off) + parity * x->world;
+    vl::exchange_merge_kernel<<<(unsigned)((n_queries + vl::kMergeWarps - 1) / vl::kMergeWarps), vl::kMergeWarps * 32, 0, st>>>(
+        flags, x->world, epoch, x->timeout_dev, reinterpret_cast<const uint32_t*>(slots),
+        reinterpret_cast<const uint64_t*>(slots + nb * 4), n_queries, k, out_score_dev, out_row_dev, x->slot_bytes / 4,
+        x->slot_bytes / 8);
+    LAUNCHED();
+    return VL_OK;
+}
+
+extern "C" int vl_exchange_destroy(vl_exchange* x) {
+    if (!x) return VL_OK;
+    DeviceGuard g(x->device);
+    cudaDeviceSynchronize();
+    for (int r = 0; r < x->world; ++r)
+        if (x->opened[r]) cudaIpcCloseMemHandle(x->peer[r]);
+    if (x->local) cudaFree(x->local);
+    if (x->timeout_host) cudaFreeHost(x->timeout_host);
+    delete x;
+    return VL_OK;
+}

@@ -20,6 +20,7 @@ identical results for identical content.
 """
 from __future__ import annotations
 
+import os
 from dataclasses import dataclass
 
 import numpy as np
@@ -78,6 +79,47 @@ class ShardedSearcher:
             device = torch.device("cuda", corpus.device) if local_search is None else torch.device("cpu")
         self.device = device
         self._bufs = {}
+        # the exchange: peer stores over CUDA IPC mappings (vl_exchange_*) on GPUs; the all-gather +
+        # merge of the host-logic tests (gloo) and wherever IPC cannot be set up
+        self._xchg = None
+        self._xchg_ok = ((merge is None or merge is _cuda_merge) and self.world > 1 and device.type == "cuda"
+                         and self.world <= 16 and os.environ.get("VLITE_B200_EXCHANGE", "ipc") == "ipc")
+
+    def _exchange(self, block_bytes: int):
+        """collective (every rank calls it with the same size): (re)build the peer mappings"""
+        from . import _capi
+        if self._xchg is not None and self._xchg.slot_bytes >= block_bytes:
+            return self._xchg
+        t, dist = self.torch, self.dist
+        if self._xchg is not None:
+            t.cuda.synchronize(self.device)
+            dist.barrier(group=self.group)
+            self._xchg.close()
+            self._xchg = None
+        ok, x, handle = 1, None, b""
+        try:
+            x = _capi.Exchange(self.device.index, self.world, self.rank, max(block_bytes, 1 << 20))
+            handle = x.handle()
+        except Exception:          # noqa: BLE001 -- decided collectively below
+            ok = 0
+        handles = [None] * self.world
+        dist.all_gather_object(handles, (ok, handle), group=self.group)
+        if all(h[0] for h in handles):
+            try:
+                for r, (_, h) in enumerate(handles):
+                    if r != self.rank:
+                        x.attach(r, h)
+            except Exception:      # noqa: BLE001
+                ok = 0
+        flag = t.tensor([ok if all(h[0] for h in handles) else 0], dtype=t.int32, device=self.device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.group)
+        if int(flag.item()) == 0:
+            if x is not None:
+                x.close()
+            self._xchg_ok = False
+            return None
+        self._xchg = x
+        return x
 
     def _buffers(self, nq: int, k: int):
         key = (nq, k)
@@ -106,9 +148,16 @@ class ShardedSearcher:
         self._local_search(self.corpus, queries, k, metric, filter_mask, ls, lr)
         if self.world == 1:
             return ls, lr
+        stream = t.cuda.current_stream().cuda_stream if self.device.type == "cuda" else None
+        if self._xchg_ok:
+            x = self._exchange(nb * 12)
+            if x is not None:
+                # the ONE exchange of the path: every rank stores its k candidates per query into every
+                # peer's buffer over NVLink and raises a flag; the merge kernel acquires all flags
+                x.gather_merge(stream, send, nb * 12, nq, k, out_s, out_r)
+                return out_s, out_r
         # the ONE collective of the path: k candidates per query per rank
         self.dist.all_gather_into_tensor(recv.view(-1), send, group=self.group)
-        stream = t.cuda.current_stream().cuda_stream if self.device.type == "cuda" else None
         dev_index = self.device.index if self.device.type == "cuda" else 0
         self._merge(recv, self.world, nq, k, out_s, out_r, dev_index, stream)
         return out_s, out_r
