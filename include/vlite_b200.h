@@ -170,6 +170,8 @@ int vl_map_rows(int device, void* cuda_stream, uint64_t* rows_dev, uint64_t n,
  * code is the unused cos_sim, vlite/utils.py:205-208) ----------------------- */
 #define VL_QTYPE_F32 0
 #define VL_QTYPE_I8  1
+#define VL_QTYPE_GATHER_PROBE 2  /* measurement only: int8-shaped queries, same gathers / sort / stores, no dot
+                                    products -- the HBM gather floor of a rescore (scores are meaningless) */
 /* docs_i8_dev: n_docs x dims int8, row-major, indexed by LOCAL row.
  * queries_any: Q x dims float32 or int8.  cand_rows_any: Q x C uint64 GLOBAL
  * rows as vl_search wrote them (sentinels skipped).  Output: top k by

@@ -38,13 +38,18 @@ def test_rescore_matches_oracle(gpu, qtype, n_cand, k):
         np.testing.assert_array_equal(r, er)                             # int32 accumulate: exact
         np.testing.assert_array_equal(s.astype(np.float64), es)
     else:
-        # fp32 accumulate: 1e-5 relative to the magnitude of the dot's terms
-        scale = np.abs(host_docs[cand[cand != osearch.SENTINEL_ROW][:8].astype(np.int64)].astype(np.float64)).sum(1).mean()
-        np.testing.assert_allclose(s, es, rtol=RTOL, atol=RTOL * scale)
-        same = r == er
-        assert same.mean() > 0.99                                        # order may swap only on near-ties
-        for qi, pos in zip(*np.nonzero(~same)):
-            assert abs(es[qi, pos] - s[qi, pos]) <= RTOL * scale
+        # int8 x fp32 products and their fp64 sum are exact on the device: the only rounding is the
+        # final one to float32.  north_star: within 1e-5 RELATIVE -- asserted per element, no absolute
+        # slack, cancelling sums included (k = n_cand = 37 keeps every candidate, near-zero scores too)
+        ok = er != osearch.SENTINEL_ROW
+        rel = np.abs(s.astype(np.float64)[ok] - es[ok]) / np.maximum(np.abs(es[ok]), 1e-300)
+        print(f"rescore fp32 queries: max relative error {rel.max():.3e} over {ok.sum()} scores")
+        assert rel.max() <= RTOL, rel.max()
+        assert rel.max() <= 1.2e-7                                       # = float32 rounding of an exact sum
+        # ordering is decided on float32 scores: rows may differ from the float64 order only where two
+        # float64 scores round to the same float32
+        for qi, pos in zip(*np.nonzero(r != er)):
+            assert np.float32(es[qi, pos]) == s[qi, pos]
 
 
 def test_binary_then_rescore_pipeline(gpu):

@@ -307,9 +307,11 @@ class Corpus:
         check(self._L.vl_scores(self._h, ptr(query), metric, first, n, ptr(out) if n else None))
         return out
 
-    def rescore(self, docs_i8_dev, n_docs: int, dims: int, queries, cand_rows, k: int, out_scores=None, out_rows=None):
+    def rescore(self, docs_i8_dev, n_docs: int, dims: int, queries, cand_rows, k: int, out_scores=None, out_rows=None,
+                gather_probe: bool = False):
         """docs_i8_dev: device tensor / address of (n_docs, dims) int8.  queries (Q, dims) float32
-        or int8; cand_rows (Q, C) uint64 global rows."""
+        or int8; cand_rows (Q, C) uint64 global rows.  gather_probe (int8 queries): measurement only --
+        the same gathers without the dot products (VL_QTYPE_GATHER_PROBE)."""
         if isinstance(queries, np.ndarray):
             queries = np.ascontiguousarray(queries)
             qtype = QTYPE_I8 if queries.dtype == np.int8 else QTYPE_F32
@@ -319,6 +321,8 @@ class Corpus:
             qtype = QTYPE_I8 if "int8" in str(queries.dtype) else QTYPE_F32
         if isinstance(cand_rows, np.ndarray):
             cand_rows = np.ascontiguousarray(cand_rows, dtype=np.uint64)
+        if gather_probe:
+            qtype = 2
         nq, nc = int(cand_rows.shape[0]), int(cand_rows.shape[1])
         if out_scores is None:
             out_scores = np.empty((nq, k), dtype=np.float32)

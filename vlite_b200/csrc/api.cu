@@ -582,12 +582,12 @@ extern "C" int vl_rescore(vl_corpus* c, const int8_t* docs_i8_dev, uint64_t n_do
         return fail(VL_EINVAL, "NULL argument");
     if (!is_device_ptr(docs_i8_dev)) return fail(VL_EINVAL, "docs must be device memory");
     if (dims < 16 || dims % 16) return fail(VL_EINVAL, "dims must be a positive multiple of 16");
-    if (qtype != VL_QTYPE_F32 && qtype != VL_QTYPE_I8) return fail(VL_EINVAL, "bad qtype");
+    if (qtype != VL_QTYPE_F32 && qtype != VL_QTYPE_I8 && qtype != VL_QTYPE_GATHER_PROBE) return fail(VL_EINVAL, "bad qtype");
     if (n_queries < 1 || n_cand < 1 || n_cand > kRescoreMaxCand || k < 1 || k > n_cand)
         return fail(VL_EINVAL, "need 1 <= k <= n_cand <= %d", kRescoreMaxCand);
     DeviceGuard g(c->device);
     cudaStream_t st = c->stream;
-    const size_t qbytes = (size_t)n_queries * dims * (qtype == VL_QTYPE_I8 ? 1 : 4);
+    const size_t qbytes = (size_t)n_queries * dims * (qtype == VL_QTYPE_F32 ? 4 : 1);
     const void* q_ptr = queries_any;
     const bool q_dev = is_device_ptr(queries_any);
     if (!q_dev || (reinterpret_cast<uintptr_t>(queries_any) & 15)) {
@@ -628,15 +628,18 @@ extern "C" int vl_rescore(vl_corpus* c, const int8_t* docs_i8_dev, uint64_t n_do
     p.n_cand = n_cand;
     p.n_sort = n_sort;
     p.k = k;
-    const size_t smem = (size_t)n_sort * 12 + (size_t)dims * (qtype == VL_QTYPE_I8 ? 1 : 4);
+    const size_t smem = (size_t)n_sort * 12 + (size_t)dims * (qtype == VL_QTYPE_F32 ? 8 : 1);   // fp32 queries are held as fp64
     c->timed = false;
     if (c->timing) CU(cudaEventRecord(c->ev0, st));
     if (qtype == VL_QTYPE_I8) {
-        TRY(allow_max_smem(rescore_kernel<true>, c->device));
-        rescore_kernel<true><<<n_queries, kRescoreThreads, smem, st>>>(p);
+        TRY(allow_max_smem(rescore_kernel<1>, c->device));
+        rescore_kernel<1><<<n_queries, kRescoreThreads, smem, st>>>(p);
+    } else if (qtype == VL_QTYPE_GATHER_PROBE) {
+        TRY(allow_max_smem(rescore_kernel<2>, c->device));
+        rescore_kernel<2><<<n_queries, kRescoreThreads, smem, st>>>(p);
     } else {
-        TRY(allow_max_smem(rescore_kernel<false>, c->device));
-        rescore_kernel<false><<<n_queries, kRescoreThreads, smem, st>>>(p);
+        TRY(allow_max_smem(rescore_kernel<0>, c->device));
+        rescore_kernel<0><<<n_queries, kRescoreThreads, smem, st>>>(p);
     }
     LAUNCHED();
     if (c->timing) {

@@ -5,8 +5,11 @@
 // ("parity unpinned").  Per query the C candidate rows are scattered 1 KB gathers, so the
 // kernel is gather-bandwidth bound, not a GEMM: one CTA per query, the query staged in
 // shared memory, one warp per candidate row with 128-bit coalesced loads, DP4A (int8 query,
-// exact int32) or FFMA (fp32 query, fp32 accumulate), then an in-CTA bitonic sort by
-// (score descending, row ascending) and the first k written out.
+// exact int32) or DFMA (fp32 query: int8 x fp32 products are exact in fp64 and the 1024-term sum
+// is accumulated in fp64, so the only rounding is the final one to float32 -- 6e-8 relative, for
+// cancelling sums too; north_star asks for 1e-5), then an in-CTA bitonic sort by (score descending,
+// row ascending) and the first k written out.  The fp64 pipe (64 DFMA/clk/SM on B200) stays under
+// the gather time.
 #pragma once
 #include <math_constants.h>
 
@@ -28,15 +31,20 @@ struct RescoreParams {
     int dims, n_cand, n_sort, k;  // n_sort = next pow2 >= n_cand
 };
 
-template <bool QI8>
+// QMODE 0: fp32 queries, 1: int8 queries, 2: gather probe (measurement only: the same loads, sort and
+// stores with the arithmetic reduced to one XOR per word -- the floor any rescore of these candidates
+// has to pay for moving Q x C x D bytes out of HBM)
+template <int QMODE>
 __global__ void __launch_bounds__(kRescoreThreads) rescore_kernel(const RescoreParams p) {
+    constexpr bool QI8 = QMODE != 0;
+    constexpr bool PROBE = QMODE == 2;
     extern __shared__ __align__(1024) uint8_t smem[];
     const int q = blockIdx.x;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int dims = p.dims;
     float* s_score = reinterpret_cast<float*>(smem);                       // n_sort
     uint64_t* s_row = reinterpret_cast<uint64_t*>(s_score + p.n_sort);     // n_sort (8B aligned: n_sort even)
-    uint8_t* s_q = reinterpret_cast<uint8_t*>(s_row + p.n_sort);           // dims * (1 | 4)
+    uint8_t* s_q = reinterpret_cast<uint8_t*>(s_row + p.n_sort);           // dims * (1 | 8): int8 query, or the fp32 query widened to fp64
 
     const size_t qbytes = (size_t)dims * (QI8 ? 1 : 4);
     {
@@ -45,11 +53,16 @@ __global__ void __launch_bounds__(kRescoreThreads) rescore_kernel(const RescoreP
         if constexpr (QI8) {
             for (int i = threadIdx.x; i < (int)(qbytes / 16); i += kRescoreThreads) dst[i] = src[i];
         } else {
-            // fp32 query: the 4 float4 that face one 16-byte doc chunk are stored chunk-minor
-            // ([j][chunk]) so that the 32 lanes of a warp read consecutive float4 (no bank conflicts)
+            // fp32 query, widened to fp64 once: the 8 double2 that face one 16-byte doc chunk are stored
+            // chunk-minor ([e][chunk]) so that the 32 lanes of a warp read consecutive 16 B (no bank conflicts)
             const int n_chunks = dims / 16;
-            for (int i = threadIdx.x; i < (int)(qbytes / 16); i += kRescoreThreads)
-                dst[(i & 3) * n_chunks + (i >> 2)] = src[i];
+            const float2* srcf = reinterpret_cast<const float2*>(src);
+            double2* dstd = reinterpret_cast<double2*>(s_q);
+            for (int i = threadIdx.x; i < dims / 2; i += kRescoreThreads) {
+                const float2 f = srcf[i];
+                dstd[(i & 7) * n_chunks + (i >> 3)] = make_double2((double)f.x, (double)f.y);
+            }
+            (void)dst;
         }
     }
     for (int i = threadIdx.x; i < p.n_sort; i += kRescoreThreads) {
@@ -62,26 +75,29 @@ __global__ void __launch_bounds__(kRescoreThreads) rescore_kernel(const RescoreP
     // one 1 KB gather per candidate is latency-bound: every warp keeps U rows (2 x 128-bit loads per
     // lane each) in flight before it starts the arithmetic of the first
     constexpr int U = 4;
-    auto accumulate = [&](const uint4& v, int ch, float& facc, int& iacc) {
+    auto accumulate = [&](const uint4& v, int ch, double& facc, int& iacc) {
         const uint32_t w[4] = {v.x, v.y, v.z, v.w};
-        if constexpr (QI8) {
+        if constexpr (PROBE) {
+            iacc ^= (int)(w[0] ^ w[1] ^ w[2] ^ w[3]) + ch;
+        } else if constexpr (QI8) {
             const uint4 qv = reinterpret_cast<const uint4*>(s_q)[ch];
             iacc = __dp4a((int)w[0], (int)qv.x, iacc);
             iacc = __dp4a((int)w[1], (int)qv.y, iacc);
             iacc = __dp4a((int)w[2], (int)qv.z, iacc);
             iacc = __dp4a((int)w[3], (int)qv.w, iacc);
         } else {
-            const float4* qf = reinterpret_cast<const float4*>(s_q) + ch;
+            const double2* qd = reinterpret_cast<const double2*>(s_q) + ch;
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-                const float4 qq = qf[j * chunks];
-                // int8 -> float without the conversion unit: byte b of (x ^ 0x80808080) is d + 128 in
-                // [0, 255]; PRMT drops it under the exponent of 2^23, so the float is 8388736 + d exactly
+                // int8 -> double without the conversion unit: byte b of (x ^ 0x80808080) is d + 128 in
+                // [0, 255]; PRMT drops it under the exponent of 2^52, so the double is 2^52 + 128 + d exactly
                 const uint32_t u = w[j] ^ 0x80808080u;
-                facc = fmaf(__uint_as_float(__byte_perm(u, 0x4B000000u, 0x7440)) - 8388736.f, qq.x, facc);
-                facc = fmaf(__uint_as_float(__byte_perm(u, 0x4B000000u, 0x7441)) - 8388736.f, qq.y, facc);
-                facc = fmaf(__uint_as_float(__byte_perm(u, 0x4B000000u, 0x7442)) - 8388736.f, qq.z, facc);
-                facc = fmaf(__uint_as_float(__byte_perm(u, 0x4B000000u, 0x7443)) - 8388736.f, qq.w, facc);
+                const double2 qa = qd[(2 * j) * chunks], qb = qd[(2 * j + 1) * chunks];
+                constexpr double kMagic = 4503599627370624.0;   // 2^52 + 128
+                facc = fma(__hiloint2double(0x43300000, (int)__byte_perm(u, 0u, 0x4440)) - kMagic, qa.x, facc);
+                facc = fma(__hiloint2double(0x43300000, (int)__byte_perm(u, 0u, 0x4441)) - kMagic, qa.y, facc);
+                facc = fma(__hiloint2double(0x43300000, (int)__byte_perm(u, 0u, 0x4442)) - kMagic, qb.x, facc);
+                facc = fma(__hiloint2double(0x43300000, (int)__byte_perm(u, 0u, 0x4443)) - kMagic, qb.y, facc);
             }
         }
     };
@@ -107,7 +123,7 @@ __global__ void __launch_bounds__(kRescoreThreads) rescore_kernel(const RescoreP
 #pragma unroll
         for (int u = 0; u < U; ++u) {
             if (grow[u] == kSentinelRow) continue;   // warp-uniform
-            float facc = 0.f;
+            double facc = 0.0;
             int iacc = 0;
 #pragma unroll
             for (int h = 0; h < 2; ++h)
@@ -116,13 +132,13 @@ __global__ void __launch_bounds__(kRescoreThreads) rescore_kernel(const RescoreP
             if constexpr (QI8) {
 #pragma unroll
                 for (int off = 16; off > 0; off >>= 1) iacc += __shfl_xor_sync(kFullMask, iacc, off);
-                facc = (float)iacc;
+                facc = (double)iacc;
             } else {
 #pragma unroll
                 for (int off = 16; off > 0; off >>= 1) facc += __shfl_xor_sync(kFullMask, facc, off);
             }
             if (lane == 0) {
-                s_score[c0 + u] = facc;
+                s_score[c0 + u] = (float)facc;
                 s_row[c0 + u] = grow[u];
             }
         }
