@@ -213,7 +213,7 @@ int vl_set_timing(vl_corpus* c, int enabled);
  * stages = depth of the TMA ring, or -1 to force the exact multi-pass path for k > 32 */
 int vl_set_tuning(vl_corpus* c, int row_splits, int stages);
 /* which scan kernel answers vl_search on this handle.  0 = automatic (default): HAMMING batches of
- * at least 64 queries with k <= 16 (and the collect pass of k > 32) go to the tensor-core kernel
+ * at least 24 queries (16 for W <= 64) with k <= 16 (and the passes of k > 32) go to the tensor-core kernel
  * (tcgen05.mma kind::i8 on rows expanded bit -> int8 in shared memory; exact int32 scores), the rest
  * to the integer-pipe kernel (LOP3 + POPC / DP4A).  1 = integer-pipe kernel only; 2 / 3 = tensor-core
  * kernel with one CTA / a CTA pair per query tile whenever the call is eligible (any batch size).

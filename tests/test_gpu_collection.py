@@ -509,3 +509,42 @@ def test_save_writes_a_zero_row_for_keys_without_a_vector(gpu, golden, tmp_path)
     assert v2.count() == n and "ghost_0" in v2.index
     v.close()
     v2.close()
+
+
+def test_journal_mode_persists_without_rewriting_the_collection(gpu, tmp_path):
+    """journal=True: set_batch / delete / update append O(change) records (new rows go to a small side
+    file) instead of reading the corpus back and rewriting the CTX file; a reopen replays them; save()
+    folds everything into clean v1 files a reference reader loads, and removes the journal."""
+    from vlite_b200 import VLite
+    rows = synth.corpus_rows(95, 0, 900, 64)
+    emb = lambda texts: np.unpackbits(rows[[int(t) for t in texts]], axis=1).astype(np.float32) * 2 - 1
+    d = str(tmp_path)
+    v = VLite("jr", ctx_dir=d, embedder=emb, journal=True)
+    v.set_batch([f"t{i}" for i in range(600)], osearch.to_ref_encoding(rows[:600]), [{"g": i % 3} for i in range(600)])
+    assert not os.path.exists(os.path.join(d, "jr.ctx"))                # nothing rewritten: the rows are in jr.j0.ctx
+    assert os.path.exists(os.path.join(d, "jr.j0.ctx")) and os.path.exists(os.path.join(d, "jr.journal"))
+    v.save()                                                             # a full save: clean file, journal gone
+    assert os.path.exists(os.path.join(d, "jr.ctx")) and not os.path.exists(os.path.join(d, "jr.journal"))
+    assert not os.path.exists(os.path.join(d, "jr.j0.ctx"))
+    stamp = os.stat(os.path.join(d, "jr.ctx")).st_mtime_ns
+    keys = list(v.index.keys())
+    v.set_batch([f"u{i}" for i in range(300)], osearch.to_ref_encoding(rows[600:]), [{"g": 7} for _ in range(300)])
+    assert v.delete([keys[5][:-2], keys[17][:-2]]) == 2
+    assert v.update(keys[40][:-2], text="changed", metadata={"g": 9})
+    assert os.stat(os.path.join(d, "jr.ctx")).st_mtime_ns == stamp      # the collection file was not touched
+    want = [v.retrieve(str(q), top_k=4, return_scores=True) for q in (5, 17, 40, 777)]
+    want_f = v.retrieve("777", top_k=3, metadata={"g": 7}, return_scores=True)
+    v.close()
+    v2 = VLite("jr", ctx_dir=d, embedder=emb, journal=True)              # last full save + journal replay
+    assert v2.count() == 898 and keys[5] not in v2.index and keys[17] not in v2.index
+    assert v2.index[keys[40]]["text"] == "changed" and v2.index[keys[40]]["metadata"]["g"] == 9
+    assert [v2.retrieve(str(q), top_k=4, return_scores=True) for q in (5, 17, 40, 777)] == want
+    assert v2.retrieve("777", top_k=3, metadata={"g": 7}, return_scores=True) == want_f
+    v2.save()
+    assert not os.path.exists(os.path.join(d, "jr.journal")) and not os.path.exists(os.path.join(d, "jr.j0.ctx"))
+    header, emb_f32, contexts, metadata, _ = octx.read_ctx(os.path.join(d, "jr.ctx"))     # reference-readable
+    assert emb_f32.shape == (898, 64) and len(contexts) == 898 and len(metadata) == 898
+    v2.close()
+    v3 = VLite("jr", ctx_dir=d, embedder=emb)                             # plain mode reads the same collection
+    assert [v3.retrieve(str(q), top_k=4, return_scores=True) for q in (5, 17, 40, 777)] == want
+    v3.close()

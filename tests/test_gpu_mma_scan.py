@@ -119,14 +119,14 @@ def test_large_k_collect_pass_on_tensor_cores(gpu, path, k):
 
 
 def test_automatic_dispatch_is_bit_identical(gpu):
-    """auto mode: Q >= 64 with k <= 16 goes to the tensor-core kernel, everything else to the
+    """auto mode: Q >= 24 (16 at W <= 64) with k <= 16 goes to the tensor-core kernel, everything else to the
     integer-pipe kernel; XORSUM never does."""
     n = 50_000
     corpus = synth.corpus_rows(18, 0, n, 64)
     queries = synth.uniform_queries(19, 260, 64)
     with gpu.Corpus(64) as c:
         c.append(corpus)
-        for nq in (63, 64, 260):
+        for nq in (15, 16, 63, 64, 260):
             _check(c, corpus, queries[:nq], 10)
         s, r = c.search(queries, 10, 1)
         es, er = cscan.search(queries, corpus, 10, 1)

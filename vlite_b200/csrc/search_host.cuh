@@ -106,13 +106,16 @@ int launch_scan_wm(vl_corpus* c, ScanParams& p, int nq, int k, ScanPlan* plan, b
 // ---- tensor-core scan (mmascan.cuh) ----------------------------------------------
 
 // smallest batch the tensor-core scan takes in automatic mode (tuning override: VLITE_B200_MMA_MINQ;
-// a value <= 0 disables the path)
-int mma_min_q() {
+// a value <= 0 disables the path).  Measured crossover against the integer-pipe kernel on 500k rows:
+// W = 128: Q = 16 0.133 vs 0.122 ms, Q = 24 0.132 vs 0.192 ms; W = 64: Q = 16 0.098 vs 0.113 ms -- a
+// 128-query tile costs the same whether it holds 16 queries or 128.
+int mma_min_q(int w) {
     static int v = [] {
         const char* e = getenv("VLITE_B200_MMA_MINQ");
-        return e ? atoi(e) : 64;
+        return e ? atoi(e) : -1;
     }();
-    return v;
+    if (v != -1) return v;
+    return w >= 128 ? 24 : 16;
 }
 
 // 0 = not eligible, 1 = one CTA per query tile, 2 = CTA pairs (cta_group::2)
@@ -123,7 +126,7 @@ int mma_path_for(const vl_corpus* c, const ScanParams& p, int nq, int k, int met
     if (c->scan_path == 1) return 0;
     if (c->scan_path == 2) return 1;
     if (c->scan_path == 3) return 2;
-    const int mq = mma_min_q();
+    const int mq = mma_min_q(c->w);
     if (mq <= 0 || nq < mq) return 0;
     return nq > kMmaQT ? 2 : 1;
 }

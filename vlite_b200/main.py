@@ -114,13 +114,16 @@ class _IndexView(dict):
 class VLite:
     def __init__(self, collection=None, device=None, model_name="mixedbread-ai/mxbai-embed-large-v1", *,
                  embedder=None, metric="xorsum", width=None, filter_mode="prefilter", ctx_dir="contexts",
-                 gpu_index=0, gpus=None):
+                 gpu_index=0, gpus=None, journal=False):
         """collection / device / model_name: as vlite/main.py:20.  Keyword-only additions:
         embedder (texts -> float array), metric ("xorsum" = the reference's live score,
         "hamming" = true Hamming distance), width (bytes per row, default from the data: 64),
         filter_mode ("prefilter" | "reference"), ctx_dir, gpu_index, gpus (a list of device
         indices: the collection is row-sharded over them inside this process; results are the
-        same as on one GPU)."""
+        same as on one GPU), journal (False = the reference's persistence: update / delete / set_batch
+        rewrite the whole collection file, vlite/main.py:181, :201, :271; True = they append an O(change)
+        record to ``<collection>.journal`` instead -- no device read-back, no rewrite -- and ``save()``
+        folds everything into clean, reference-readable CTX v1 files)."""
         if metric not in METRICS:
             raise ValueError(f"metric must be one of {sorted(METRICS)}")
         if filter_mode not in ("prefilter", "reference"):
@@ -144,6 +147,9 @@ class VLite:
         # "float32" = the reference's layout (default); "ubinary" = packed bytes, 4x smaller, opt-in
         self.ctx_dtype = "float32"
         self._width = width
+        self.journal = bool(journal)
+        self._journal_seq = 0      # number of side files (<collection>.jN.ctx) the journal refers to
+        self._replaying = False
         self._corpus = None
         self._row_of = {}          # chunk_id -> row (None: no stored vector)
         self._ids = []             # row -> chunk_id (None once deleted)
@@ -278,6 +284,75 @@ class VLite:
                 parts = int(cf.header.get("parts", 1)) if isinstance(cf.header, dict) else 1
             self._load_part(cf)
             i += 1
+        self._replay_journal()
+
+    # ------------------------------------------------------------------ journal (deferred persistence)
+    # The reference persists by rewriting the whole collection on every update / delete / set_batch.
+    # With ``journal=True`` those calls append one JSON line each to ``<collection>.journal``:
+    #   {"op": "del", "ids": [chunk ids]}
+    #   {"op": "upd", "id": item id, "text": ..., "metadata": ..., "vector": ...}
+    #   {"op": "add", "file": "<collection>.jN", "n": rows}   rows of a set_batch, written as a small
+    #                                                         standalone CTX v1 file of just those rows
+    # A reopen loads the last full save and replays the journal; ``save()`` writes clean v1 files (what a
+    # reference reader loads) and removes the journal and its side files.
+    def _journal_path(self) -> str:
+        return self.ctx.get(self.collection)[: -len(".ctx")] + ".journal"
+
+    def _journal_append(self, record: dict):
+        import json
+        os.makedirs(os.path.dirname(self._journal_path()) or ".", exist_ok=True)
+        with open(self._journal_path(), "a", encoding="utf-8") as f:
+            f.write(json.dumps(record, default=lambda o: o.tolist() if hasattr(o, "tolist") else str(o)) + "\n")
+            f.flush()
+            os.fsync(f.fileno())
+
+    def _persist(self, record_fn):
+        """what the reference does with ``self.save()`` after a mutation"""
+        if getattr(self, "_replaying", False):
+            return
+        if getattr(self, "journal", False):
+            self._journal_append(record_fn())
+        else:
+            self.save()
+
+    def _replay_journal(self):
+        import json
+        path = self._journal_path()
+        if not os.path.exists(path):
+            return
+        self._replaying = True
+        try:
+            with open(path, "r", encoding="utf-8") as f:
+                for line in f:
+                    line = line.strip()
+                    if not line:
+                        continue
+                    rec = json.loads(line)
+                    if rec["op"] == "del":
+                        self._delete_chunks(rec["ids"])
+                    elif rec["op"] == "upd":
+                        self.update(rec["id"], rec.get("text"), rec.get("metadata"), rec.get("vector"))
+                    elif rec["op"] == "add":
+                        cf = self.ctx.read(rec["file"])
+                        cf.load(materialise=False)
+                        self._load_part(cf)
+                        self._journal_seq = max(self._journal_seq, int(rec["file"].rsplit(".j", 1)[1]) + 1)
+        finally:
+            self._replaying = False
+
+    def _drop_journal(self):
+        if os.path.exists(self._journal_path()):
+            os.remove(self._journal_path())
+        i = 0
+        while True:
+            name = f"{self.collection}.j{i}"
+            if not os.path.exists(self.ctx.get(name)):
+                if i >= self._journal_seq:
+                    break
+            else:
+                self.ctx.delete(name)
+            i += 1
+        self._journal_seq = 0
 
     def _part_name(self, i: int) -> str:
         return self.collection if i == 0 else f"{self.collection}.part{i}"
@@ -456,7 +531,7 @@ class VLite:
                 self._metas[cid].update(metadata)
             if vector is not None:
                 self._extra.setdefault(cid, {})["vector"] = vector
-        self.save()
+        self._persist(lambda: {"op": "upd", "id": id, "text": text, "metadata": metadata, "vector": vector})
         return True
 
     @_locked
@@ -464,22 +539,31 @@ class VLite:
         """vlite/main.py:190-205: prefix match on ``{id}_``; returns the number of chunks removed."""
         if isinstance(ids, str):
             ids = [ids]
-        deleted, dead_rows = 0, []
+        gone = []
         for id in ids:
-            for cid in self._chunks_of(id):
-                row = self._row_of.pop(cid)
-                self._unfile_prefixes(cid)
-                self._texts.pop(cid, None)
-                self._metas.pop(cid, None)
-                self._extra.pop(cid, None)
-                if row is not None:
-                    dead_rows.append(row)
-                    self._ids[row] = None
-                deleted += 1
+            gone.extend(self._chunks_of(id))
+        gone = list(dict.fromkeys(gone))
+        deleted = self._delete_chunks(gone)
+        if deleted > 0:
+            self._persist(lambda: {"op": "del", "ids": gone})
+        return deleted
+
+    def _delete_chunks(self, chunk_ids):
+        deleted, dead_rows = 0, []
+        for cid in chunk_ids:
+            if cid not in self._row_of:
+                continue
+            row = self._row_of.pop(cid)
+            self._unfile_prefixes(cid)
+            self._texts.pop(cid, None)
+            self._metas.pop(cid, None)
+            self._extra.pop(cid, None)
+            if row is not None:
+                dead_rows.append(row)
+                self._ids[row] = None
+            deleted += 1
         if dead_rows:
             self._corpus.tombstone(dead_rows)
-        if deleted > 0:
-            self.save()
         return deleted
 
     @_locked
@@ -524,10 +608,35 @@ class VLite:
             raise ValueError("The number of texts and embeddings must be the same.")
         if len(texts) != len(metadatas):
             raise ValueError("The number of texts and metadatas must be the same.")
+        keys = []
         if len(texts):
             first = self._append_vectors(np.asarray(embeddings))
-            self._register_many([f"{uid}_0" for uid in self._new_ids(len(texts))], texts, metadatas, first)
-        self.save()
+            keys = [f"{uid}_0" for uid in self._new_ids(len(texts))]
+            self._register_many(keys, texts, metadatas, first)
+        if self.journal and not self._replaying:
+            if keys:
+                # only the new rows go to disk: a standalone CTX v1 file named by the journal
+                name = f"{self.collection}.j{self._journal_seq}"
+                self._journal_seq += 1
+                self._write_rows_file(name, keys, np.asarray(embeddings))
+                self._journal_append({"op": "add", "file": name, "n": len(keys)})
+        else:
+            self.save()
+
+    def _write_rows_file(self, name, keys, embeddings):
+        """a complete CTX v1 file holding just these rows (given in the reference encoding or raw bytes)"""
+        width = self._width or 64
+        compact = self.ctx_dtype == "ubinary"
+        cf = self.ctx.create(name)
+        cf.set_header(embedding_model="mixedbread-ai/mxbai-embed-large-v1", embedding_size=width,
+                      embedding_dtype="ubinary" if compact else self.model.embedding_dtype,
+                      context_length=self.model.context_length)
+        u8 = np.ascontiguousarray(np.atleast_2d(from_reference_encoding(np.asarray(embeddings))))
+        cf.set_embeddings_array(u8 if compact else to_reference_encoding(u8).astype(np.float32))
+        for k in keys:
+            cf.add_context(self._texts[k])
+            cf.add_metadata(k, self._metas[k])
+        cf.save()
 
     @_locked
     def count(self):
@@ -587,6 +696,7 @@ class VLite:
         while os.path.exists(self.ctx.get(self._part_name(stale))):
             self.ctx.delete(self._part_name(stale))
             stale += 1
+        self._drop_journal()                                                 # everything is in the v1 files now
 
     @_locked
     def clear(self):
@@ -604,6 +714,7 @@ class VLite:
         while i == 0 or os.path.exists(self.ctx.get(self._part_name(i))):
             self.ctx.delete(self._part_name(i))
             i += 1
+        self._drop_journal()
 
     def info(self):
         print("[VLite.info] Collection Information:")
@@ -669,6 +780,16 @@ class ShardedVLite(VLite):
         rows = self._corpus.read() if (self._corpus is not None and self._row_of) else None   # collective
         rank = dist.get_rank(self._group) if dist.is_initialized() else 0
         self._rank0_then_all(lambda: VLite.save(self, _all_rows=rows), rank)
+
+    def _journal_append(self, record):
+        import torch.distributed as dist
+        if not dist.is_initialized() or dist.get_rank(self._group) == 0:      # rank 0 alone writes files
+            super()._journal_append(record)
+
+    def _write_rows_file(self, name, keys, embeddings):
+        import torch.distributed as dist
+        if not dist.is_initialized() or dist.get_rank(self._group) == 0:
+            super()._write_rows_file(name, keys, embeddings)
 
     def _rank0_then_all(self, fn, rank):
         """Run ``fn`` on rank 0 only; its outcome is broadcast so that a failure (I/O error, bad

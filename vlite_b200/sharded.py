@@ -218,6 +218,83 @@ class CudaShardBackend:
         self.local.close()
 
 
+class SegmentTable:
+    """The placement bookkeeping both sharded collections share: which shard owns which GLOBAL rows.
+
+    A batch goes to the least-full shard (ties: lowest index) and takes the next global rows, so
+    global rows are insertion order whatever the shard count.  Segments are
+    ``(global_base, owner, local_start, n)``, ascending in ``global_base``; an append that continues
+    the previous segment (same owner -- its local range is then contiguous too) extends it instead
+    of adding one, the base array for ``locate``'s bisect and the per-owner tables the device needs
+    (``local_start -> global_base``, for ``vl_map_rows``) are kept incrementally, and a shard whose
+    table changed is only marked dirty: the upload happens once, before the next search, so a stream
+    of small ``add()`` calls costs O(1) each on the host."""
+
+    def __init__(self, n_shards: int):
+        self.n_shards = n_shards
+        self.clear()
+
+    def clear(self):
+        self.counts = [0] * self.n_shards        # local rows per shard
+        self.segments = []                       # (global_base, owner, local_start, n)
+        self._bases = []                         # [s[0] for s in segments], kept for bisect
+        self._by_owner = [([], []) for _ in range(self.n_shards)]   # (local starts, global bases) per shard
+        self.dirty = set(range(self.n_shards))   # shards whose device table is stale
+        self.total = 0
+
+    def least_full(self) -> int:
+        return min(range(self.n_shards), key=lambda r: (self.counts[r], r))
+
+    def add(self, owner: int, n: int) -> int:
+        """place n rows on `owner`; returns their first GLOBAL row"""
+        base, lstart = self.total, self.counts[owner]
+        last = self.segments[-1] if self.segments else None
+        if last is not None and last[1] == owner and last[0] + last[3] == base and last[2] + last[3] == lstart:
+            self.segments[-1] = (last[0], owner, last[2], last[3] + n)      # same mapping: nothing to upload
+        else:
+            self.segments.append((base, owner, lstart, n))
+            self._bases.append(base)
+            self._by_owner[owner][0].append(lstart)
+            self._by_owner[owner][1].append(base)
+            self.dirty.add(owner)
+        self.counts[owner] += n
+        self.total += n
+        return base
+
+    def locate(self, global_row: int):
+        """(owner, local row) of a global row"""
+        import bisect
+        i = bisect.bisect_right(self._bases, global_row) - 1
+        if i < 0 or global_row >= self.segments[i][0] + self.segments[i][3]:
+            raise IndexError(f"global row {global_row} out of range")
+        base, owner, lstart, _ = self.segments[i]
+        return owner, lstart + (global_row - base)
+
+    def table_of(self, owner: int):
+        """(local starts, global bases) of one shard, ascending"""
+        return self._by_owner[owner]
+
+    def local_masks(self, mask_words_global, owners=None):
+        """global bit-per-row mask -> one local mask per shard (host-side bit gather); None for an
+        empty shard or one not in `owners`"""
+        bits = np.unpackbits(np.ascontiguousarray(mask_words_global, dtype=np.uint32).view(np.uint8),
+                             bitorder="little")
+        want = range(self.n_shards) if owners is None else owners
+        local = {r: np.zeros((self.counts[r] + 31) // 32 * 32, dtype=np.uint8) for r in want}
+        for base, owner, lstart, n in self.segments:
+            if owner in local:
+                local[owner][lstart:lstart + n] = bits[base:base + n]
+        return [np.packbits(local[r].reshape(-1, 32), axis=1, bitorder="little").view(np.uint32).reshape(-1)
+                if r in local and local[r].size else None for r in range(self.n_shards)]
+
+    def overlapping(self, first: int, n: int):
+        """(offset in [first, first+n), owner, local start, count) pieces of a global row range"""
+        for base, owner, lstart, cnt in self.segments:
+            lo, hi = max(base, first), min(base + cnt, first + n)
+            if lo < hi:
+                yield lo - first, owner, lstart + (lo - base), hi - lo
+
+
 class ShardedCorpus:
     """A collection row-sharded over the ranks of a process group, driven SPMD: every rank
     constructs it and makes the SAME calls with the SAME host arguments.
@@ -242,34 +319,30 @@ class ShardedCorpus:
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self.width = width
         self.backend = backend or CudaShardBackend(width, device if device is not None else 0)
-        self.counts = [0] * self.world            # local rows per shard (replicated bookkeeping)
-        self.segments = []                        # (global_base, owner, local_start, n), ascending global_base
-        self.total = 0
+        self.table = SegmentTable(self.world)     # replicated bookkeeping: every rank makes the same calls
         self._searcher = ShardedSearcher(None, group=group, local_search=self.backend.local_search,
                                          merge=self.backend.merge, device=getattr(self.backend, "device", None))
 
-    # ---- bookkeeping ----
+    # ---- bookkeeping (SegmentTable) ----
+    counts = property(lambda self: self.table.counts)
+    segments = property(lambda self: self.table.segments)
+    total = property(lambda self: self.table.total)
+
     def _add_segment(self, owner: int, n: int) -> int:
-        base = self.total
-        self.segments.append((base, owner, self.counts[owner], n))
-        self.counts[owner] += n
-        self.total += n
-        mine = [s for s in self.segments if s[1] == self.rank]
-        self.backend.set_segments([s[2] for s in mine], [s[0] for s in mine])
-        return base
+        return self.table.add(owner, n)
+
+    def _sync_segments(self):
+        if self.rank in self.table.dirty:
+            self.backend.set_segments(*self.table.table_of(self.rank))
+        self.table.dirty.clear()
 
     def locate(self, global_row: int):
         """(owner rank, local row) of a global row."""
-        import bisect
-        i = bisect.bisect_right([s[0] for s in self.segments], global_row) - 1
-        if i < 0 or global_row >= self.segments[i][0] + self.segments[i][3]:
-            raise IndexError(f"global row {global_row} out of range")
-        base, owner, lstart, _ = self.segments[i]
-        return owner, lstart + (global_row - base)
+        return self.table.locate(global_row)
 
     @property
     def rows(self) -> int:
-        return self.total
+        return self.table.total
 
     @property
     def live_rows(self) -> int:
@@ -285,7 +358,7 @@ class ShardedCorpus:
         n = int(rows_u8.shape[0])
         if n == 0:
             return self.total
-        owner = min(range(self.world), key=lambda r: (self.counts[r], r))      # least-full shard
+        owner = self.table.least_full()
         if owner == self.rank:
             first_local = self.backend.append(rows_u8)
             assert first_local == self.counts[owner]
@@ -323,22 +396,13 @@ class ShardedCorpus:
 
     def clear(self):
         self.backend.clear()
-        self.counts = [0] * self.world
-        self.segments = []
-        self.total = 0
+        self.table.clear()
         self.backend.set_segments([], [])
 
     # ---- query ----
     def _local_mask(self, mask_words_global):
         """global bit-per-row mask -> this shard's local mask (host-side bit gather)"""
-        bits = np.unpackbits(np.ascontiguousarray(mask_words_global, dtype=np.uint32).view(np.uint8),
-                             bitorder="little")
-        n_local = self.counts[self.rank]
-        local = np.zeros((n_local + 31) // 32 * 32, dtype=np.uint8)
-        for base, owner, lstart, n in self.segments:
-            if owner == self.rank:
-                local[lstart:lstart + n] = bits[base:base + n]
-        return np.packbits(local.reshape(-1, 32), axis=1, bitorder="little").view(np.uint32).reshape(-1)
+        return self.table.local_masks(mask_words_global, owners=[self.rank])[self.rank]
 
     def search(self, queries, k: int, metric: int = 0, filter_mask=None):
         """queries (Q, W) uint8 host array, identical on every rank; filter_mask: optional GLOBAL
@@ -352,6 +416,7 @@ class ShardedCorpus:
         mask = None
         if filter_mask is not None and self.counts[self.rank]:
             mask = self._local_mask(filter_mask)
+        self._sync_segments()
         dq = self.backend.to_device(q)
         s, r = self._searcher.search(dq, k, metric, mask)
         # copies: the searcher hands out views of its reusable exchange buffers
@@ -364,11 +429,8 @@ class ShardedCorpus:
         if n is None:
             n = self.total - first
         out = np.zeros((n, self.width), dtype=np.uint8)
-        pieces = []
-        for base, owner, lstart, cnt in self.segments:
-            lo, hi = max(base, first), min(base + cnt, first + n)
-            if lo < hi and owner == self.rank:
-                pieces.append((lo - first, self.backend.read(lstart + (lo - base), hi - lo)))
+        pieces = [(off, self.backend.read(lstart, cnt)) for off, owner, lstart, cnt in self.table.overlapping(first, n)
+                  if owner == self.rank]
         if self.world > 1:
             gathered = [None] * self.world
             self.dist.all_gather_object(gathered, pieces, group=self.group)
@@ -399,31 +461,27 @@ class LocalShardedCorpus:
             raise ValueError("need at least one GPU")
         self.shards = [_capi.Corpus(width, device=d) for d in self.devices]
         self.group = _capi.ShardGroup(self.shards)
-        self.counts = [0] * len(self.shards)
-        self.segments = []                        # (global_base, owner, local_start, n), ascending global_base
-        self.total = 0
+        self.table = SegmentTable(len(self.shards))
 
-    # ---- bookkeeping (same rules as ShardedCorpus) ----
+    # ---- bookkeeping (the same SegmentTable rules as ShardedCorpus) ----
+    counts = property(lambda self: self.table.counts)
+    segments = property(lambda self: self.table.segments)
+    total = property(lambda self: self.table.total)
+
     def _add_segment(self, owner: int, n: int) -> int:
-        base = self.total
-        self.segments.append((base, owner, self.counts[owner], n))
-        self.counts[owner] += n
-        self.total += n
-        mine = [s for s in self.segments if s[1] == owner]
-        self.group.set_segments(owner, [s[2] for s in mine], [s[0] for s in mine])
-        return base
+        return self.table.add(owner, n)
+
+    def _sync_segments(self):
+        for owner in sorted(self.table.dirty):
+            self.group.set_segments(owner, *self.table.table_of(owner))
+        self.table.dirty.clear()
 
     def locate(self, global_row: int):
-        import bisect
-        i = bisect.bisect_right([s[0] for s in self.segments], global_row) - 1
-        if i < 0 or global_row >= self.segments[i][0] + self.segments[i][3]:
-            raise IndexError(f"global row {global_row} out of range")
-        base, owner, lstart, _ = self.segments[i]
-        return owner, lstart + (global_row - base)
+        return self.table.locate(global_row)
 
     @property
     def rows(self) -> int:
-        return self.total
+        return self.table.total
 
     @property
     def live_rows(self) -> int:
@@ -435,7 +493,7 @@ class LocalShardedCorpus:
         n = int(rows_u8.shape[0])
         if n == 0:
             return self.total
-        owner = min(range(len(self.shards)), key=lambda r: (self.counts[r], r))
+        owner = self.table.least_full()
         first_local = self.shards[owner].append(rows_u8)
         assert first_local == self.counts[owner]
         return self._add_segment(owner, n)
@@ -472,32 +530,20 @@ class LocalShardedCorpus:
         for i, c in enumerate(self.shards):
             c.clear()
             self.group.set_segments(i, [], [])
-        self.counts = [0] * len(self.shards)
-        self.segments = []
-        self.total = 0
+        self.table.clear()
 
     # ---- query ----
-    def _local_masks(self, mask_words_global):
-        bits = np.unpackbits(np.ascontiguousarray(mask_words_global, dtype=np.uint32).view(np.uint8),
-                             bitorder="little")
-        local = [np.zeros((n + 31) // 32 * 32, dtype=np.uint8) for n in self.counts]
-        for base, owner, lstart, n in self.segments:
-            local[owner][lstart:lstart + n] = bits[base:base + n]
-        return [np.packbits(b.reshape(-1, 32), axis=1, bitorder="little").view(np.uint32).reshape(-1) if b.size
-                else None for b in local]
-
     def search(self, queries, k: int, metric: int = 0, filter_mask=None):
-        masks = self._local_masks(filter_mask) if filter_mask is not None else None
+        self._sync_segments()
+        masks = self.table.local_masks(filter_mask) if filter_mask is not None else None
         return self.group.search(queries, k, metric, masks)
 
     def read(self, first: int = 0, n: int | None = None) -> np.ndarray:
         if n is None:
             n = self.total - first
         out = np.zeros((n, self.width), dtype=np.uint8)
-        for base, owner, lstart, cnt in self.segments:
-            lo, hi = max(base, first), min(base + cnt, first + n)
-            if lo < hi:
-                out[lo - first:hi - first] = self.shards[owner].read(lstart + (lo - base), hi - lo)
+        for off, owner, lstart, cnt in self.table.overlapping(first, n):
+            out[off:off + cnt] = self.shards[owner].read(lstart, cnt)
         return out
 
     def close(self):
