@@ -212,6 +212,10 @@ int vl_set_timing(vl_corpus* c, int enabled);
 /* tuning knobs for experiments and tests (0 = automatic): row_splits = CTAs per query tile;
  * stages = depth of the TMA ring, or -1 to force the exact multi-pass path for k > 32 */
 int vl_set_tuning(vl_corpus* c, int row_splits, int stages);
+/* debug build only (-DVL_DEBUG_BOUNDS, `python -m vlite_b200.build --debug`): how many device-side
+ * bounds / protocol assertions failed on `device` so far and the id of the first (0 = none).  The
+ * shipped build returns VL_EINVAL.  Stands in for compute-sanitizer, which the GPU pool keeps closed. */
+int vl_debug_checks(int device, uint32_t* failures_out, uint32_t* first_id_out);
 /* which scan kernel answers vl_search on this handle.  0 = automatic (default): HAMMING batches of
  * at least 24 queries (16 for W <= 64) with k <= 16 (and the passes of k > 32) go to the tensor-core kernel
  * (tcgen05.mma kind::i8 on rows expanded bit -> int8 in shared memory; exact int32 scores), the rest

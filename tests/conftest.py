@@ -28,3 +28,16 @@ def gpu():
     _capi.load()
     assert _capi.device_count() > 0, "no sm_100 device visible to libvlite_b200.so"
     return _capi
+
+
+@pytest.fixture(autouse=True)
+def _device_assertions(request):
+    """With VLITE_B200_LIB pointing at the -DVL_DEBUG_BOUNDS build, every GPU test also asserts that no
+    device-side bounds / protocol check fired while it ran (the stand-in for compute-sanitizer)."""
+    yield
+    if "gpu" in request.keywords and os.environ.get("VLITE_B200_LIB"):
+        from vlite_b200 import _capi
+        for d in range(_capi.device_count()):
+            got = _capi.debug_checks(d)
+            assert got is not None, "VLITE_B200_LIB is not a debug build"
+            assert got[0] == 0, f"{got[0]} device-side check(s) failed on GPU {d}, first id {got[1]}"

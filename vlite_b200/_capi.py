@@ -48,10 +48,11 @@ def load():
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(LIB_PATH):
+    path = os.environ.get("VLITE_B200_LIB") or LIB_PATH      # e.g. the -DVL_DEBUG_BOUNDS build
+    if path == LIB_PATH and not os.path.exists(LIB_PATH):
         from . import build as _build
         _build.build()
-    L = ctypes.CDLL(LIB_PATH)
+    L = ctypes.CDLL(path)
     c_void_p, c_int, c_u64 = ctypes.c_void_p, ctypes.c_int, ctypes.c_uint64
     P = ctypes.POINTER
     sig = {
@@ -99,6 +100,7 @@ def load():
         "vl_set_timing": (c_int, [c_void_p, c_int]),
         "vl_set_tuning": (c_int, [c_void_p, c_int, c_int]),
         "vl_set_scan_path": (c_int, [c_void_p, c_int]),
+        "vl_debug_checks": (c_int, [c_int, P(ctypes.c_uint32), P(ctypes.c_uint32)]),
         "vl_exchange_create": (c_int, [c_int, c_int, c_int, c_u64, P(c_void_p)]),
         "vl_exchange_handle": (c_int, [c_void_p, c_void_p]),
         "vl_exchange_attach": (c_int, [c_void_p, c_int, c_void_p]),
@@ -508,6 +510,14 @@ def microbench(kind: int, iters: int = 4096, device: int = 0):
     ops, ms = ctypes.c_double(), ctypes.c_double()
     check(load().vl_microbench(device, kind, iters, ctypes.byref(ops), ctypes.byref(ms)))
     return ops.value, ms.value
+
+
+def debug_checks(device: int = 0):
+    """(failures, id of the first) from the -DVL_DEBUG_BOUNDS build; None in the shipped build."""
+    n, first = ctypes.c_uint32(), ctypes.c_uint32()
+    if load().vl_debug_checks(device, ctypes.byref(n), ctypes.byref(first)) != 0:
+        return None
+    return n.value, first.value
 
 
 def device_count() -> int:

@@ -58,5 +58,16 @@ def build(force: bool = False, verbose: bool = False, out: str | None = None, ex
     return out
 
 
+DEBUG_LIB_PATH = os.path.join(LIB_DIR, "libvlite_b200_dbg.so")
+
+
+def build_debug() -> str:
+    """the bounds-checked twin (-DVL_DEBUG_BOUNDS); load it with VLITE_B200_LIB=<path>"""
+    return build(out=DEBUG_LIB_PATH, extra_flags=["-DVL_DEBUG_BOUNDS"])
+
+
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv))
+    if "--debug" in sys.argv:
+        print(build_debug())
+    else:
+        print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv))

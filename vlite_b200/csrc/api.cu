@@ -842,6 +842,24 @@ extern "C" int vl_set_tuning(vl_corpus* c, int row_splits, int stages) {
     return VL_OK;
 }
 
+extern "C" int vl_debug_checks(int device, uint32_t* failures_out, uint32_t* first_id_out) {
+#ifdef VL_DEBUG_BOUNDS
+    TRY(check_device(device, nullptr));
+    DeviceGuard g(device);
+    unsigned int h[2] = {0, 0};
+    CU(cudaDeviceSynchronize());
+    CU(cudaMemcpyFromSymbol(h, vl::g_vl_dcheck, sizeof h));
+    if (failures_out) *failures_out = h[0];
+    if (first_id_out) *first_id_out = h[1];
+    return VL_OK;
+#else
+    (void)device;
+    if (failures_out) *failures_out = 0;
+    if (first_id_out) *first_id_out = 0;
+    return fail(VL_EINVAL, "not a debug build: rebuild with -DVL_DEBUG_BOUNDS (python -m vlite_b200.build --debug)");
+#endif
+}
+
 extern "C" int vl_set_scan_path(vl_corpus* c, int path) {
     if (!c) return fail(VL_EINVAL, "corpus is NULL");
     if (path < 0 || path > 3) return fail(VL_EINVAL, "scan path must be 0 (auto), 1 (integer pipes), 2 or 3 (tensor cores, 1 or 2 CTAs per tile)");

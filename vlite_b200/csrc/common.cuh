@@ -10,6 +10,24 @@
 
 namespace vl {
 
+// ---- debug build (-DVL_DEBUG_BOUNDS): device-side bounds / protocol assertions -----------------
+// compute-sanitizer is closed on the GPU pool, so the kernels carry their own checks: every index
+// into a list, candidate buffer, shared-memory ring, TMEM column range or document store, and the
+// pipeline distances the mbarrier rings rely on, are asserted in this build.  A failed check does
+// not trap (a trap would take the context down): it bumps a counter and records the id of the
+// first failure, which vl_debug_checks() returns to the host.  Off (zero cost) in the shipped build.
+#ifdef VL_DEBUG_BOUNDS
+__device__ unsigned int g_vl_dcheck[2];   // [0] failures so far, [1] id of the first one
+#define VL_DCHECK(cond, id)                                                   \
+    do {                                                                      \
+        if (!(cond)) {                                                        \
+            if (atomicAdd(&::vl::g_vl_dcheck[0], 1u) == 0u) ::vl::g_vl_dcheck[1] = (id); \
+        }                                                                     \
+    } while (0)
+#else
+#define VL_DCHECK(cond, id) ((void)0)
+#endif
+
 constexpr uint32_t kSentinelScore = 0xFFFFFFFFu;
 constexpr uint64_t kSentinelRow = 0xFFFFFFFFFFFFFFFFull;
 constexpr unsigned kFullMask = 0xFFFFFFFFu;
@@ -40,6 +58,18 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
         "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+// non-blocking probe (debug assertions only)
+__device__ __forceinline__ bool mbar_test_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(ok)
         : "r"(smem_u32(bar)), "r"(parity)

@@ -44,6 +44,7 @@ merge_topk_kernel(const uint32_t* __restrict__ scores, const uint64_t* __restric
         cs[j] = kSentinelScore;
         cr[j] = kSentinelRow;
         if (l < n_lists && hd[j] < k_in) {
+            VL_DCHECK(l >= 0 && hd[j] >= 0 && q < n_queries, 301);
             const size_t idx = (size_t)q * k_in + hd[j];
             cr[j] = rows[(size_t)l * row_list_stride + idx];
             cs[j] = scores[(size_t)l * score_list_stride + idx];

@@ -206,6 +206,7 @@ __device__ __forceinline__ void expand_chunks(const uint4& x, uint32_t keep, uin
             case 6: o0 = expand_pm1<6>(x.x, keep); o1 = expand_pm1<6>(x.y, keep); o2 = expand_pm1<6>(x.z, keep); o3 = expand_pm1<6>(x.w, keep); break;
             default: o0 = expand_pm1<7>(x.x, keep); o1 = expand_pm1<7>(x.y, keep); o2 = expand_pm1<7>(x.z, keep); o3 = expand_pm1<7>(x.w, keep); break;
         }
+        VL_DCHECK(r7 < 8u && (slab_row_saddr & 127u) == 0u, 201);   // a 128 B row of a 1024 B-aligned slab
         sts128(slab_row_saddr + (((uint32_t)c ^ r7) << 4), o0, o1, o2, o3);
     }
 }
@@ -406,6 +407,7 @@ mma_scan_kernel(const __grid_constant__ CUtensorMap tmap, const ScanParams p) {
             for (int ch = 0; ch < NT / 32; ++ch) {
                 uint32_t vu[32];
                 __syncwarp();   // tcgen05.ld is warp-aligned: reconverge after a divergent insert
+                VL_DCHECK(buf * NT + (uint32_t)ch * 32u + 32u <= (uint32_t)Cfg::TMEM_COLS, 202);
                 tmem_ld32(tmem_base + (lane_base << 16) + buf * NT + (uint32_t)ch * 32u, vu);
                 tmem_ld_wait();
                 if (ch == NT / 32 - 1) {
@@ -446,11 +448,13 @@ mma_scan_kernel(const __grid_constant__ CUtensorMap tmap, const ScanParams p) {
                     for (int e = 0; e < 2; ++e) s2[e] = (pc & 2) ? s4[e + 2] : s4[e];
                     const int pv = (pc & 1) ? s2[1] : s2[0];
                     const uint32_t rit = (uint32_t)ch * 32u + (uint32_t)pc;      // row in tile
+                    VL_DCHECK(rit < (uint32_t)NT && (rit >> 5) < (uint32_t)MW, 203);
                     const uint32_t wv = __shfl_sync(kFullMask, vw, (int)(rit >> 5));
                     if (mine && pv > thrd && ((wv >> (rit & 31)) & 1u)) {
                         const uint32_t score = (uint32_t)(K - pv) >> 1;
                         const uint32_t lrow = t * (uint32_t)NT + rit;
                         const uint64_t key = ((uint64_t)score << 32) | lrow;
+                        VL_DCHECK(pv >= -K && pv <= K && ((K - pv) & 1) == 0 && lrow < p.n_rows, 204);   // a +-1 dot product of K terms
                         if constexpr (COLLECT) {
                             const uint32_t slot = atomicAdd(p.collect_count + qg, 1u);
                             if (slot < p.collect_cap) p.collect_keys[(size_t)qg * p.collect_cap + slot] = key;
@@ -511,6 +515,7 @@ mma_scan_kernel(const __grid_constant__ CUtensorMap tmap, const ScanParams p) {
                 for (int qq = h; qq < kMmaQT; qq += 64) {
                     const int qg = q0 + qq;
                     if (qg >= p.n_queries) continue;
+                    VL_DCHECK(qq < kMmaQT, 206);
                     const uint32_t* hq = p.hist + (size_t)qg * kHistWords;
                     const uint4* coarse = reinterpret_cast<const uint4*>(hq + kHistFine);
                     uint32_t cum = 0, before = 0;
@@ -578,9 +583,12 @@ mma_scan_kernel(const __grid_constant__ CUtensorMap tmap, const ScanParams p) {
 #pragma unroll
             for (int j = 0; j < SLABS; ++j, ++g) {
                 const uint32_t st = g % kMmaBStages;
+                VL_DCHECK(rot < (uint32_t)CHUNKS && r < kMmaRows, 205);
                 const uint4 x = lds128(pk_saddr + (uint32_t)s * Cfg::PK_BYTES + (((uint32_t)j ^ rot) << 4));
                 if (g >= (uint32_t)kMmaBStages) mbar_wait(&b_empty[st], ((g / kMmaBStages) - 1) & 1);
                 const uint32_t row_saddr = b_saddr + st * kMmaSlabBytes;
+                // ring protocol: nobody may have declared THIS generation of the slab full before it is written
+                VL_DCHECK(CG == 2 || !mbar_test_wait(&b_full[st], (g / kMmaBStages) & 1), 207);
                 if (half == 0)
                     expand_chunks<0, 4>(x, keep, row_saddr, r7);
                 else

@@ -137,6 +137,7 @@ __global__ void __launch_bounds__(kRescoreThreads) rescore_kernel(const RescoreP
 #pragma unroll
                 for (int off = 16; off > 0; off >>= 1) facc += __shfl_xor_sync(kFullMask, facc, off);
             }
+            VL_DCHECK(c0 + u < p.n_sort && grow[u] - p.base_row < p.n_docs, 401);
             if (lane == 0) {
                 s_score[c0 + u] = (float)facc;
                 s_row[c0 + u] = grow[u];

@@ -210,6 +210,7 @@ __device__ __noinline__ uint32_t warp_list_insert(uint32_t* ls, uint32_t* li, in
         }
         __syncwarp();
     }
+    VL_DCHECK(pos >= 0 && pos < k, 101);
     if (lane == 0) {
         ls[pos] = s;
         li[pos] = idx;
@@ -354,6 +355,7 @@ scan_topk_kernel(const __grid_constant__ CUtensorMap tmap, const ScanParams p) {
         const int s = i % stages;
         const uint32_t t = (tile_begin + i) * p.tile_stride;
         const uint32_t row0 = t * TR;
+        VL_DCHECK(i < my_tiles && (uint64_t)row0 < (uint64_t)p.n_rows + TR, 102);   // never a tile past the shard
         const uint32_t mask_bytes = MASKW * 4;
         // the tile arrives hardware-swizzled (16 B chunk index ^= row bits): rows past n_rows are
         // zero-filled by the TMA unit and the whole box is always counted
@@ -479,6 +481,9 @@ scan_topk_kernel(const __grid_constant__ CUtensorMap tmap, const ScanParams p) {
         }
         mbar_wait(&s_full[s], (i / stages) & 1);
         const uint32_t* m = s_masks + s * 2 * MASKW;
+        // ring protocol: the stage being read must not have been handed to a tile `stages` ahead yet --
+        // the refill of this stage waits on s_empty, which this warp has not arrived on for tile i
+        VL_DCHECK(!mbar_test_wait(&s_empty[s], (i / stages) & 1), 103);
 
 #pragma unroll 1
         for (int st = 0; st < STEPS; ++st) {
@@ -613,6 +618,7 @@ scan_topk_kernel(const __grid_constant__ CUtensorMap tmap, const ScanParams p) {
                             if (lane == __ffs(sel) - 1) base = atomicAdd(p.collect_count + qg, (uint32_t)__popc(sel));
                             base = __shfl_sync(kFullMask, base, __ffs(sel) - 1);
                             const uint32_t slot = base + (uint32_t)__popc(sel & ((1u << lane) - 1));
+                            VL_DCHECK(qg < p.n_queries, 104);
                             if (mine && slot < p.collect_cap)
                                 p.collect_keys[(size_t)qg * p.collect_cap + slot] =
                                     ((unsigned long long)v << 32) | idx;
@@ -734,6 +740,7 @@ scan_topk_kernel(const __grid_constant__ CUtensorMap tmap, const ScanParams p) {
         const int q = qtile * QT + wq * C + c;
         if (q >= p.n_queries) continue;
         const size_t o = ((size_t)list_id * p.n_queries + q) * k;
+        VL_DCHECK(list_id < n_splits * WR && q < p.n_queries, 105);
         for (int e = lane; e < k; e += 32) {
             const uint32_t idx = li[c * k + e];
             p.part_scores[o + e] = ls[c * k + e];
