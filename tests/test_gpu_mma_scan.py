@@ -11,21 +11,22 @@ from oracle import cscan, synth
 
 pytestmark = pytest.mark.gpu
 
-HAMMING = 0
+HAMMING, XORSUM = 0, 1
 PATHS = [2, 3]
 
 
-def _check(c, corpus, queries, k, mask_words=None, base_row=0):
-    s, r = c.search(queries, k, HAMMING, mask_words)
-    es, er = cscan.search(queries, corpus, k, HAMMING, mask_words, base_row)
+def _check(c, corpus, queries, k, mask_words=None, base_row=0, metric=HAMMING):
+    s, r = c.search(queries, k, metric, mask_words)
+    es, er = cscan.search(queries, corpus, k, metric, mask_words, base_row)
     np.testing.assert_array_equal(s, es)
     np.testing.assert_array_equal(r, er)
 
 
 @pytest.mark.parametrize("path", PATHS)
+@pytest.mark.parametrize("metric", [HAMMING, XORSUM])
 @pytest.mark.parametrize("width", [128, 64, 32])
 @pytest.mark.parametrize("nq", [1, 100, 128, 129, 300])
-def test_topk_query_tilings(gpu, path, width, nq):
+def test_topk_query_tilings(gpu, path, metric, width, nq):
     n, k = 20011, 10   # ragged: not a multiple of the 128 / 256-row tile
     corpus = synth.corpus_rows(5, 0, n, width)
     queries = synth.uniform_queries(6, nq, width)
@@ -33,7 +34,27 @@ def test_topk_query_tilings(gpu, path, width, nq):
     with gpu.Corpus(width) as c:
         c.append(corpus)
         c.set_scan_path(path)
-        _check(c, corpus, queries, k)
+        _check(c, corpus, queries, k, metric=metric)
+
+
+@pytest.mark.parametrize("path", PATHS)
+@pytest.mark.parametrize("width", [128, 64, 32])
+def test_xorsum_extreme_scores_and_weights(gpu, path, width):
+    """XORSUM on the tensor cores = a +-weight contraction with bit 7 counted as 64 + 64: rows that differ
+    from the query in exactly one bit position per byte must score that bit's weight times W, the
+    complement 255 W, the query itself 0."""
+    rng = np.random.default_rng(3)
+    q = rng.integers(0, 256, size=(1, width), dtype=np.uint8)
+    rows = [q[0] ^ np.uint8(1 << b) for b in range(8)] + [q[0] ^ np.uint8(0xFF), q[0].copy(), q[0] ^ np.uint8(0x81)]
+    corpus = np.concatenate([np.stack(rows), synth.corpus_rows(31, 0, 3000, width)])
+    with gpu.Corpus(width) as c:
+        c.append(corpus)
+        c.set_scan_path(path)
+        got = {int(r): int(s) for s, r in zip(*[a[0] for a in c.search(np.repeat(q, 70, 0), 16, XORSUM)])}
+        assert got[9] == 0 and [got[b] for b in range(6)] == [width << b for b in range(6)]
+        _check(c, corpus, np.repeat(q, 3, 0), len(corpus) if len(corpus) <= 16 else 16, metric=XORSUM)
+        full = c.scores(q[0], XORSUM)
+        assert full[8] == 255 * width and full[10] == 0x81 * width and full[7] == 128 * width
 
 
 @pytest.mark.parametrize("path", PATHS)
@@ -59,6 +80,7 @@ def test_duplicates_ties_break_on_row(gpu, path):
         c.set_scan_path(path)
         _check(c, corpus, queries, 10)
         _check(c, corpus, queries, 16)
+        _check(c, corpus, queries, 10, metric=XORSUM)
 
 
 @pytest.mark.parametrize("path", PATHS)
@@ -81,6 +103,10 @@ def test_filter_mask_and_tombstones(gpu, path, sel):
         np.testing.assert_array_equal(r, er)
         s, r = c.search(queries, 10, HAMMING)
         es, er = cscan.search(queries, corpus, 10, HAMMING, synth.pack_mask(live))
+        np.testing.assert_array_equal(s, es)
+        np.testing.assert_array_equal(r, er)
+        s, r = c.search(queries, 10, XORSUM, synth.pack_mask(valid))
+        es, er = cscan.search(queries, corpus, 10, XORSUM, synth.pack_mask(valid & live))
         np.testing.assert_array_equal(s, es)
         np.testing.assert_array_equal(r, er)
 
@@ -107,20 +133,21 @@ def test_matches_integer_pipe_kernel_and_base_row(gpu, path):
 
 
 @pytest.mark.parametrize("path", PATHS)
+@pytest.mark.parametrize("metric", [HAMMING, XORSUM])
 @pytest.mark.parametrize("k", [100, 1000])
-def test_large_k_collect_pass_on_tensor_cores(gpu, path, k):
+def test_large_k_collect_pass_on_tensor_cores(gpu, path, metric, k):
     n = 200_000
     corpus = synth.corpus_rows(16, 0, n, 128)
     queries = synth.uniform_queries(17, 130, 128)
     with gpu.Corpus(128) as c:
         c.append(corpus)
         c.set_scan_path(path)
-        _check(c, corpus, queries, k)
+        _check(c, corpus, queries, k, metric=metric)
 
 
 def test_automatic_dispatch_is_bit_identical(gpu):
-    """auto mode: Q >= 24 (16 at W <= 64) with k <= 16 goes to the tensor-core kernel, everything else to the
-    integer-pipe kernel; XORSUM never does."""
+    """auto mode: Q >= 24 (16 at W <= 64) with k <= 16 goes to the tensor-core kernel (both metrics),
+    everything else to the integer-pipe kernel."""
     n = 50_000
     corpus = synth.corpus_rows(18, 0, n, 64)
     queries = synth.uniform_queries(19, 260, 64)
@@ -128,7 +155,4 @@ def test_automatic_dispatch_is_bit_identical(gpu):
         c.append(corpus)
         for nq in (15, 16, 63, 64, 260):
             _check(c, corpus, queries[:nq], 10)
-        s, r = c.search(queries, 10, 1)
-        es, er = cscan.search(queries, corpus, 10, 1)
-        np.testing.assert_array_equal(s, es)
-        np.testing.assert_array_equal(r, er)
+            _check(c, corpus, queries[:nq], 10, metric=XORSUM)

@@ -44,7 +44,7 @@ exchange_push_kernel(const uint4* __restrict__ src, uint64_t n16, PeerPtrs peers
     if (threadIdx.x == 0) st_release_sys(reinterpret_cast<uint32_t*>(base + flag_off), epoch);
 }
 
-// the merge of merge.cuh behind an acquire of every rank's flag (spins at most ~2 s, then reports)
+// the merge of merge.cuh behind an acquire of every rank's flag (spins at most ~2 minutes, then reports)
 __global__ void __launch_bounds__(kMergeWarps * 32)
 exchange_merge_kernel(const uint32_t* flags, int world, uint32_t epoch, int* timeout_flag_host,
                       const uint32_t* __restrict__ scores, const uint64_t* __restrict__ rows, int n_queries, int k,
@@ -53,7 +53,7 @@ exchange_merge_kernel(const uint32_t* flags, int world, uint32_t epoch, int* tim
     if (threadIdx.x < world) {
         const long long t0 = clock64();
         while (ld_acquire_sys(flags + threadIdx.x) != epoch) {
-            if (clock64() - t0 > 4000000000ll) {
+            if (clock64() - t0 > 240000000000ll) {   // ~2 minutes: a peer may be busy on its host for seconds
                 *timeout_flag_host = 1;
                 break;
             }

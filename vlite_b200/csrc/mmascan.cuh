@@ -173,51 +173,69 @@ __host__ __device__ constexpr uint32_t umma_idesc_i8(int m, int n) {
     return (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 
-// bit -> int8: byte i of the result is -1 (0xFF) if bit (8 i + 7 - s) of x is set, else +1 (0x01);
-// `keep` = 0 zeroes the word (masked row).  SHL + PRMT (sign replicate) + LOP3.
-template <int S>
-__device__ __forceinline__ uint32_t expand_pm1(uint32_t x, uint32_t keep) {
+// ---- bit -> int8 expansion -----------------------------------------------------------------------
+// Element order of an expanded row ("bit planes"): e = p * W + byte, p = 0..7 <-> bit (7 - p) of every
+// byte -- the same permutation of K for corpus rows and queries, so the contraction is unchanged.
+// Output chunk g (16 int8) is plane p = g / (W/16), bytes 16 * (g % (W/16)) .. + 15, i.e. four packed
+// words shifted left by p with the sign of each byte replicated (PRMT) -> -1 (bit set) / +1.
+// Rows are always +-1.  Queries are +-1 for HAMMING; for XORSUM (score = sum of byte values of q ^ e,
+// vlite/model.py:82) they carry the bit's weight: +-2^(7-p) for p >= 1 and +-64 for plane 0, whose
+// k-steps the MMA thread issues TWICE (64 + 64 = 128: +128 does not fit an int8).  Then
+//     sum_e a_e q_e = sum_bits weight * (+1 equal, -1 different)  =>  score = (255 W - dot) / 2.
+template <int P, bool WEIGHTED>
+__device__ __forceinline__ uint32_t expand_plane(uint32_t x, uint32_t keep) {
     // prmt selector nibble 8 + i: replicate the sign bit of byte i (the __byte_perm intrinsic masks
     // that mode bit off, hence inline PTX)
     uint32_t m;
-    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(m) : "r"(x << S), "r"(0u), "r"(0xBA98u));
-    return (m | 0x01010101u) & keep;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(m) : "r"(x << P), "r"(0u), "r"(0xBA98u));
+    if constexpr (!WEIGHTED) {
+        return (m | 0x01010101u) & keep;
+    } else {
+        constexpr uint32_t w = P == 0 ? 64u : (1u << (7 - P));
+        constexpr uint32_t POS = w * 0x01010101u, NEG = ((256u - w) & 0xFFu) * 0x01010101u;
+        return ((POS & ~m) | (NEG & m)) & keep;
+    }
 }
 __device__ __forceinline__ void sts128(uint32_t saddr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
     asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
-// one 16 B packed chunk (4 words) of a row -> K-slab chunks [C0, C0 + NC) of that row.  Element
-// (chunk c, word t, byte i) of the slab is bit (8 i + 7 - c) of packed word t: the same permutation
-// of K for corpus rows and queries, so the contraction is unchanged.
-template <int C0, int NC>
-__device__ __forceinline__ void expand_chunks(const uint4& x, uint32_t keep, uint32_t slab_row_saddr, uint32_t r7) {
-#pragma unroll
-    for (int cc = 0; cc < NC; ++cc) {
-        constexpr int kBase = C0;
-        const int c = kBase + cc;
-        uint32_t o0, o1, o2, o3;
-        switch (c) {   // c is a compile-time constant after unrolling
-            case 0: o0 = expand_pm1<0>(x.x, keep); o1 = expand_pm1<0>(x.y, keep); o2 = expand_pm1<0>(x.z, keep); o3 = expand_pm1<0>(x.w, keep); break;
-            case 1: o0 = expand_pm1<1>(x.x, keep); o1 = expand_pm1<1>(x.y, keep); o2 = expand_pm1<1>(x.z, keep); o3 = expand_pm1<1>(x.w, keep); break;
-            case 2: o0 = expand_pm1<2>(x.x, keep); o1 = expand_pm1<2>(x.y, keep); o2 = expand_pm1<2>(x.z, keep); o3 = expand_pm1<2>(x.w, keep); break;
-            case 3: o0 = expand_pm1<3>(x.x, keep); o1 = expand_pm1<3>(x.y, keep); o2 = expand_pm1<3>(x.z, keep); o3 = expand_pm1<3>(x.w, keep); break;
-            case 4: o0 = expand_pm1<4>(x.x, keep); o1 = expand_pm1<4>(x.y, keep); o2 = expand_pm1<4>(x.z, keep); o3 = expand_pm1<4>(x.w, keep); break;
-            case 5: o0 = expand_pm1<5>(x.x, keep); o1 = expand_pm1<5>(x.y, keep); o2 = expand_pm1<5>(x.z, keep); o3 = expand_pm1<5>(x.w, keep); break;
-            case 6: o0 = expand_pm1<6>(x.x, keep); o1 = expand_pm1<6>(x.y, keep); o2 = expand_pm1<6>(x.z, keep); o3 = expand_pm1<6>(x.w, keep); break;
-            default: o0 = expand_pm1<7>(x.x, keep); o1 = expand_pm1<7>(x.y, keep); o2 = expand_pm1<7>(x.z, keep); o3 = expand_pm1<7>(x.w, keep); break;
-        }
-        VL_DCHECK(r7 < 8u && (slab_row_saddr & 127u) == 0u, 201);   // a 128 B row of a 1024 B-aligned slab
-        sts128(slab_row_saddr + (((uint32_t)c ^ r7) << 4), o0, o1, o2, o3);
+// output chunk G of one row from its packed words pk[W/4] (registers): stored at chunk position
+// (G % 8) ^ (row & 7) of the row's 128 B in slab G / 8 (the UMMA 128 B-swizzle layout)
+template <int W, int G, bool WEIGHTED>
+__device__ __forceinline__ void emit_chunk(const uint32_t (&pk)[W / 4], uint32_t keep, uint32_t slab0_row_saddr, uint32_t r7) {
+    constexpr int CHUNKS = W / 16, P = G / CHUNKS, B = G % CHUNKS;
+    const uint32_t o0 = expand_plane<P, WEIGHTED>(pk[4 * B + 0], keep), o1 = expand_plane<P, WEIGHTED>(pk[4 * B + 1], keep);
+    const uint32_t o2 = expand_plane<P, WEIGHTED>(pk[4 * B + 2], keep), o3 = expand_plane<P, WEIGHTED>(pk[4 * B + 3], keep);
+    VL_DCHECK(r7 < 8u && (slab0_row_saddr & 127u) == 0u, 201);   // a 128 B row of a 1024 B-aligned slab
+    sts128(slab0_row_saddr + (uint32_t)(G / 8) * kMmaSlabBytes + ((((uint32_t)(G % 8)) ^ r7) << 4), o0, o1, o2, o3);
+}
+// the four chunks [8 J + 4 H, 8 J + 4 H + 4) of slab J (slab_row_saddr addresses the row inside THAT slab's buffer)
+template <int W, int J, int H, bool WEIGHTED>
+__device__ __forceinline__ void emit_half_slab(const uint32_t (&pk)[W / 4], uint32_t keep, uint32_t slab_row_saddr, uint32_t r7) {
+    const uint32_t base = slab_row_saddr - (uint32_t)J * kMmaSlabBytes;   // emit_chunk adds (G / 8) slabs back
+    emit_chunk<W, 8 * J + 4 * H + 0, WEIGHTED>(pk, keep, base, r7);
+    emit_chunk<W, 8 * J + 4 * H + 1, WEIGHTED>(pk, keep, base, r7);
+    emit_chunk<W, 8 * J + 4 * H + 2, WEIGHTED>(pk, keep, base, r7);
+    emit_chunk<W, 8 * J + 4 * H + 3, WEIGHTED>(pk, keep, base, r7);
+}
+template <int W, int H, bool WEIGHTED, int J = 0>
+__device__ __forceinline__ void emit_half_slab_rt(int j, const uint32_t (&pk)[W / 4], uint32_t keep, uint32_t slab_row_saddr,
+                                                  uint32_t r7) {
+    if constexpr (J < W / 16) {
+        if (j == J) emit_half_slab<W, J, H, WEIGHTED>(pk, keep, slab_row_saddr, r7);
+        else emit_half_slab_rt<W, H, WEIGHTED, J + 1>(j, pk, keep, slab_row_saddr, r7);
     }
 }
 
-template <int W, int CG, bool COLLECT>
+template <int W, int CG, bool COLLECT, int METRIC>
 __global__ void __launch_bounds__(kMmaThreads, 1)
 mma_scan_kernel(const __grid_constant__ CUtensorMap tmap, const ScanParams p) {
     using Cfg = MmaCfg<W, CG>;
     if (p.gate != nullptr && *p.gate == 0) return;   // uniform over the grid (and over a cluster)
-    constexpr int SLABS = Cfg::SLABS, NT = Cfg::NT, MW = Cfg::MW, K = Cfg::K;
+    constexpr int SLABS = Cfg::SLABS, NT = Cfg::NT, MW = Cfg::MW;
     constexpr int CHUNKS = W / 16;
+    constexpr bool XS = METRIC == kXorSum;
+    constexpr int K = XS ? 255 * W : 8 * W;      // score = (K - dot) / 2: the dot product of a perfect match
 
     extern __shared__ uint8_t smem_raw[];
     // the dynamic shared window is only 16 B aligned by contract: swizzled operands want 1024 B
@@ -268,25 +286,30 @@ mma_scan_kernel(const __grid_constant__ CUtensorMap tmap, const ScanParams p) {
     if (threadIdx.x < kMmaQT) s_bound[threadIdx.x] = kSentinelScore;
     if (warp == 2) tmem_alloc<CG>(s_tmem, (uint32_t)Cfg::TMEM_COLS);
 
-    // ---- A operand: expand this CTA's queries once (zeros past n_queries) ----
+    // ---- A operand: expand this CTA's queries once (zeros past n_queries; XORSUM: weighted) ----
     {
-        const uint32_t a_saddr = smem_u32(sA);
-        for (int it = threadIdx.x; it < kMmaQT * SLABS * 2; it += kMmaThreads) {
-            const int ql = it % kMmaQT;
-            const int j = (it / kMmaQT) % SLABS;
-            const int h = it / (kMmaQT * SLABS);
-            const int qg = q0 + ql;
-            uint4 x = make_uint4(0, 0, 0, 0);
-            uint32_t keep = 0;
-            if (qg < p.n_queries) {
-                x = *reinterpret_cast<const uint4*>(p.queries + (size_t)qg * W + j * 16);
-                keep = 0xFFFFFFFFu;
+        const int ql = threadIdx.x % kMmaQT;        // 4 threads per query, each a quarter of the half-slabs
+        const int part = threadIdx.x / kMmaQT;
+        const int qg = q0 + ql;
+        uint32_t pk[W / 4];
+        uint32_t keep = 0;
+#pragma unroll
+        for (int i = 0; i < W / 4; ++i) pk[i] = 0;
+        if (qg < p.n_queries) {
+            const uint4* src = reinterpret_cast<const uint4*>(p.queries + (size_t)qg * W);
+#pragma unroll
+            for (int i = 0; i < CHUNKS; ++i) {
+                const uint4 v = src[i];
+                pk[4 * i] = v.x, pk[4 * i + 1] = v.y, pk[4 * i + 2] = v.z, pk[4 * i + 3] = v.w;
             }
-            const uint32_t row_saddr = a_saddr + (uint32_t)j * kMmaSlabBytes + (uint32_t)ql * 128u;
-            if (h == 0)
-                expand_chunks<0, 4>(x, keep, row_saddr, (uint32_t)(ql & 7));
-            else
-                expand_chunks<4, 4>(x, keep, row_saddr, (uint32_t)(ql & 7));
+            keep = 0xFFFFFFFFu;
+        }
+        const uint32_t row_saddr = smem_u32(sA) + (uint32_t)ql * 128u;
+        const uint32_t r7 = (uint32_t)(ql & 7);
+        for (int u = part; u < SLABS * 2; u += kMmaThreads / kMmaQT) {
+            const int j = u >> 1;
+            if (u & 1) emit_half_slab_rt<W, 1, XS>(j, pk, keep, row_saddr + (uint32_t)j * kMmaSlabBytes, r7);
+            else emit_half_slab_rt<W, 0, XS>(j, pk, keep, row_saddr + (uint32_t)j * kMmaSlabBytes, r7);
         }
         fence_proxy_async_smem();
     }
@@ -335,8 +358,13 @@ mma_scan_kernel(const __grid_constant__ CUtensorMap tmap, const ScanParams p) {
                     const uint64_t ad = umma_desc_sw128(a_saddr + (uint32_t)j * kMmaSlabBytes);
                     const uint64_t bd = umma_desc_sw128(b_saddr + st * kMmaSlabBytes);
 #pragma unroll
-                    for (int kk = 0; kk < 4; ++kk)   // K = 32 int8 = 32 B per instruction: +2 in the address field
+                    for (int kk = 0; kk < 4; ++kk) {   // K = 32 int8 = 32 B per instruction: +2 in the address field
                         umma_i8<CG>(d_tmem, ad + (uint64_t)(kk * 2), bd + (uint64_t)(kk * 2), idesc, (j | kk) != 0 ? 1u : 0u);
+                        // XORSUM: the elements of plane 0 (bit 7 of every byte, the first W of the row) weigh
+                        // 128 = 64 + 64: their k-steps are accumulated twice
+                        if (XS && j * 128 + kk * 32 < W)
+                            umma_i8<CG>(d_tmem, ad + (uint64_t)(kk * 2), bd + (uint64_t)(kk * 2), idesc, 1u);
+                    }
                     umma_commit<CG>(&b_empty[st]);
                 }
                 umma_commit<CG>(&acc_full[buf]);
@@ -364,7 +392,7 @@ mma_scan_kernel(const __grid_constant__ CUtensorMap tmap, const ScanParams p) {
         constexpr int kNever = 1 << 30;
         auto to_dot = [&](uint32_t th) -> int {   // score < th  <=>  dot > K - 2 th
             if (!q_ok) return kNever;
-            return (th > (uint32_t)K) ? -kNever : K - 2 * (int)th;
+            return (th > (uint32_t)K) ? -kNever : K - 2 * (int)th;   // (K = 8 W or 255 W: the largest score)
         };
         int thrd = to_dot(thr);
         const bool use_tau = !COLLECT && q_ok;
@@ -469,7 +497,7 @@ mma_scan_kernel(const __grid_constant__ CUtensorMap tmap, const ScanParams p) {
                             thrd = to_dot(thr);
                             dirty = true;
                             if (use_hist) {
-                                const uint32_t b = min(score, (uint32_t)(kHistFine - 1));
+                                const uint32_t b = min(score >> p.hist_shift, (uint32_t)(kHistFine - 1));
                                 atomicAdd(hq + b, 1u);
                                 atomicAdd(hq + kHistFine + (b >> 5), 1u);
                             }
@@ -548,7 +576,7 @@ mma_scan_kernel(const __grid_constant__ CUtensorMap tmap, const ScanParams p) {
                         }
                     }
                     // (the fine bins can lag the coarse ones: x < 0 then; the last bucket is open-ended)
-                    if (x >= 0 && x < kHistFine - 1) s_bound[qq] = (uint32_t)x + 1u;
+                    if (x >= 0 && x < kHistFine - 1) s_bound[qq] = ((uint32_t)x + 1u) << p.hist_shift;   // k-th best < this
                 }
                 // sleep in slices so that the end of the scan is noticed within ~2 us
                 for (uint32_t slept = 0; slept < nap && *reinterpret_cast<volatile uint32_t*>(s_done) < 4u; slept += 2000)
@@ -580,19 +608,28 @@ mma_scan_kernel(const __grid_constant__ CUtensorMap tmap, const ScanParams p) {
             uint32_t wv = m[mword];
             if (has_filter) wv &= m[MW + mword];
             const uint32_t keep = ((wv >> lane) & 1u) ? 0xFFFFFFFFu : 0u;
+            // the whole packed row goes to registers (every slab needs one bit plane of ALL its bytes) and
+            // the packed box is handed back to the TMA producer before the expansion starts
+            uint32_t pk[W / 4];
+            VL_DCHECK(rot < (uint32_t)CHUNKS && r < kMmaRows, 205);
+#pragma unroll
+            for (int c = 0; c < CHUNKS; ++c) {
+                const uint4 x = lds128(pk_saddr + (uint32_t)s * Cfg::PK_BYTES + (((uint32_t)c ^ rot) << 4));
+                pk[4 * c] = x.x, pk[4 * c + 1] = x.y, pk[4 * c + 2] = x.z, pk[4 * c + 3] = x.w;
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&pk_empty[s]);
 #pragma unroll
             for (int j = 0; j < SLABS; ++j, ++g) {
                 const uint32_t st = g % kMmaBStages;
-                VL_DCHECK(rot < (uint32_t)CHUNKS && r < kMmaRows, 205);
-                const uint4 x = lds128(pk_saddr + (uint32_t)s * Cfg::PK_BYTES + (((uint32_t)j ^ rot) << 4));
                 if (g >= (uint32_t)kMmaBStages) mbar_wait(&b_empty[st], ((g / kMmaBStages) - 1) & 1);
                 const uint32_t row_saddr = b_saddr + st * kMmaSlabBytes;
                 // ring protocol: nobody may have declared THIS generation of the slab full before it is written
                 VL_DCHECK(CG == 2 || !mbar_test_wait(&b_full[st], (g / kMmaBStages) & 1), 207);
                 if (half == 0)
-                    expand_chunks<0, 4>(x, keep, row_saddr, r7);
+                    emit_half_slab_rt<W, 0, false>(j, pk, keep, row_saddr, r7);
                 else
-                    expand_chunks<4, 4>(x, keep, row_saddr, r7);
+                    emit_half_slab_rt<W, 1, false>(j, pk, keep, row_saddr, r7);
                 fence_proxy_async_smem();
                 __syncwarp();
                 if (lane == 0) {
@@ -600,8 +637,6 @@ mma_scan_kernel(const __grid_constant__ CUtensorMap tmap, const ScanParams p) {
                     else mbar_arrive(&b_full[st]);
                 }
             }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&pk_empty[s]);
         }
     }
 

@@ -120,7 +120,8 @@ int mma_min_q(int w) {
 
 // 0 = not eligible, 1 = one CTA per query tile, 2 = CTA pairs (cta_group::2)
 int mma_path_for(const vl_corpus* c, const ScanParams& p, int nq, int k, int metric) {
-    if (metric != VL_METRIC_HAMMING || p.cur_score != nullptr) return 0;
+    (void)metric;   // both metrics: XORSUM runs as a weighted +-1 contraction (mmascan.cuh)
+    if (p.cur_score != nullptr) return 0;
     const bool collect = p.collect_thr != nullptr;
     if (!collect && k > kMmaListCap) return 0;
     if (c->scan_path == 1) return 0;
@@ -131,10 +132,10 @@ int mma_path_for(const vl_corpus* c, const ScanParams& p, int nq, int k, int met
     return nq > kMmaQT ? 2 : 1;
 }
 
-template <int W, int CG, bool COLLECT>
+template <int W, int CG, bool COLLECT, int METRIC>
 int launch_mma_cfg(vl_corpus* c, ScanParams& p, int nq, int k, ScanPlan* plan_out, bool dry) {
     using Cfg = MmaCfg<W, CG>;
-    auto kern = mma_scan_kernel<W, CG, COLLECT>;
+    auto kern = mma_scan_kernel<W, CG, COLLECT, METRIC>;
     const uint32_t all_tiles = (uint32_t)((p.n_rows + Cfg::NT - 1) / Cfg::NT);
     p.n_tiles = (all_tiles + p.tile_stride - 1) / p.tile_stride;
     const int T = (nq + kMmaQT * CG - 1) / (kMmaQT * CG);   // clusters along the queries
@@ -165,22 +166,27 @@ int launch_mma_cfg(vl_corpus* c, ScanParams& p, int nq, int k, ScanPlan* plan_ou
     return VL_OK;
 }
 
-template <int W>
-int launch_mma_w(vl_corpus* c, ScanParams& p, int nq, int k, int cg, ScanPlan* plan, bool dry) {
+template <int W, int METRIC>
+int launch_mma_wm(vl_corpus* c, ScanParams& p, int nq, int k, int cg, ScanPlan* plan, bool dry) {
     const bool collect = p.collect_thr != nullptr;
     if (cg == 2)
-        return collect ? launch_mma_cfg<W, 2, true>(c, p, nq, k, plan, dry)
-                       : launch_mma_cfg<W, 2, false>(c, p, nq, k, plan, dry);
-    return collect ? launch_mma_cfg<W, 1, true>(c, p, nq, k, plan, dry)
-                   : launch_mma_cfg<W, 1, false>(c, p, nq, k, plan, dry);
+        return collect ? launch_mma_cfg<W, 2, true, METRIC>(c, p, nq, k, plan, dry)
+                       : launch_mma_cfg<W, 2, false, METRIC>(c, p, nq, k, plan, dry);
+    return collect ? launch_mma_cfg<W, 1, true, METRIC>(c, p, nq, k, plan, dry)
+                   : launch_mma_cfg<W, 1, false, METRIC>(c, p, nq, k, plan, dry);
+}
+template <int W>
+int launch_mma_w(vl_corpus* c, ScanParams& p, int nq, int k, int cg, int metric, ScanPlan* plan, bool dry) {
+    return metric == VL_METRIC_HAMMING ? launch_mma_wm<W, kHamming>(c, p, nq, k, cg, plan, dry)
+                                       : launch_mma_wm<W, kXorSum>(c, p, nq, k, cg, plan, dry);
 }
 
 int launch_scan(vl_corpus* c, ScanParams& p, int nq, int k, int metric, ScanPlan* plan, bool dry) {
     if (const int cg = mma_path_for(c, p, nq, k, metric)) {
         switch (c->w) {
-            case 32: return launch_mma_w<32>(c, p, nq, k, cg, plan, dry);
-            case 64: return launch_mma_w<64>(c, p, nq, k, cg, plan, dry);
-            case 128: return launch_mma_w<128>(c, p, nq, k, cg, plan, dry);
+            case 32: return launch_mma_w<32>(c, p, nq, k, cg, metric, plan, dry);
+            case 64: return launch_mma_w<64>(c, p, nq, k, cg, metric, plan, dry);
+            case 128: return launch_mma_w<128>(c, p, nq, k, cg, metric, plan, dry);
             default: break;
         }
     }
