@@ -25,7 +25,8 @@ own 500k-row shard of an N x 500k corpus, all ranks scan all queries.
             cfg1 (VLite.retrieve latency), hbm (1-2 queries over 4 GB), cfg3 (100M rows, 4096 queries,
             top-1000 -> int8 rescore), cfg5 (filters, streaming add, 4 GiB CTX load); N > 1: hbm (16 GB
             per GPU: the 1B-vector corpus at 8 GPUs), strong (500k rows split N ways), group (the
-            in-process shard group over the N GPUs, driven by rank 0).
+            in-process shard group over the N GPUs, driven by rank 0), ctxfan (one 4 GiB CTX file
+            loaded by the N ranks, each its own byte range).
 """
 from __future__ import annotations
 
@@ -404,7 +405,7 @@ def run_ours(args):
 
     ctx = {"torch": torch, "dist": dist, "capi": _capi, "world": world, "rank": rank, "local_rank": local_rank,
            "dev": dev, "hbm_peak": hbm_peak, "barrier": barrier, "flush": flush, "no_cpu": args.no_cpu, "align": align}
-    default_legs = ["extra", "hbm", "cfg1", "cfg3", "cfg5"] if world == 1 else ["hbm", "strong", "group"]
+    default_legs = ["extra", "hbm", "cfg1", "cfg3", "cfg5"] if world == 1 else ["hbm", "strong", "group", "ctxfan"]
     want = default_legs if args.legs == "default" else [x for x in args.legs.split(",") if x]
     if args.no_legs:
         want = []
@@ -480,6 +481,8 @@ def run_ours(args):
         if rank == 0:
             run_leg("group", lambda: legs_mod.leg_group(ctx, queries), collective=False)
         dist.barrier(group=cpu_group)
+    if "ctxfan" in want and world > 1:
+        run_leg("ctxfan", lambda: legs_mod.leg_ctx_fanout(ctx))
     if "cfg1" in want and rank == 0:
         run_leg("cfg1", lambda: legs_mod.leg_cfg1(ctx), collective=False)
     if "cfg5" in want and world == 1:
@@ -537,7 +540,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
     ap.add_argument("--no-legs", action="store_true", help="headline step only (profiling runs)")
     ap.add_argument("--legs", default="default",
-                    help="comma list of extra,hbm,cfg1,cfg3,cfg5 (N=1) / hbm,strong,group (N>1); default = all of them")
+                    help="comma list of extra,hbm,cfg1,cfg3,cfg5 (N=1) / hbm,strong,group,ctxfan (N>1); default = all of them")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

@@ -512,3 +512,70 @@ def leg_cfg5(ctx, n=32_000_000, ctx_rows=16_000_000, tmp=None):
         if os.path.exists(path):
             os.remove(path)
     return out
+
+
+# ------------------------------------------------------------------------------------------------
+# configs[4], multi-GPU part: ONE CTX file loaded by N ranks, each streaming its own byte range to its GPU
+# ------------------------------------------------------------------------------------------------
+def leg_ctx_fanout(ctx, rows=16_000_000, tmp=None):
+    torch, dist, _capi = ctx["torch"], ctx["dist"], ctx["capi"]
+    from oracle import ctxfile as octx, search as osearch, synth
+    from vlite_b200.ctx import CtxFile
+    from vlite_b200.sharded import ShardedCorpus
+    world, rank = ctx["world"], ctx["rank"]
+    tmp = tmp or ("/dev/shm" if os.path.isdir("/dev/shm") else tempfile.gettempdir())
+    path = os.path.join(tmp, "vlite_b200_bench_fanout.ctx")
+    try:
+        free_tmp = os.statvfs(tmp).f_bavail * os.statvfs(tmp).f_frsize
+    except OSError:
+        free_tmp = 0
+    if free_tmp < rows * 256 + (2 << 30):
+        rows = max(1_000_000, int((free_tmp - (2 << 30)) // 256) // 1_000_000 * 1_000_000)
+    sizes = torch.tensor([rows], dtype=torch.int64, device=ctx["dev"])
+    if world > 1:
+        dist.broadcast(sizes, src=0)
+    rows = int(sizes.item())
+    try:
+        if rank == 0:
+            rows64 = synth.corpus_rows(9, 0, rows, 64)
+            octx.write_ctx(path, {"embedding_model": "m", "embedding_size": 64, "embedding_dtype": "float32",
+                                  "context_length": 512}, osearch.to_ref_encoding(rows64).astype(np.float32), [], {})
+            del rows64
+        ctx["barrier"]()
+        cf = CtxFile(path)
+        cf.load(materialise=False)
+        off, ln = cf.embeddings_section
+        best = None
+        for trial in range(2):
+            c = ShardedCorpus(64, device=ctx["local_rank"])
+            try:
+                ctx["barrier"]()
+                t0 = time.perf_counter()
+                first, got = c.load_file(path, off, ln, _capi.SRC_F32_OFFSET)
+                torch.cuda.synchronize()
+                ctx["barrier"]()
+                dt = time.perf_counter() - t0
+                gate(got == rows and c.rows == rows, "ctx fan-out: row count")
+                if trial == 1:
+                    probe = [0, rows // 3, rows - 1]
+                    qs = np.concatenate([synth.corpus_rows(9, r, 1, 64) for r in probe])
+                    qs = np.concatenate([qs, qs[:1]]) if (len(qs) * 1) % 2 else qs
+                    s, r = c.search(qs, 1, _capi.HAMMING)
+                    gate(np.array_equal(r[:3, 0], np.asarray(probe, dtype=np.uint64)) and (s[:3] == 0).all(),
+                         "ctx fan-out: probe rows (first, middle, last) are not found at score 0 under their global numbers")
+                t = torch.tensor([dt], dtype=torch.float64, device=ctx["dev"])
+                if world > 1:
+                    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                best = float(t.item()) if best is None else min(best, float(t.item()))
+            finally:
+                c.close()
+    finally:
+        ctx["barrier"]()
+        if rank == 0 and os.path.exists(path):
+            os.remove(path)
+    return {"rows": rows, "file_GB": ln / 1e9, "gpus": world, "seconds_max_over_ranks": best,
+            "file_GBps_aggregate": ln / best / 1e9, "corpus_GBps_aggregate": rows * 64 / best / 1e9,
+            "rows_per_s": rows / best, "tmp": tmp,
+            "gate": "row counts; probe rows (first, middle, last) found at score 0 under their GLOBAL row numbers",
+            "what": "one page-cache-warm CTXF v1 file; every rank streams ITS byte range of the EMBEDDINGS payload "
+                    "(64 float32 per row) through its own reader pool and pinned ring to its own GPU"}

@@ -104,6 +104,7 @@ extern "C" int vl_corpus_destroy(vl_corpus* c) {
         if (c->stage_ev[i]) cudaEventDestroy(c->stage_ev[i]);
     }
     if (c->io_pinned) cudaFreeHost(c->io_pinned);
+    if (c->trace_dev) cudaFree(c->trace_dev);
     if (c->d_err) cudaFree(c->d_err);
     if (c->d_counter) cudaFree(c->d_counter);
     if (c->ev0) cudaEventDestroy(c->ev0);
@@ -492,6 +493,7 @@ extern "C" int vl_search(vl_corpus* c, const uint8_t* queries_any, int n_queries
     p.n_queries = n_queries;
     p.tile_stride = 1;
     p.one = 1u;
+    p.trace = c->trace_dev;
     bool done = false;
     if (k > large_k_min() && !c->force_multipass) {
         int rc = search_large_k(c, p, n_queries, k, metric, o_s, o_r, &done);
@@ -858,6 +860,22 @@ extern "C" int vl_debug_checks(int device, uint32_t* failures_out, uint32_t* fir
     if (first_id_out) *first_id_out = 0;
     return fail(VL_EINVAL, "not a debug build: rebuild with -DVL_DEBUG_BOUNDS (python -m vlite_b200.build --debug)");
 #endif
+}
+
+// tuning aid, not part of the documented ABI surface: %globaltimer stamps (ns) of CTA (0,0) of the last
+// tensor-core scan: [0] kernel entry, [1] prologue done, [2] last epilogue done, [3] exit, [4..15] accumulator i ready
+extern "C" int vl_scan_trace(vl_corpus* c, uint64_t* out16_host) {
+    if (!c) return fail(VL_EINVAL, "corpus is NULL");
+    DeviceGuard g(c->device);
+    if (!c->trace_dev) {
+        CU(cudaMalloc(&c->trace_dev, 16 * 8));
+        CU(cudaMemset(c->trace_dev, 0, 16 * 8));
+    }
+    if (out16_host) {
+        CU(cudaStreamSynchronize(c->stream));
+        CU(cudaMemcpy(out16_host, c->trace_dev, 16 * 8, cudaMemcpyDeviceToHost));
+    }
+    return VL_OK;
 }
 
 extern "C" int vl_set_scan_path(vl_corpus* c, int path) {

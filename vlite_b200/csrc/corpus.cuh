@@ -146,6 +146,7 @@ struct vl_corpus {
     bool timed = false;
     int tune_splits = 0;
     int tune_stages = 0;
+    unsigned long long* trace_dev = nullptr;   // vl_scan_trace
     int fuse_merge = 1;  // 1-2 queries: final merge inside the scan launch (0 = separate merge kernels, for A/B runs)
     int scan_path = 0;  // 0 auto, 1 integer-pipe kernel only, 2 / 3 tensor-core kernel with 1 / 2 CTAs per tile
 };

@@ -36,7 +36,7 @@ namespace vl {
 
 constexpr int kMmaQT = 128;          // queries per CTA = TMEM lanes = UMMA M per CTA
 constexpr int kMmaRows = 128;        // corpus rows one CTA expands per tile
-constexpr int kMmaBStages = 3;       // expanded K slabs in flight
+constexpr int kMmaMaxBStages = 8;
 constexpr int kMmaPkStages = 2;      // packed row boxes in flight
 constexpr int kMmaThreads = 512;     // warps 0 TMA, 1 MMA, 2 TMEM alloc, 3 idle | 4-7 epilogue | 8-15 expanders
 constexpr int kMmaExpWarps = 8;
@@ -52,9 +52,14 @@ struct MmaCfg {
     static constexpr int A_BYTES = SLABS * kMmaSlabBytes;
     static constexpr int PK_BYTES = kMmaRows * W;
     static constexpr int TMEM_COLS = 2 * NT;        // two accumulator buffers
+    // expanded K slabs in flight.  One slab hand-off (b_empty wake -> expand -> st.shared -> fence.proxy.async
+    // -> arrive -> MMA thread wake -> 4 MMAs -> commit) is ~4x longer than the slab's 512 tensor clocks, so
+    // the ring must hold that many: 4 is what fits beside the 128 KB query operand at W = 128 (3 stages
+    // measured 71 % of the tensor rate in steady state), narrower rows leave room for more.
+    static constexpr int BSTAGES = W >= 128 ? 4 : 6;
     static constexpr size_t SMEM =
-        (size_t)A_BYTES + (size_t)kMmaBStages * kMmaSlabBytes + (size_t)kMmaPkStages * PK_BYTES +
-        (size_t)kMmaPkStages * 2 * MW * 4 + 16 * 8 + 16 + kMmaQT * 4 + 1024 /* alignment slack */;
+        (size_t)A_BYTES + (size_t)BSTAGES * kMmaSlabBytes + (size_t)kMmaPkStages * PK_BYTES +
+        (size_t)kMmaPkStages * 2 * MW * 4 + 32 * 8 + 16 + kMmaQT * 4 + 1024 /* alignment slack */;
     static_assert(W == 32 || W == 64 || W == 128, "row width");
     static_assert(CG == 1 || CG == 2, "cta group");
 };
@@ -98,6 +103,11 @@ __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity
 // generic-proxy shared-memory writes -> visible to the async proxy (UMMA operand reads)
 __device__ __forceinline__ void fence_proxy_async_smem() {
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ unsigned long long global_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -218,6 +228,30 @@ __device__ __forceinline__ void emit_half_slab(const uint32_t (&pk)[W / 4], uint
     emit_chunk<W, 8 * J + 4 * H + 2, WEIGHTED>(pk, keep, base, r7);
     emit_chunk<W, 8 * J + 4 * H + 3, WEIGHTED>(pk, keep, base, r7);
 }
+// the same four chunks for corpus ROWS (+-1, no weights) with the slab index a RUNTIME value: the plane
+// only enters as a shift amount, so the expanders' slab loop stays rolled -- ~3 KB of SASS instead of
+// ~21 KB unrolled, which matters twice: every SM starts with a cold instruction cache, and the hot
+// loops of the four warp roles together must fit the 32 KB L1.5 instruction cache
+template <int W, int H>
+__device__ __forceinline__ void emit_half_slab_rows(const uint32_t (&pk)[W / 4], int j, uint32_t keep, uint32_t slab_row_saddr,
+                                                    uint32_t r7) {
+    constexpr int CHUNKS = W / 16;
+#pragma unroll
+    for (int cc = 0; cc < 4; ++cc) {
+        // global chunk G = 8 j + 4 H + cc: plane G / CHUNKS (runtime), packed chunk G % CHUNKS (static)
+        constexpr int kPlanesPerSlab = 8 / CHUNKS;                    // 1, 2 or 4 bit planes per 128-element slab
+        const int B = (4 * H + cc) % CHUNKS;
+        const uint32_t sh = (uint32_t)(j * kPlanesPerSlab + (4 * H + cc) / CHUNKS);
+        uint32_t o[4];
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+            uint32_t m;
+            asm("prmt.b32 %0, %1, %2, %3;" : "=r"(m) : "r"(pk[4 * B + t] << sh), "r"(0u), "r"(0xBA98u));
+            o[t] = (m | 0x01010101u) & keep;
+        }
+        sts128(slab_row_saddr + ((((uint32_t)(4 * H + cc)) ^ r7) << 4), o[0], o[1], o[2], o[3]);
+    }
+}
 template <int W, int H, bool WEIGHTED, int J = 0>
 __device__ __forceinline__ void emit_half_slab_rt(int j, const uint32_t (&pk)[W / 4], uint32_t keep, uint32_t slab_row_saddr,
                                                   uint32_t r7) {
@@ -236,22 +270,27 @@ mma_scan_kernel(const __grid_constant__ CUtensorMap tmap, const ScanParams p) {
     constexpr int CHUNKS = W / 16;
     constexpr bool XS = METRIC == kXorSum;
     constexpr int K = XS ? 255 * W : 8 * W;      // score = (K - dot) / 2: the dot product of a perfect match
+    const bool tracing = p.trace != nullptr && blockIdx.x == 0 && blockIdx.y == 0;
+    if (tracing && threadIdx.x == 0) p.trace[0] = global_ns();
 
     extern __shared__ uint8_t smem_raw[];
     // the dynamic shared window is only 16 B aligned by contract: swizzled operands want 1024 B
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint8_t* sA = smem;
     uint8_t* sB = sA + Cfg::A_BYTES;
-    uint8_t* sPk = sB + kMmaBStages * kMmaSlabBytes;
+    // ring depth: Cfg::BSTAGES unless a tuning run asks for fewer (p.stages in [2, BSTAGES]); the shared
+    // memory layout always reserves BSTAGES slabs
+    const uint32_t kMmaBStages = (p.stages >= 2 && p.stages <= Cfg::BSTAGES) ? (uint32_t)p.stages : (uint32_t)Cfg::BSTAGES;
+    uint8_t* sPk = sB + Cfg::BSTAGES * kMmaSlabBytes;
     uint32_t* sMask = reinterpret_cast<uint32_t*>(sPk + kMmaPkStages * Cfg::PK_BYTES);   // [stage][live | filter][MW]
     uint64_t* bars = reinterpret_cast<uint64_t*>(sMask + kMmaPkStages * 2 * MW);
     uint64_t* pk_full = bars;                    // [2]  TMA -> expanders
     uint64_t* pk_empty = bars + 2;               // [2]  expanders -> TMA
-    uint64_t* b_full = bars + 4;                 // [3]  expanders (both CTAs) -> MMA thread of the leader
-    uint64_t* b_empty = bars + 7;                // [3]  tcgen05.commit -> expanders (each CTA its own copy)
-    uint64_t* acc_full = bars + 10;              // [2]  tcgen05.commit -> epilogue (each CTA its own copy)
-    uint64_t* acc_empty = bars + 12;             // [2]  epilogue warps (both CTAs) -> MMA thread of the leader
-    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 14);
+    uint64_t* acc_full = bars + 4;               // [2]  tcgen05.commit -> epilogue (each CTA its own copy)
+    uint64_t* acc_empty = bars + 6;              // [2]  epilogue warps (both CTAs) -> MMA thread of the leader
+    uint64_t* b_full = bars + 8;                 // [BSTAGES]  expanders (both CTAs) -> MMA thread of the leader
+    uint64_t* b_empty = bars + 8 + kMmaMaxBStages;   // [BSTAGES]  tcgen05.commit -> expanders (each CTA its own copy)
+    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 8 + 2 * kMmaMaxBStages);
     uint32_t* s_done = s_tmem + 1;                // epilogue warps that have finished (stops the helper warps)
     uint32_t* s_bound = s_tmem + 4;              // [128] per-query admission bound from the device-wide histogram
 
@@ -272,7 +311,7 @@ mma_scan_kernel(const __grid_constant__ CUtensorMap tmap, const ScanParams p) {
             mbar_init(&pk_full[s], 1);
             mbar_init(&pk_empty[s], kMmaExpWarps);
         }
-        for (int s = 0; s < kMmaBStages; ++s) {
+        for (int s = 0; s < Cfg::BSTAGES; ++s) {
             mbar_init(&b_full[s], kMmaExpWarps * CG);
             mbar_init(&b_empty[s], 1);
         }
@@ -317,6 +356,7 @@ mma_scan_kernel(const __grid_constant__ CUtensorMap tmap, const ScanParams p) {
     if constexpr (CG == 2) cluster_sync_all(); else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *s_tmem;
+    if (tracing && threadIdx.x == 0) p.trace[1] = global_ns();     // prologue done (TMEM, barriers, A operand)
 
     if (warp == 0) {
         // ===================== TMA producer: packed row boxes + their mask words =====================
@@ -378,10 +418,15 @@ mma_scan_kernel(const __grid_constant__ CUtensorMap tmap, const ScanParams p) {
         const int qg = q0 + ql;
         const bool q_ok = qg < p.n_queries;
         const int k = p.k;
-        // descending list: kk[0] = k-th best (worst kept), kk[k-1] = best; slots >= k stay 0
-        uint64_t kk[kMmaListCap];
+        // descending list in registers: slot 0 = k-th best (worst kept), slot k-1 = best; slots >= k stay 0.
+        // Rows reach a thread in ascending order (tiles, chunks and columns ascend), so a candidate with
+        // the score of a kept entry is always the later row: the list order needs score compares only.
+        uint32_t ks[kMmaListCap], kr[kMmaListCap];
 #pragma unroll
-        for (int e = 0; e < kMmaListCap; ++e) kk[e] = (!COLLECT && e < k) ? ~0ull : 0ull;
+        for (int e = 0; e < kMmaListCap; ++e) {
+            ks[e] = (!COLLECT && e < k) ? kSentinelScore : 0u;
+            kr[e] = 0xFFFFFFFFu;
+        }
         uint32_t thr = kSentinelScore;      // admit rows with score < thr
         if constexpr (COLLECT) {
             if (q_ok) {
@@ -431,6 +476,7 @@ mma_scan_kernel(const __grid_constant__ CUtensorMap tmap, const ScanParams p) {
             }
             mbar_wait(&acc_full[buf], (i >> 1) & 1);
             tc_fence_after();
+            if (tracing && warp == 4 && lane == 0 && i < 3) p.trace[i == 0 ? 4 : 12 + i] = global_ns();   // accumulator 0 / 1 / 2 ready
 #pragma unroll 1
             for (int ch = 0; ch < NT / 32; ++ch) {
                 uint32_t vu[32];
@@ -453,6 +499,7 @@ mma_scan_kernel(const __grid_constant__ CUtensorMap tmap, const ScanParams p) {
                 int m = v[0];
 #pragma unroll
                 for (int c = 1; c < 32; c += 2) m = max(m, max(v[c], (c + 1 < 32) ? v[c + 1] : v[c]));
+                if (tracing && warp == 4 && lane == 0 && i == 0 && ch < 8) p.trace[5 + ch] = global_ns();   // tile 0: chunk ch loaded
                 if (!__any_sync(kFullMask, m > thrd)) continue;
                 // ---- rare: some thread of the warp has a candidate among these 32 rows.  Candidates
                 // are taken in ascending row order (so an equal score never displaces an earlier row);
@@ -487,13 +534,16 @@ mma_scan_kernel(const __grid_constant__ CUtensorMap tmap, const ScanParams p) {
                             const uint32_t slot = atomicAdd(p.collect_count + qg, 1u);
                             if (slot < p.collect_cap) p.collect_keys[(size_t)qg * p.collect_cap + slot] = key;
                         } else {
-                            // drop kk[0] (the worst), slide `key` into the descending list
+                            // drop slot 0 (the worst), slide the candidate into the descending list
 #pragma unroll
                             for (int e = 0; e < kMmaListCap; ++e) {
-                                const uint64_t nxt = (e + 1 < kMmaListCap) ? kk[e + 1] : 0ull;
-                                kk[e] = (nxt > key) ? nxt : ((kk[e] > key) ? key : kk[e]);
+                                const uint32_t ns = (e + 1 < kMmaListCap) ? ks[e + 1] : 0u;
+                                const uint32_t nr = (e + 1 < kMmaListCap) ? kr[e + 1] : 0xFFFFFFFFu;
+                                const bool up = ns > score, here = ks[e] > score;
+                                kr[e] = up ? nr : (here ? lrow : kr[e]);
+                                ks[e] = up ? ns : (here ? score : ks[e]);
                             }
-                            thr = min(thr, (uint32_t)(kk[0] >> 32));   // never looser than a shared bound
+                            thr = min(thr, ks[0]);                       // never looser than a shared bound
                             thrd = to_dot(thr);
                             dirty = true;
                             if (use_hist) {
@@ -511,6 +561,7 @@ mma_scan_kernel(const __grid_constant__ CUtensorMap tmap, const ScanParams p) {
             }
         }
         __syncwarp();
+        if (tracing && warp == 4 && lane == 0) p.trace[2] = global_ns();   // last tile's epilogue done
         if (lane == 0) atomicAdd(s_done, 1u);
         if constexpr (!COLLECT) {
             if (q_ok) {
@@ -518,10 +569,9 @@ mma_scan_kernel(const __grid_constant__ CUtensorMap tmap, const ScanParams p) {
 #pragma unroll
                 for (int e = 0; e < kMmaListCap; ++e)
                     if (e < k) {
-                        const uint64_t key = kk[e];
-                        const bool none = key == ~0ull;
-                        p.part_scores[o + (k - 1 - e)] = none ? kSentinelScore : (uint32_t)(key >> 32);
-                        p.part_rows[o + (k - 1 - e)] = none ? kSentinelRow : p.base_row + (uint32_t)key;
+                        const bool none = kr[e] == 0xFFFFFFFFu;
+                        p.part_scores[o + (k - 1 - e)] = none ? kSentinelScore : ks[e];
+                        p.part_rows[o + (k - 1 - e)] = none ? kSentinelRow : p.base_row + kr[e];
                     }
             }
         }
@@ -619,17 +669,17 @@ mma_scan_kernel(const __grid_constant__ CUtensorMap tmap, const ScanParams p) {
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(&pk_empty[s]);
-#pragma unroll
+#pragma unroll 1
             for (int j = 0; j < SLABS; ++j, ++g) {
                 const uint32_t st = g % kMmaBStages;
-                if (g >= (uint32_t)kMmaBStages) mbar_wait(&b_empty[st], ((g / kMmaBStages) - 1) & 1);
+                if (g >= kMmaBStages) mbar_wait(&b_empty[st], ((g / kMmaBStages) - 1) & 1);
                 const uint32_t row_saddr = b_saddr + st * kMmaSlabBytes;
                 // ring protocol: nobody may have declared THIS generation of the slab full before it is written
                 VL_DCHECK(CG == 2 || !mbar_test_wait(&b_full[st], (g / kMmaBStages) & 1), 207);
                 if (half == 0)
-                    emit_half_slab_rt<W, 0, false>(j, pk, keep, row_saddr, r7);
+                    emit_half_slab_rows<W, 0>(pk, j, keep, row_saddr, r7);
                 else
-                    emit_half_slab_rt<W, 1, false>(j, pk, keep, row_saddr, r7);
+                    emit_half_slab_rows<W, 1>(pk, j, keep, row_saddr, r7);
                 fence_proxy_async_smem();
                 __syncwarp();
                 if (lane == 0) {
@@ -647,6 +697,7 @@ mma_scan_kernel(const __grid_constant__ CUtensorMap tmap, const ScanParams p) {
         tc_fence_after();
         tmem_dealloc<CG>(tmem_base, (uint32_t)Cfg::TMEM_COLS);
     }
+    if (tracing && threadIdx.x == 0) p.trace[3] = global_ns();
 }
 
 }  // namespace vl
