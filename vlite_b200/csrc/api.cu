@@ -494,6 +494,12 @@ extern "C" int vl_search(vl_corpus* c, const uint8_t* queries_any, int n_queries
     p.tile_stride = 1;
     p.one = 1u;
     p.trace = c->trace_dev;
+    {
+        static const uint32_t poll_ns = [] { const char* e = getenv("VLITE_B200_POLL_NS"); return e ? (uint32_t)atoi(e) : 0u; }();
+        static const uint32_t poll_steady = [] { const char* e = getenv("VLITE_B200_POLL_STEADY"); return e ? (uint32_t)atoi(e) : 0u; }();
+        p.poll_ns = poll_ns;
+        p.poll_steady = poll_steady;
+    }
     bool done = false;
     if (k > large_k_min() && !c->force_multipass) {
         int rc = search_large_k(c, p, n_queries, k, metric, o_s, o_r, &done);

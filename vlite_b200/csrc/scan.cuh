@@ -85,6 +85,7 @@ struct ScanParams {
     // fused final merge (1-2 queries, the latency path): every CTA merges its warps' lists, stores one
     // list of keys per query in fuse_keys[split][q][k], takes a ticket; the LAST CTA to finish merges all
     // splits and writes the final top-k -- one launch instead of scan + two merge levels.
+    uint32_t poll_ns, poll_steady;   // tuning (0 = defaults): histogram poll interval and how many polls keep it
     unsigned long long* trace;       // optional (tuning): %globaltimer stamps of CTA (0,0) of the tensor-core scan
     unsigned long long* fuse_keys;   // nullptr = off
     unsigned int* fuse_ticket;       // zero before the launch; the last CTA resets it
