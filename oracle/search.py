@@ -237,9 +237,12 @@ def rank_and_filter_port(index: dict, q: np.ndarray, top_k: int, metadata=None,
 def rescore(queries: np.ndarray, docs_i8: np.ndarray, cand_rows: np.ndarray, k: int):
     """float64 dot of each query with its candidates' int8 document rows, then
     top-k by DESCENDING score, ties by ascending row.  ``cand_rows`` (Q, C)
-    uint64 with SENTINEL_ROW padding.  The nearest reference code is the unused
-    ``utils.cos_sim`` (vlite/utils.py:205-208); there is no reference rescore,
-    so this function defines the expected value ("parity unpinned").
+    uint64 with SENTINEL_ROW padding.  The reference has no rescore stage; its only
+    dense similarity is the unused ``utils.cos_sim`` (vlite/utils.py:205-208): ``a @ b.T``
+    over the norms.  The dot products here are pinned to that function's outputs on
+    seeded inputs (tests/golden/rescore_golden.npz, tests/test_oracle.py); ranking by the
+    raw dot (not the cosine) and the (score desc, row asc) tie-break are north_star's
+    definition, not the reference's.
     Returns (scores float64 (Q,k) padded with -inf, rows uint64 (Q,k))."""
     qs = np.atleast_2d(np.asarray(queries))
     Q, C = cand_rows.shape

@@ -15,6 +15,9 @@ produced.  Files written:
   collection_golden.json   VLite.rank_and_filter / retrieve / delete / set_batch (vlite/main.py)
   ref_written.ctx(+.json)  a CTXF v1 file written by CtxFile.save, and what CtxFile.load returns
   fixture_facts.json       facts about tests/contexts/vlite-bench.ctx (the reference's fixture)
+  rescore_golden.npz       cos_sim (vlite/utils.py:205-208), the only dense similarity the reference holds:
+                           queries x int8 documents, float32 and float64 -- pins the rescore's dot product
+                           (``--only rescore`` regenerates this file alone)
 """
 import hashlib
 import importlib.util
@@ -287,8 +290,32 @@ def fixture_facts(ref_ctx):
     print("fixture_facts.json:", facts["legacy_rows"], "rows,", facts["n_contexts"], "contexts")
 
 
+def golden_rescore():
+    """The reference has no rescore stage; its only dense similarity is ``cos_sim`` (vlite/utils.py:205-208):
+    ``a @ b.T`` divided by the norms.  The rescore here is that numerator over int8 document rows, so
+    cos_sim's outputs on seeded queries / documents pin the oracle's dot products (divided by the same
+    norms) and the ranking they induce."""
+    import vlite.utils as ref_utils                    # importable once import_reference() has stubbed its deps
+    rng = np.random.default_rng(77)
+    dims, n_docs = 1024, 300
+    docs_i8 = rng.integers(-128, 128, size=(n_docs, dims), dtype=np.int8)
+    docs_i8[17] = docs_i8[5]                           # an exact tie: the rank test must break it by row
+    q_f32 = rng.standard_normal((4, dims)).astype(np.float32)
+    q_i8 = rng.integers(-128, 128, size=(2, dims), dtype=np.int8)
+    out = {"docs_i8": docs_i8, "queries_f32": q_f32, "queries_i8": q_i8}
+    for name, qs in (("f32", q_f32), ("i8", q_i8)):
+        for qi, q in enumerate(qs):
+            out[f"{name}_q{qi}_cos_f32"] = np.asarray(ref_utils.cos_sim(q.astype(np.float32), docs_i8.astype(np.float32)))
+            out[f"{name}_q{qi}_cos_f64"] = np.asarray(ref_utils.cos_sim(q.astype(np.float64), docs_i8.astype(np.float64)))
+    np.savez_compressed(os.path.join(HERE, "rescore_golden.npz"), **out)
+    print("rescore_golden.npz:", len(out), "arrays")
+
+
 if __name__ == "__main__":
     ref_model, ref_main, ref_ctx = import_reference()
+    if sys.argv[1:3] == ["--only", "rescore"]:
+        golden_rescore()
+        sys.exit(0)
     # the reference drops a telemetry id file under ./contexts on every save/load
     # (ctx.py:58, :89): run from a scratch cwd so nothing lands in the repo
     _scratch = tempfile.mkdtemp()
@@ -298,3 +325,4 @@ if __name__ == "__main__":
     golden_collection(ref_model, ref_main)
     golden_ctx(ref_ctx)
     fixture_facts(ref_ctx)
+    golden_rescore()

@@ -156,3 +156,27 @@ def test_automatic_dispatch_is_bit_identical(gpu):
         for nq in (15, 16, 63, 64, 260):
             _check(c, corpus, queries[:nq], 10)
             _check(c, corpus, queries[:nq], 10, metric=XORSUM)
+
+
+@pytest.mark.parametrize("k", [17, 24, 32])
+@pytest.mark.parametrize("period", [0, 700])
+@pytest.mark.parametrize("width,metric", [(128, HAMMING), (64, XORSUM), (32, HAMMING)])
+def test_k_17_to_32_batches_take_the_collect_path(gpu, k, period, width, metric):
+    """The tensor-core kernel's register lists end at k = 16; a batch with 16 < k <= 32 runs sampled
+    threshold + collect + select on the tensor cores (search_host.cuh::large_k_min) instead of the
+    integer-pipe lists.  period=700 floods the candidate buffer with ties: the gated exact fallback answers.
+    Same result either way, and the same as the integer-pipe kernel."""
+    n = 150_000
+    corpus = synth.corpus_rows(41, 0, n, width, period)
+    queries = synth.uniform_queries(42, 70, width)
+    queries[0] = corpus[n - 3]
+    valid = synth.filter_valid(3, 0, n, 0.1)
+    with gpu.Corpus(width) as c:
+        c.append(corpus)
+        _check(c, corpus, queries, k, metric=metric)
+        _check(c, corpus, queries, k, synth.pack_mask(valid), metric=metric)
+        auto = c.search(queries, k, metric)
+        c.set_scan_path(1)                       # integer-pipe lists
+        lists = c.search(queries, k, metric)
+    np.testing.assert_array_equal(auto[0], lists[0])
+    np.testing.assert_array_equal(auto[1], lists[1])

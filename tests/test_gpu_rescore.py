@@ -1,5 +1,6 @@
-"""-m gpu: rescore kernel vs the oracle (float64 dot; "parity unpinned": the reference has no
-rescore) and the single-GPU emulation of the sharded merge."""
+"""-m gpu: rescore kernel vs the oracle (float64 dot) and vs the outputs of the reference's cos_sim
+(vlite/utils.py:205-208, the only dense similarity it holds: tests/golden/rescore_golden.npz), and the
+single-GPU emulation of the sharded merge."""
 import numpy as np
 import pytest
 
@@ -108,3 +109,32 @@ def test_sharded_merge_single_gpu_emulation(gpu, shards):
     es, er = cscan.search(queries, full, k, gpu.HAMMING)
     np.testing.assert_array_equal(out_s.cpu().numpy().view(np.uint32), es)
     np.testing.assert_array_equal(out_r.cpu().numpy().view(np.uint64), er)
+
+
+@pytest.mark.parametrize("qname", ["f32", "i8"])
+def test_rescore_matches_reference_cos_sim_golden(gpu, qname):
+    """rescore_golden.npz holds what the reference's cos_sim (vlite/utils.py:205-208) returned for seeded
+    queries x int8 documents.  The device scores divided by the same norms must reproduce them within
+    1e-5 relative (north_star), with identical documents ranked by row."""
+    torch = pytest.importorskip("torch")
+    import os
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "rescore_golden.npz"))
+    docs = g["docs_i8"]
+    n, dims = docs.shape
+    qs = g[f"queries_{qname}"]
+    d = torch.from_numpy(docs).cuda()
+    cand = np.tile(np.arange(n, dtype=np.uint64), (len(qs), 1))
+    with gpu.Corpus(128) as c:
+        s, r = c.rescore(d, n, dims, qs, cand, n)
+    doc_norm = np.linalg.norm(docs.astype(np.float64), axis=1)
+    for qi, q in enumerate(qs):
+        rows = r[qi].astype(np.int64)
+        assert sorted(rows.tolist()) == list(range(n))
+        cos = s[qi].astype(np.float64) / (np.linalg.norm(q.astype(np.float64)) * doc_norm[rows])
+        ref = g[f"{qname}_q{qi}_cos_f64"][rows]
+        rel = np.abs(cos - ref) / np.maximum(np.abs(ref), 1e-300)
+        big = np.abs(ref) > 1e-6 * np.abs(ref).max()          # (a cosine that cancels to ~0 has no relative scale)
+        assert rel[big].max() <= RTOL, rel[big].max()
+        assert np.abs(cos - ref).max() <= 1e-7
+        pos5, pos17 = int(np.nonzero(rows == 5)[0][0]), int(np.nonzero(rows == 17)[0][0])
+        assert pos17 == pos5 + 1

@@ -165,3 +165,29 @@ def test_synth_generator_properties():
     assert all(((m[i >> 5] >> (i & 31)) & 1) == int(v[i]) for i in range(70))
     # mix64 known answer (splitmix64 finaliser of 1)
     assert int(synth.mix64(np.array([1], dtype=np.uint64))[0]) == 0x5692161D100B05E5
+
+
+def test_rescore_dot_matches_reference_cos_sim():
+    """The reference's only dense similarity is cos_sim (vlite/utils.py:205-208): a @ b.T over the norms.
+    Its outputs on seeded queries / int8 documents (rescore_golden.npz, produced by executing it) pin the
+    oracle's rescore: same dot products once divided by the same norms, and the ranking they induce
+    (descending dot, ties by ascending row)."""
+    g = np.load(os.path.join(GOLD, "rescore_golden.npz"))
+    docs = g["docs_i8"]
+    n = docs.shape[0]
+    doc_norm = np.linalg.norm(docs.astype(np.float64), axis=1)
+    rows = np.arange(n, dtype=np.uint64)[None, :]
+    for name in ("f32", "i8"):
+        qs = g[f"queries_{name}"]
+        for qi, q in enumerate(qs):
+            s, r = osearch.rescore(q[None, :], docs, rows, n)           # every document, ranked
+            dots = np.empty(n)
+            dots[r[0].astype(np.int64)] = s[0]
+            cos = dots / (np.linalg.norm(q.astype(np.float64)) * doc_norm)
+            np.testing.assert_allclose(cos, g[f"{name}_q{qi}_cos_f64"], rtol=1e-12, atol=1e-15)
+            np.testing.assert_allclose(cos, g[f"{name}_q{qi}_cos_f32"].astype(np.float64), rtol=0, atol=2e-6)
+            # the ranking the reference's numbers induce once the document norm is multiplied back
+            ref_dot = g[f"{name}_q{qi}_cos_f64"] * doc_norm
+            assert np.all(np.diff(ref_dot[r[0].astype(np.int64)]) <= 1e-9 * np.abs(ref_dot).max())
+            pos5, pos17 = int(np.nonzero(r[0] == 5)[0][0]), int(np.nonzero(r[0] == 17)[0][0])
+            assert pos17 == pos5 + 1                                    # identical documents: lower row first

@@ -501,7 +501,7 @@ extern "C" int vl_search(vl_corpus* c, const uint8_t* queries_any, int n_queries
         p.poll_steady = poll_steady;
     }
     bool done = false;
-    if (k > large_k_min() && !c->force_multipass) {
+    if (k > large_k_min(c, p, n_queries, metric) && !c->force_multipass) {
         int rc = search_large_k(c, p, n_queries, k, metric, o_s, o_r, &done);
         if (rc != VL_OK) return rc;
     }
@@ -874,13 +874,32 @@ extern "C" int vl_scan_trace(vl_corpus* c, uint64_t* out16_host) {
     if (!c) return fail(VL_EINVAL, "corpus is NULL");
     DeviceGuard g(c->device);
     if (!c->trace_dev) {
-        CU(cudaMalloc(&c->trace_dev, 16 * 8));
-        CU(cudaMemset(c->trace_dev, 0, 16 * 8));
+        CU(cudaMalloc(&c->trace_dev, vl::kTraceWords * 8));
+        CU(cudaMemset(c->trace_dev, 0, vl::kTraceWords * 8));
     }
     if (out16_host) {
         CU(cudaStreamSynchronize(c->stream));
         CU(cudaMemcpy(out16_host, c->trace_dev, 16 * 8, cudaMemcpyDeviceToHost));
     }
+    return VL_OK;
+}
+// ... and the per-tile part of the same trace: [16 + i] = epilogue of tile i done (ns), [16 + 256 + i] = insert-loop
+// iterations warp 4 ran in tile i, for the first 256 tiles of CTA (0,0)
+extern "C" int vl_scan_trace_tiles(vl_corpus* c, uint64_t* out512_host) {
+    if (!c || !out512_host) return fail(VL_EINVAL, "NULL argument");
+    if (!c->trace_dev) return fail(VL_EINVAL, "tracing is off: call vl_scan_trace(h, NULL) first");
+    DeviceGuard g(c->device);
+    CU(cudaStreamSynchronize(c->stream));
+    CU(cudaMemcpy(out512_host, c->trace_dev + 16, 512 * 8, cudaMemcpyDeviceToHost));
+    return VL_OK;
+}
+// ... and entry [i] / exit [296 + i] stamps of every CTA (linear index, first 296)
+extern "C" int vl_scan_trace_ctas(vl_corpus* c, uint64_t* out592_host) {
+    if (!c || !out592_host) return fail(VL_EINVAL, "NULL argument");
+    if (!c->trace_dev) return fail(VL_EINVAL, "tracing is off: call vl_scan_trace(h, NULL) first");
+    DeviceGuard g(c->device);
+    CU(cudaStreamSynchronize(c->stream));
+    CU(cudaMemcpy(out592_host, c->trace_dev + 16 + 512, 2 * vl::kTraceCtas * 8, cudaMemcpyDeviceToHost));
     return VL_OK;
 }
 

@@ -42,6 +42,8 @@ constexpr int kMmaThreads = 512;     // warps 0 TMA, 1 MMA, 2 TMEM alloc, 3 idle
 constexpr int kMmaExpWarps = 8;
 constexpr int kMmaListCap = 16;      // k <= 16 per-thread register list
 constexpr int kMmaSlabBytes = 128 * 128;
+constexpr int kTraceCtas = 296;
+constexpr int kTraceWords = 16 + 512 + 2 * kTraceCtas;   // vl_scan_trace: 16 stamps | per-tile stamps + insert counts of 256 tiles | entry / exit of every CTA
 
 template <int W, int CG>
 struct MmaCfg {
@@ -272,6 +274,8 @@ mma_scan_kernel(const __grid_constant__ CUtensorMap tmap, const ScanParams p) {
     constexpr int K = XS ? 255 * W : 8 * W;      // score = (K - dot) / 2: the dot product of a perfect match
     const bool tracing = p.trace != nullptr && blockIdx.x == 0 && blockIdx.y == 0;
     if (tracing && threadIdx.x == 0) p.trace[0] = global_ns();
+    const uint32_t cta_lin = blockIdx.y * gridDim.x + blockIdx.x;
+    if (p.trace != nullptr && threadIdx.x == 0 && cta_lin < (uint32_t)kTraceCtas) p.trace[16 + 512 + cta_lin] = global_ns();
 
     extern __shared__ uint8_t smem_raw[];
     // the dynamic shared window is only 16 B aligned by contract: swizzled operands want 1024 B
@@ -451,6 +455,7 @@ mma_scan_kernel(const __grid_constant__ CUtensorMap tmap, const ScanParams p) {
         for (uint32_t i = 0; i < my_tiles; ++i) {
             const uint32_t buf = i & 1;
             const uint32_t t = (tile_begin + i) * p.tile_stride;
+            if (tracing && warp == 4 && lane == 0 && i < 256) p.trace[16 + 256 + i] = 0;
             if (use_tau) {
                 const uint32_t gth = (tau_pref == kSentinelScore) ? tau_pref : tau_pref + 1;
                 if (gth < thr) {
@@ -501,6 +506,7 @@ mma_scan_kernel(const __grid_constant__ CUtensorMap tmap, const ScanParams p) {
                 for (int c = 1; c < 32; c += 2) m = max(m, max(v[c], (c + 1 < 32) ? v[c + 1] : v[c]));
                 if (tracing && warp == 4 && lane == 0 && i == 0 && ch < 8) p.trace[5 + ch] = global_ns();   // tile 0: chunk ch loaded
                 if (!__any_sync(kFullMask, m > thrd)) continue;
+                if (tracing && warp == 4 && lane == 0 && i < 256) p.trace[16 + 256 + i] += 1u << 16;   // chunks that took the rare path
                 // ---- rare: some thread of the warp has a candidate among these 32 rows.  Candidates
                 // are taken in ascending row order (so an equal score never displaces an earlier row);
                 // every thread works on its own query, the warp only votes on "anything left". ----
@@ -508,6 +514,7 @@ mma_scan_kernel(const __grid_constant__ CUtensorMap tmap, const ScanParams p) {
 #pragma unroll
                 for (int c = 0; c < 32; ++c) hm |= (v[c] > thrd) ? (1u << c) : 0u;
                 while (__any_sync(kFullMask, hm != 0u)) {
+                    if (tracing && warp == 4 && lane == 0 && i < 256) p.trace[16 + 256 + i] += 1u;   // insert-loop iterations
                     const bool mine = hm != 0u;
                     const int pc = mine ? __ffs(hm) - 1 : 0;
                     hm &= hm - 1u;
@@ -559,6 +566,7 @@ mma_scan_kernel(const __grid_constant__ CUtensorMap tmap, const ScanParams p) {
                 dirty = false;
                 if (use_tau && thr != kSentinelScore && thr < tau_pref) atomicMin(tau_ptr, thr);
             }
+            if (tracing && warp == 4 && lane == 0 && i < 256) p.trace[16 + i] = global_ns();
         }
         __syncwarp();
         if (tracing && warp == 4 && lane == 0) p.trace[2] = global_ns();   // last tile's epilogue done
@@ -701,6 +709,7 @@ mma_scan_kernel(const __grid_constant__ CUtensorMap tmap, const ScanParams p) {
         tmem_dealloc<CG>(tmem_base, (uint32_t)Cfg::TMEM_COLS);
     }
     if (tracing && threadIdx.x == 0) p.trace[3] = global_ns();
+    if (p.trace != nullptr && threadIdx.x == 0 && cta_lin < (uint32_t)kTraceCtas) p.trace[16 + 512 + kTraceCtas + cta_lin] = global_ns();
 }
 
 }  // namespace vl

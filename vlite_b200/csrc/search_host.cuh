@@ -358,12 +358,19 @@ int search_lists(vl_corpus* c, ScanParams p, int n_queries, int k, int metric, u
 
 // above this k the sampled collect/select path replaces the per-warp k-lists (tuning override:
 // VLITE_B200_LARGEK_MIN)
-int large_k_min() {
+int large_k_min(const vl_corpus* c, const ScanParams& p, int n_queries, int metric) {
     static int v = [] {
         const char* e = getenv("VLITE_B200_LARGEK_MIN");
-        return e ? atoi(e) : 32;  // measured crossover: equal at k=32, 1.7x faster at k=100, 3x at k=256
+        return e ? atoi(e) : -1;
     }();
-    return v;
+    if (v >= 0) return v;
+    // integer-pipe kernel (shared-memory lists up to 32): measured crossover: equal at k=32, 1.7x faster at k=100,
+    // 3x at k=256.  Where the batch is big enough for the tensor-core kernel, its register lists end at 16
+    // and both passes of this path run on it: k = 17..32 at 500k x 1024 queries 2.62-2.72 ms (integer-pipe
+    // lists) vs 0.65 ms (sampled + collect on the tensor cores), 4M rows: 19.1 vs 3.09 ms.
+    ScanParams pc = p;
+    pc.collect_thr = reinterpret_cast<const uint32_t*>(&pc);   // "collect mode" for the eligibility question only
+    return mma_path_for(c, pc, n_queries, 1, metric) ? kMmaListCap : 32;
 }
 
 // k > large_k_min(): sampled threshold + collect + select (largek.cuh).  *done = false asks the caller to run
