@@ -3,7 +3,8 @@ expanded bit -> int8 in shared memory) through the C ABI against the CPU oracle.
 
 Bar: bit-exact scores and row lists under the (score, row) tie-break, identical to the
 integer-pipe kernel on every shape.  vl_set_scan_path forces the kernel: 2 = one CTA per query
-tile, 3 = CTA pairs (cta_group::2)."""
+tile, 3 = CTA pairs (cta_group::2); HAMMING then runs as a 4-bit-float contraction (kind::mxf4, 224-row
+tiles for pairs), 5 / 6 ask for its int8 form (kind::i8, 256-row tiles)."""
 import numpy as np
 import pytest
 
@@ -12,7 +13,7 @@ from oracle import cscan, synth
 pytestmark = pytest.mark.gpu
 
 HAMMING, XORSUM = 0, 1
-PATHS = [2, 3]
+PATHS = [2, 3, 5, 6]   # 2 / 3: HAMMING as e2m1 (kind::mxf4), XORSUM as int8; 5 / 6: HAMMING as int8 (kind::i8)
 
 
 def _check(c, corpus, queries, k, mask_words=None, base_row=0, metric=HAMMING):
@@ -180,3 +181,23 @@ def test_k_17_to_32_batches_take_the_collect_path(gpu, k, period, width, metric)
         lists = c.search(queries, k, metric)
     np.testing.assert_array_equal(auto[0], lists[0])
     np.testing.assert_array_equal(auto[1], lists[1])
+
+
+@pytest.mark.parametrize("path", PATHS)
+@pytest.mark.parametrize("nq", [128, 1024])
+def test_many_tiles_per_cta_repeated(gpu, path, nq):
+    """Regression: 8+ tiles per CTA, launched repeatedly.  The packed-row box used to be handed back to the TMA
+    producer while the expanders' shared-memory loads of it were still in flight (an mbarrier arrive does not
+    wait for them): with the fast e2m1 pipeline rows of tile i then carried 16-byte chunks of tile i + 2 in
+    most launches of this shape.  Every launch must be bit-exact."""
+    n, w = 150_003, 128
+    corpus = synth.corpus_rows(11, 0, n, w)
+    queries, _ = synth.clustered_queries(12, 0, n, nq, w)
+    es, er = cscan.search(queries, corpus, 10, HAMMING)
+    with gpu.Corpus(w) as c:
+        c.append(corpus)
+        c.set_scan_path(path)
+        for _ in range(12):
+            s, r = c.search(queries, 10, HAMMING)
+            np.testing.assert_array_equal(s, es)
+            np.testing.assert_array_equal(r, er)

@@ -905,7 +905,8 @@ extern "C" int vl_scan_trace_ctas(vl_corpus* c, uint64_t* out592_host) {
 
 extern "C" int vl_set_scan_path(vl_corpus* c, int path) {
     if (!c) return fail(VL_EINVAL, "corpus is NULL");
-    if (path < 0 || path > 3) return fail(VL_EINVAL, "scan path must be 0 (auto), 1 (integer pipes), 2 or 3 (tensor cores, 1 or 2 CTAs per tile)");
+    if (path < 0 || path > 6 || path == 4)
+        return fail(VL_EINVAL, "scan path must be 0 (auto), 1 (integer pipes), 2 / 3 (tensor cores, 1 / 2 CTAs per tile), 5 / 6 (the same, HAMMING as int8 instead of e2m1)");
     c->scan_path = path;
     return VL_OK;
 }

@@ -130,7 +130,6 @@ __device__ __forceinline__ uint4 lds128(uint32_t saddr) {
     asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(saddr));
     return v;
 }
-
 // streaming 128-bit global load that does not allocate in L1
 __device__ __forceinline__ uint4 ldg128_stream(const void* p) {
     uint4 v;

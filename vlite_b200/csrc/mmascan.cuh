@@ -30,6 +30,7 @@
 //             the per-query collect buffer (large k).  tau[] shares thresholds between CTAs as in
 //             scan.cuh.  Output = one sorted list per (row split, query) for merge.cuh.
 #pragma once
+#include <type_traits>
 #include "scan.cuh"
 
 namespace vl {
@@ -45,25 +46,36 @@ constexpr int kMmaSlabBytes = 128 * 128;
 constexpr int kTraceCtas = 296;
 constexpr int kTraceWords = 16 + 512 + 2 * kTraceCtas;   // vl_scan_trace: 16 stamps | per-tile stamps + insert counts of 256 tiles | entry / exit of every CTA
 
-template <int W, int CG>
+// F4 = the +-1 contraction in 4-bit floats (tcgen05.mma kind::mxf4: e2m1 operands, +1.0 = 0x2, -1.0 = 0xA, two per
+// byte, unit UE8M0 block scales, fp32 accumulation -- exact: every product is +-1 and |sum| <= 1024 < 2^24).  The
+// instruction takes K = 64 in the time kind::i8 takes K = 32 (measured: 8.9 vs 4.6 POP/s, scripts/umma_probe.cu),
+// an expanded row is 4 W bytes instead of 8 W, and the expansion is 2 instructions per 8 elements instead of
+// 3 per 4.  HAMMING only: XORSUM's bit weights do not fit e2m1.  The 32 scale-factor columns need TMEM room
+// beside the two accumulators, so a CTA pair scores 224 rows per tile (112 per CTA) instead of 256.
+template <int W, int CG, bool F4 = false>
 struct MmaCfg {
-    static constexpr int K = W * 8;                 // int8 elements per row
-    static constexpr int SLABS = W / 16;            // K slabs of 128 elements (= one 16 B packed chunk)
-    static constexpr int NT = kMmaRows * CG;        // rows per tile = UMMA N
+    static constexpr int K = W * 8;                 // elements per row
+    static constexpr int SLABS = F4 ? W / 32 : W / 16;   // K slabs: 128 B per row = 256 e2m1 / 128 int8
+    static constexpr int ROWS = (F4 && CG == 2) ? 112 : kMmaRows;   // corpus rows one CTA expands per tile
+    static constexpr int NT = ROWS * CG;            // rows per tile = UMMA N
     static constexpr int MW = NT / 32;              // mask words per tile
     static constexpr int A_BYTES = SLABS * kMmaSlabBytes;
-    static constexpr int PK_BYTES = kMmaRows * W;
-    static constexpr int TMEM_COLS = 2 * NT;        // two accumulator buffers
+    static constexpr int PK_BYTES = ROWS * W;
+    static constexpr int PK_STRIDE = (PK_BYTES + 1023) & ~1023;   // swizzled boxes start on the swizzle period
+    static constexpr int SF_COLS = F4 ? 32 : 0;     // scale factors: 16 columns for A, 16 for B
+    static constexpr int TMEM_COLS = F4 ? 512 : 2 * NT;   // two accumulator buffers [| scale factors]; a power of two
     // expanded K slabs in flight.  One slab hand-off (b_empty wake -> expand -> st.shared -> fence.proxy.async
     // -> arrive -> MMA thread wake -> 4 MMAs -> commit) is ~4x longer than the slab's 512 tensor clocks, so
     // the ring must hold that many: 4 is what fits beside the 128 KB query operand at W = 128 (3 stages
     // measured 71 % of the tensor rate in steady state), narrower rows leave room for more.
-    static constexpr int BSTAGES = W >= 128 ? 4 : 6;
+    static constexpr int BSTAGES = F4 ? 8 : (W >= 128 ? 4 : 6);
     static constexpr size_t SMEM =
-        (size_t)A_BYTES + (size_t)BSTAGES * kMmaSlabBytes + (size_t)kMmaPkStages * PK_BYTES +
-        (size_t)kMmaPkStages * 2 * MW * 4 + 32 * 8 + 16 + kMmaQT * 4 + 1024 /* alignment slack */;
+        (size_t)A_BYTES + (size_t)BSTAGES * kMmaSlabBytes + (size_t)kMmaPkStages * PK_STRIDE +
+        (size_t)kMmaPkStages * 2 * 8 * 4 + 32 * 8 + 16 + kMmaQT * 4 + 1024 /* alignment slack */;
     static_assert(W == 32 || W == 64 || W == 128, "row width");
     static_assert(CG == 1 || CG == 2, "cta group");
+    static_assert(NT % 32 == 0 && 2 * NT + SF_COLS <= 512, "tile width / TMEM budget");
+    static_assert(SMEM <= 227 * 1024, "shared memory");
 };
 
 // ---- tcgen05 / cluster PTX wrappers ------------------------------------------------------------
@@ -145,6 +157,28 @@ __device__ __forceinline__ void umma_i8(uint32_t d_tmem, uint64_t a_desc, uint64
                      "r"(idesc), "r"(accumulate)
                      : "memory");
 }
+// D[tmem] (+)= A * B, e2m1 x e2m1 -> f32 with UE8M0 block scales (one per 32 elements) read from TMEM (SASS UTCOMMA)
+template <int CG>
+__device__ __forceinline__ void umma_mxf4(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate,
+                                          uint32_t sfa_tmem, uint32_t sfb_tmem) {
+    if constexpr (CG == 1)
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                     "tcgen05.mma.cta_group::1.kind::mxf4.block_scale.scale_vec::2X [%0], %1, %2, %3, [%5], [%6], p;\n\t}" ::"r"(d_tmem),
+                     "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(sfa_tmem), "r"(sfb_tmem)
+                     : "memory");
+    else
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                     "tcgen05.mma.cta_group::2.kind::mxf4.block_scale.scale_vec::2X [%0], %1, %2, %3, [%5], [%6], p;\n\t}" ::"r"(d_tmem),
+                     "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(sfa_tmem), "r"(sfb_tmem)
+                     : "memory");
+}
+// one value into 32 lanes x 16 consecutive 32-bit columns of TMEM (lane = thread)
+__device__ __forceinline__ void tmem_fill16(uint32_t taddr, uint32_t x) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1};" ::"r"(taddr), "r"(x)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 // arrive on an mbarrier once every tcgen05 operation issued so far by this thread has completed;
 // CG = 2: the same barrier offset in both CTAs of the pair
 template <int CG>
@@ -183,6 +217,21 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
 // instruction descriptor: D = s32, A = B = signed 8 bit, both K-major, shape M x N (K = 32 implied)
 __host__ __device__ constexpr uint32_t umma_idesc_i8(int m, int n) {
     return (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+
+__device__ __forceinline__ void sts128(uint32_t saddr, uint32_t a, uint32_t b, uint32_t c, uint32_t d);
+// block-scaled instruction descriptor: A = B = e2m1 (format 1), both K-major, scale format UE8M0, shape M x N (K = 64)
+__host__ __device__ constexpr uint32_t umma_idesc_mxf4(int m, int n) {
+    return (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | (1u << 23) | ((uint32_t)(m >> 4) << 24);
+}
+
+// ---- bit -> e2m1 expansion (F4) ------------------------------------------------------------------
+// One packed 32-bit word -> one 16-byte chunk of 32 e2m1 elements: nibble n of output word j is bit 4 n + j
+// of the input, as sign (bit 1 -> 0xA = -1.0, bit 0 -> 0x2 = +1.0).  The same map for rows and queries; a
+// masked row passes keep = 0 and expands to zeros.  Two instructions per 8 elements (SHL + LOP3).
+__device__ __forceinline__ void emit_chunk_f4(uint32_t x, uint32_t keep, uint32_t chunk_saddr) {
+    const uint32_t sgn = 0x88888888u & keep, one = 0x22222222u & keep;
+    sts128(chunk_saddr, ((x << 3) & sgn) | one, ((x << 2) & sgn) | one, ((x << 1) & sgn) | one, (x & sgn) | one);
 }
 
 // ---- bit -> int8 expansion -----------------------------------------------------------------------
@@ -263,14 +312,16 @@ __device__ __forceinline__ void emit_half_slab_rt(int j, const uint32_t (&pk)[W 
     }
 }
 
-template <int W, int CG, bool COLLECT, int METRIC>
+template <int W, int CG, bool COLLECT, int METRIC, bool F4 = false>
 __global__ void __launch_bounds__(kMmaThreads, 1)
 mma_scan_kernel(const __grid_constant__ CUtensorMap tmap, const ScanParams p) {
-    using Cfg = MmaCfg<W, CG>;
+    using Cfg = MmaCfg<W, CG, F4>;
     if (p.gate != nullptr && *p.gate == 0) return;   // uniform over the grid (and over a cluster)
-    constexpr int SLABS = Cfg::SLABS, NT = Cfg::NT, MW = Cfg::MW;
+    constexpr int SLABS = Cfg::SLABS, NT = Cfg::NT, MW = Cfg::MW, ROWS = Cfg::ROWS;
     constexpr int CHUNKS = W / 16;
     constexpr bool XS = METRIC == kXorSum;
+    static_assert(!(F4 && XS), "the 4-bit contraction is +-1 only");
+    using AccT = typename std::conditional<F4, float, int>::type;   // accumulator type as the epilogue compares it
     constexpr int K = XS ? 255 * W : 8 * W;      // score = (K - dot) / 2: the dot product of a perfect match
     const bool tracing = p.trace != nullptr && blockIdx.x == 0 && blockIdx.y == 0;
     if (tracing && threadIdx.x == 0) p.trace[0] = global_ns();
@@ -286,7 +337,7 @@ mma_scan_kernel(const __grid_constant__ CUtensorMap tmap, const ScanParams p) {
     // memory layout always reserves BSTAGES slabs
     const uint32_t kMmaBStages = (p.stages >= 2 && p.stages <= Cfg::BSTAGES) ? (uint32_t)p.stages : (uint32_t)Cfg::BSTAGES;
     uint8_t* sPk = sB + Cfg::BSTAGES * kMmaSlabBytes;
-    uint32_t* sMask = reinterpret_cast<uint32_t*>(sPk + kMmaPkStages * Cfg::PK_BYTES);   // [stage][live | filter][MW]
+    uint32_t* sMask = reinterpret_cast<uint32_t*>(sPk + kMmaPkStages * Cfg::PK_STRIDE);   // [stage][live | filter][MW]
     uint64_t* bars = reinterpret_cast<uint64_t*>(sMask + kMmaPkStages * 2 * MW);
     uint64_t* pk_full = bars;                    // [2]  TMA -> expanders
     uint64_t* pk_empty = bars + 2;               // [2]  expanders -> TMA
@@ -330,7 +381,26 @@ mma_scan_kernel(const __grid_constant__ CUtensorMap tmap, const ScanParams p) {
     if (warp == 2) tmem_alloc<CG>(s_tmem, (uint32_t)Cfg::TMEM_COLS);
 
     // ---- A operand: expand this CTA's queries once (zeros past n_queries; XORSUM: weighted) ----
-    {
+    if constexpr (F4) {
+        const int ql = threadIdx.x % kMmaQT;        // 4 threads per query, each a quarter of the half-slabs
+        const int part = threadIdx.x / kMmaQT;
+        const int qg = q0 + ql;
+        const uint32_t keep = qg < p.n_queries ? 0xFFFFFFFFu : 0u;
+        const uint32_t row_saddr = smem_u32(sA) + (uint32_t)ql * 128u;
+        const uint32_t r7 = (uint32_t)(ql & 7);
+        for (int u = part; u < SLABS * 2; u += kMmaThreads / kMmaQT) {
+            // half-slab u = chunks [4 (u & 1), + 4) of slab u / 2 <- packed words [4 u, 4 u + 4) of the query
+            uint4 x = make_uint4(0u, 0u, 0u, 0u);
+            if (keep) x = *reinterpret_cast<const uint4*>(p.queries + (size_t)qg * W + (size_t)u * 16);
+            const uint32_t base = row_saddr + (uint32_t)(u >> 1) * kMmaSlabBytes;
+            const uint32_t c0 = (uint32_t)(u & 1) * 4u;
+            emit_chunk_f4(x.x, keep, base + (((c0 + 0u) ^ r7) << 4));
+            emit_chunk_f4(x.y, keep, base + (((c0 + 1u) ^ r7) << 4));
+            emit_chunk_f4(x.z, keep, base + (((c0 + 2u) ^ r7) << 4));
+            emit_chunk_f4(x.w, keep, base + (((c0 + 3u) ^ r7) << 4));
+        }
+        fence_proxy_async_smem();
+    } else {
         const int ql = threadIdx.x % kMmaQT;        // 4 threads per query, each a quarter of the half-slabs
         const int part = threadIdx.x / kMmaQT;
         const int qg = q0 + ql;
@@ -356,6 +426,17 @@ mma_scan_kernel(const __grid_constant__ CUtensorMap tmap, const ScanParams p) {
         }
         fence_proxy_async_smem();
     }
+    if constexpr (F4) {
+        // unit block scales (UE8M0 0x7F = 2^0) in every byte of the 32 scale-factor columns of all 128 lanes:
+        // whatever bytes an MMA reads for its A and B scale vectors, it reads 1.0
+        __syncthreads();                               // s_tmem is written
+        if (warp >= 4 && warp < 8) {
+            const uint32_t sf = *s_tmem + ((uint32_t)((warp & 3) * 32) << 16) + 2u * NT;
+            tmem_fill16(sf, 0x7F7F7F7Fu);
+            tmem_fill16(sf + 16u, 0x7F7F7F7Fu);
+            tmem_st_wait();
+        }
+    }
     tc_fence_before();
     if constexpr (CG == 2) cluster_sync_all(); else __syncthreads();
     tc_fence_after();
@@ -370,19 +451,26 @@ mma_scan_kernel(const __grid_constant__ CUtensorMap tmap, const ScanParams p) {
                 const int s = i % kMmaPkStages;
                 if (i >= kMmaPkStages) mbar_wait(&pk_empty[s], ((i / kMmaPkStages) - 1) & 1);
                 const uint32_t t = (tile_begin + i) * p.tile_stride;
-                const uint32_t mask_bytes = MW * 4;
-                mbar_arrive_expect_tx(&pk_full[s], Cfg::PK_BYTES + mask_bytes + (has_filter ? mask_bytes : 0));
-                tma_load_2d(sPk + (size_t)s * Cfg::PK_BYTES, &tmap, 0, (int)(t * NT + rank * kMmaRows), &pk_full[s], policy);
-                uint32_t* m = sMask + s * 2 * MW;
-                bulk_g2s(m, p.live + (size_t)t * MW, mask_bytes, &pk_full[s]);
-                if (has_filter) bulk_g2s(m + MW, p.filter + (size_t)t * MW, mask_bytes, &pk_full[s]);
+                if constexpr (F4) {
+                    // (28-byte mask rows cannot ride a bulk copy: the expanders read their mask bits from global)
+                    mbar_arrive_expect_tx(&pk_full[s], Cfg::PK_BYTES);
+                    tma_load_2d(sPk + (size_t)s * Cfg::PK_STRIDE, &tmap, 0, (int)(t * NT + rank * ROWS), &pk_full[s], policy);
+                } else {
+                    const uint32_t mask_bytes = MW * 4;
+                    mbar_arrive_expect_tx(&pk_full[s], Cfg::PK_BYTES + mask_bytes + (has_filter ? mask_bytes : 0));
+                    tma_load_2d(sPk + (size_t)s * Cfg::PK_STRIDE, &tmap, 0, (int)(t * NT + rank * ROWS), &pk_full[s], policy);
+                    uint32_t* m = sMask + s * 2 * MW;
+                    bulk_g2s(m, p.live + (size_t)t * MW, mask_bytes, &pk_full[s]);
+                    if (has_filter) bulk_g2s(m + MW, p.filter + (size_t)t * MW, mask_bytes, &pk_full[s]);
+                }
             }
         }
         __syncwarp();   // reconverge: the teardown barrier / cluster barrier is warp-aligned
     } else if (warp == 1) {
         // ===================== MMA issuer: one thread of the leader CTA =====================
         if (rank == 0 && lane == 0) {
-            constexpr uint32_t idesc = umma_idesc_i8(kMmaQT * CG, NT);
+            constexpr uint32_t idesc = F4 ? umma_idesc_mxf4(kMmaQT * CG, NT) : umma_idesc_i8(kMmaQT * CG, NT);
+            const uint32_t sfa = tmem_base + 2u * NT, sfb = sfa + 16u;
             const uint32_t a_saddr = smem_u32(sA), b_saddr = smem_u32(sB);
             uint32_t g = 0;   // slab counter
             for (uint32_t i = 0; i < my_tiles; ++i) {
@@ -402,7 +490,11 @@ mma_scan_kernel(const __grid_constant__ CUtensorMap tmap, const ScanParams p) {
                     const uint64_t ad = umma_desc_sw128(a_saddr + (uint32_t)j * kMmaSlabBytes);
                     const uint64_t bd = umma_desc_sw128(b_saddr + st * kMmaSlabBytes);
 #pragma unroll
-                    for (int kk = 0; kk < 4; ++kk) {   // K = 32 int8 = 32 B per instruction: +2 in the address field
+                    for (int kk = 0; kk < 4; ++kk) {   // K = 32 int8 (64 e2m1) = 32 B per instruction: +2 in the address field
+                        if constexpr (F4) {
+                            umma_mxf4<CG>(d_tmem, ad + (uint64_t)(kk * 2), bd + (uint64_t)(kk * 2), idesc, (j | kk) != 0 ? 1u : 0u, sfa, sfb);
+                            continue;
+                        }
                         umma_i8<CG>(d_tmem, ad + (uint64_t)(kk * 2), bd + (uint64_t)(kk * 2), idesc, (j | kk) != 0 ? 1u : 0u);
                         // XORSUM: the elements of plane 0 (bit 7 of every byte, the first W of the row) weigh
                         // 128 = 64 + 64: their k-steps are accumulated twice
@@ -439,11 +531,12 @@ mma_scan_kernel(const __grid_constant__ CUtensorMap tmap, const ScanParams p) {
             }
         }
         constexpr int kNever = 1 << 30;
-        auto to_dot = [&](uint32_t th) -> int {   // score < th  <=>  dot > K - 2 th
-            if (!q_ok) return kNever;
-            return (th > (uint32_t)K) ? -kNever : K - 2 * (int)th;   // (K = 8 W or 255 W: the largest score)
+        auto to_dot = [&](uint32_t th) -> AccT {   // score < th  <=>  dot > K - 2 th
+            if (!q_ok) return (AccT)kNever;
+            return (AccT)((th > (uint32_t)K) ? -kNever : K - 2 * (int)th);   // (K = 8 W or 255 W: the largest score)
         };
-        int thrd = to_dot(thr);
+        AccT thrd = to_dot(thr);
+        const uint32_t n_mask_words = (p.n_rows + 31u) >> 5;
         const bool use_tau = !COLLECT && q_ok;
         uint32_t* tau_ptr = p.tau + (q_ok ? qg : 0);
         uint32_t tau_pref = kSentinelScore;
@@ -475,7 +568,7 @@ mma_scan_kernel(const __grid_constant__ CUtensorMap tmap, const ScanParams p) {
             // this tile's eligibility bits (live & filter), one word per lane: fetched before the wait so
             // that the rare path below never touches memory
             uint32_t vw = 0;
-            if (lane < MW) {
+            if (lane < MW && (!F4 || t * (uint32_t)MW + (uint32_t)lane < n_mask_words)) {   // (224-row tiles can end past the padded mask)
                 vw = __ldg(p.live + (size_t)t * MW + lane);
                 if (has_filter) vw &= __ldg(p.filter + (size_t)t * MW + lane);
             }
@@ -498,10 +591,13 @@ mma_scan_kernel(const __grid_constant__ CUtensorMap tmap, const ScanParams p) {
                         else mbar_arrive(&acc_empty[buf]);
                     }
                 }
-                int v[32];
+                AccT v[32];
 #pragma unroll
-                for (int c = 0; c < 32; ++c) v[c] = (int)vu[c];
-                int m = v[0];
+                for (int c = 0; c < 32; ++c) {
+                    if constexpr (F4) v[c] = __uint_as_float(vu[c]);   // exact integers in fp32: compared as floats
+                    else v[c] = (int)vu[c];
+                }
+                AccT m = v[0];
 #pragma unroll
                 for (int c = 1; c < 32; c += 2) m = max(m, max(v[c], (c + 1 < 32) ? v[c + 1] : v[c]));
                 if (tracing && warp == 4 && lane == 0 && i == 0 && ch < 8) p.trace[5 + ch] = global_ns();   // tile 0: chunk ch loaded
@@ -519,7 +615,7 @@ mma_scan_kernel(const __grid_constant__ CUtensorMap tmap, const ScanParams p) {
                     const int pc = mine ? __ffs(hm) - 1 : 0;
                     hm &= hm - 1u;
                     // v[pc] without dynamic register indexing: a 5-level select tree
-                    int s16[16], s8[8], s4[4], s2[2];
+                    AccT s16[16], s8[8], s4[4], s2[2];
 #pragma unroll
                     for (int e = 0; e < 16; ++e) s16[e] = (pc & 16) ? v[e + 16] : v[e];
 #pragma unroll
@@ -528,15 +624,15 @@ mma_scan_kernel(const __grid_constant__ CUtensorMap tmap, const ScanParams p) {
                     for (int e = 0; e < 4; ++e) s4[e] = (pc & 4) ? s8[e + 4] : s8[e];
 #pragma unroll
                     for (int e = 0; e < 2; ++e) s2[e] = (pc & 2) ? s4[e + 2] : s4[e];
-                    const int pv = (pc & 1) ? s2[1] : s2[0];
+                    const AccT pv = (pc & 1) ? s2[1] : s2[0];
                     const uint32_t rit = (uint32_t)ch * 32u + (uint32_t)pc;      // row in tile
                     VL_DCHECK(rit < (uint32_t)NT && (rit >> 5) < (uint32_t)MW, 203);
                     const uint32_t wv = __shfl_sync(kFullMask, vw, (int)(rit >> 5));
                     if (mine && pv > thrd && ((wv >> (rit & 31)) & 1u)) {
-                        const uint32_t score = (uint32_t)(K - pv) >> 1;
+                        const uint32_t score = (uint32_t)(K - (int)pv) >> 1;
                         const uint32_t lrow = t * (uint32_t)NT + rit;
                         const uint64_t key = ((uint64_t)score << 32) | lrow;
-                        VL_DCHECK(pv >= -K && pv <= K && ((K - pv) & 1) == 0 && lrow < p.n_rows, 204);   // a +-1 dot product of K terms
+                        VL_DCHECK((int)pv >= -K && (int)pv <= K && ((K - (int)pv) & 1) == 0 && (AccT)(int)pv == pv && lrow < p.n_rows, 204);   // a +-1 dot product of K terms
                         if constexpr (COLLECT) {
                             const uint32_t slot = atomicAdd(p.collect_count + qg, 1u);
                             if (slot < p.collect_cap) p.collect_keys[(size_t)qg * p.collect_cap + slot] = key;
@@ -652,11 +748,13 @@ mma_scan_kernel(const __grid_constant__ CUtensorMap tmap, const ScanParams p) {
         const int rgrp = ew & 3;            // 32 rows of the CTA's 128
         const int half = ew >> 2;           // chunks [4 half, 4 half + 4) of every slab
         const int r = rgrp * 32 + lane;
+        const bool r_ok = r < ROWS;         // (F4 pairs: 112 rows per CTA, the last 16 row slots idle)
+        const uint32_t n_mask_words = (p.n_rows + 31u) >> 5;
         // TMA swizzle of the packed box: logical chunk j of row r at chunk j ^ rot(r)
         constexpr int LANES_PER_128B = (W >= 128) ? 1 : 128 / W;
         constexpr int ROT_MASK = (CHUNKS < 8 ? CHUNKS : 8) - 1;
         const uint32_t rot = (uint32_t)((r / LANES_PER_128B) & ROT_MASK);
-        const uint32_t pk_saddr = smem_u32(sPk) + (uint32_t)r * W;
+        const uint32_t pk_saddr = smem_u32(sPk) + (uint32_t)(r_ok ? r : 0) * W;
         const uint32_t b_saddr = smem_u32(sB) + (uint32_t)r * 128u;
         const uint32_t r7 = (uint32_t)(r & 7);
         const uint32_t b_full_remote = (CG == 2) ? mapa_shared(smem_u32(&b_full[0]), 0) : 0u;
@@ -664,22 +762,46 @@ mma_scan_kernel(const __grid_constant__ CUtensorMap tmap, const ScanParams p) {
         uint32_t g = 0;
         for (uint32_t i = 0; i < my_tiles; ++i) {
             const int s = i % kMmaPkStages;
-            mbar_wait(&pk_full[s], (i / kMmaPkStages) & 1);
-            const uint32_t* m = sMask + s * 2 * MW;
-            uint32_t wv = m[mword];
-            if (has_filter) wv &= m[MW + mword];
-            const uint32_t keep = ((wv >> lane) & 1u) ? 0xFFFFFFFFu : 0u;
+            uint32_t keep;
+            if constexpr (F4) {
+                // this row's eligibility bit straight from global memory, requested before the wait
+                const uint32_t bit = (uint32_t)rank * ROWS + (uint32_t)r;
+                const uint32_t widx = (tile_begin + i) * p.tile_stride * (uint32_t)MW + (bit >> 5);
+                uint32_t wv = 0;
+                if (r_ok && widx < n_mask_words) {
+                    wv = __ldg(p.live + widx);
+                    if (has_filter) wv &= __ldg(p.filter + widx);
+                }
+                mbar_wait(&pk_full[s], (i / kMmaPkStages) & 1);
+                keep = ((wv >> (bit & 31u)) & 1u) ? 0xFFFFFFFFu : 0u;
+            } else {
+                mbar_wait(&pk_full[s], (i / kMmaPkStages) & 1);
+                const uint32_t* m = sMask + s * 2 * MW;
+                uint32_t wv = m[mword];
+                if (has_filter) wv &= m[MW + mword];
+                keep = ((wv >> lane) & 1u) ? 0xFFFFFFFFu : 0u;
+            }
             // the whole packed row goes to registers (every slab needs one bit plane of ALL its bytes) and
             // the packed box is handed back to the TMA producer before the expansion starts
             uint32_t pk[W / 4];
             VL_DCHECK(rot < (uint32_t)CHUNKS && r < kMmaRows, 205);
 #pragma unroll
             for (int c = 0; c < CHUNKS; ++c) {
-                const uint4 x = lds128(pk_saddr + (uint32_t)s * Cfg::PK_BYTES + (((uint32_t)c ^ rot) << 4));
+                const uint4 x = lds128(pk_saddr + (uint32_t)s * Cfg::PK_STRIDE + (((uint32_t)c ^ rot) << 4));
                 pk[4 * c] = x.x, pk[4 * c + 1] = x.y, pk[4 * c + 2] = x.z, pk[4 * c + 3] = x.w;
             }
+            // The box may only be handed back once the loads have RETURNED.  An mbarrier arrive does not wait for the
+            // thread's own outstanding shared-memory loads (SASS: LDS.128 x8, then SYNCS.ARRIVE with no scoreboard
+            // wait), and with the TMA producer one wake-up away the next box was seen to land before the last
+            // wavefronts of those loads had read the old one: rows of tile i carried chunks of tile i + 2
+            // (found with the e2m1 path, whose later slabs use the loaded words late; scripts/fp4_debug.py).  Making
+            // the barrier address depend on every loaded word makes the arrive wait for them.
+            uint32_t h = 0;
+#pragma unroll
+            for (int c = 0; c < W / 4; ++c) h ^= pk[c];
+            h &= p.one - 1u;                       // == 0, but only at run time: the arrive below depends on every load
             __syncwarp();
-            if (lane == 0) mbar_arrive(&pk_empty[s]);
+            if (lane == 0) mbar_arrive(&pk_empty[s] + h);
 #pragma unroll 1
             for (int j = 0; j < SLABS; ++j, ++g) {
                 const uint32_t st = g % kMmaBStages;
@@ -687,7 +809,21 @@ mma_scan_kernel(const __grid_constant__ CUtensorMap tmap, const ScanParams p) {
                 const uint32_t row_saddr = b_saddr + st * kMmaSlabBytes;
                 // ring protocol: nobody may have declared THIS generation of the slab full before it is written
                 VL_DCHECK(CG == 2 || !mbar_test_wait(&b_full[st], (g / kMmaBStages) & 1), 207);
-                if (half == 0)
+                if constexpr (F4) {
+                    // slab j <- packed words [8 j, 8 j + 8); this thread's four chunks [4 half, + 4).  The word
+                    // index must be static (registers): the slab switch is unrolled (SLABS <= 4).
+                    if (r_ok) {
+#pragma unroll
+                        for (int jj = 0; jj < SLABS; ++jj) {
+                            if (j != jj) continue;
+#pragma unroll
+                            for (int cc = 0; cc < 4; ++cc) {
+                                const uint32_t x = half == 0 ? pk[8 * jj + cc] : pk[8 * jj + 4 + cc];
+                                emit_chunk_f4(x, keep, row_saddr + ((((uint32_t)(4 * half + cc)) ^ r7) << 4));
+                            }
+                        }
+                    }
+                } else if (half == 0)
                     emit_half_slab_rows<W, 0>(pk, j, keep, row_saddr, r7);
                 else
                     emit_half_slab_rows<W, 1>(pk, j, keep, row_saddr, r7);

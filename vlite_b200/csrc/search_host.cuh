@@ -125,17 +125,17 @@ int mma_path_for(const vl_corpus* c, const ScanParams& p, int nq, int k, int met
     const bool collect = p.collect_thr != nullptr;
     if (!collect && k > kMmaListCap) return 0;
     if (c->scan_path == 1) return 0;
-    if (c->scan_path == 2) return 1;
-    if (c->scan_path == 3) return 2;
+    if (c->scan_path == 2 || c->scan_path == 5) return 1;
+    if (c->scan_path == 3 || c->scan_path == 6) return 2;
     const int mq = mma_min_q(c->w);
     if (mq <= 0 || nq < mq) return 0;
     return nq > kMmaQT ? 2 : 1;
 }
 
-template <int W, int CG, bool COLLECT, int METRIC>
+template <int W, int CG, bool COLLECT, int METRIC, bool F4 = false>
 int launch_mma_cfg(vl_corpus* c, ScanParams& p, int nq, int k, ScanPlan* plan_out, bool dry) {
-    using Cfg = MmaCfg<W, CG>;
-    auto kern = mma_scan_kernel<W, CG, COLLECT, METRIC>;
+    using Cfg = MmaCfg<W, CG, F4>;
+    auto kern = mma_scan_kernel<W, CG, COLLECT, METRIC, F4>;
     const uint32_t all_tiles = (uint32_t)((p.n_rows + Cfg::NT - 1) / Cfg::NT);
     p.n_tiles = (all_tiles + p.tile_stride - 1) / p.tile_stride;
     const int T = (nq + kMmaQT * CG - 1) / (kMmaQT * CG);   // clusters along the queries
@@ -149,7 +149,7 @@ int launch_mma_cfg(vl_corpus* c, ScanParams& p, int nq, int k, ScanPlan* plan_ou
     p.stages = c->tune_stages;   // 0 = the configuration's own ring depth
     TRY(allow_max_smem(kern, c->device));
     CUtensorMap tmap;
-    TRY(make_corpus_tmap(c, &tmap, kMmaRows));
+    TRY(make_corpus_tmap(c, &tmap, Cfg::ROWS));
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3((unsigned)(T * CG), (unsigned)S);
     cfg.blockDim = dim3(kMmaThreads);
@@ -167,9 +167,25 @@ int launch_mma_cfg(vl_corpus* c, ScanParams& p, int nq, int k, ScanPlan* plan_ou
     return VL_OK;
 }
 
+// HAMMING runs the +-1 contraction in 4-bit floats (kind::mxf4, exact) unless VLITE_B200_FP4=0 or the
+// scan path asks for the int8 form (vl_set_scan_path 5 / 6)
+bool mma_use_f4(const vl_corpus* c) {
+    static const bool env_on = [] { const char* e = getenv("VLITE_B200_FP4"); return !(e && atoi(e) == 0); }();
+    return env_on && c->scan_path != 5 && c->scan_path != 6;
+}
+
 template <int W, int METRIC>
 int launch_mma_wm(vl_corpus* c, ScanParams& p, int nq, int k, int cg, ScanPlan* plan, bool dry) {
     const bool collect = p.collect_thr != nullptr;
+    if constexpr (METRIC == kHamming) {
+        if (mma_use_f4(c)) {
+            if (cg == 2)
+                return collect ? launch_mma_cfg<W, 2, true, METRIC, true>(c, p, nq, k, plan, dry)
+                               : launch_mma_cfg<W, 2, false, METRIC, true>(c, p, nq, k, plan, dry);
+            return collect ? launch_mma_cfg<W, 1, true, METRIC, true>(c, p, nq, k, plan, dry)
+                           : launch_mma_cfg<W, 1, false, METRIC, true>(c, p, nq, k, plan, dry);
+        }
+    }
     if (cg == 2)
         return collect ? launch_mma_cfg<W, 2, true, METRIC>(c, p, nq, k, plan, dry)
                        : launch_mma_cfg<W, 2, false, METRIC>(c, p, nq, k, plan, dry);
