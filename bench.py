@@ -13,10 +13,11 @@ own 500k-row shard of an N x 500k corpus, all ranks scan all queries.
             arm reports the SAME unit, so the driver's ratio compares like with like at every N;
             ``qps_over_whole_corpus`` is the plain queries/s over the N x 500k corpus.
 ``e2e``     the same metric through the C ABI with HOST buffers (pinned queries in, results out).
-``roofline`` of the dominant kernel.  Batches of >= 64 queries run on the tensor-core scan
-            (tcgen05.mma kind::i8 on rows expanded bit -> int8 in shared memory): bound "tensor",
-            achieved = 2 N Q 8W int8 ops / kernel time, peak = 2 x the measured bf16 cuBLAS rate of
-            MEASURED_PEAKS.json (int8 issues at twice the bf16 rate on B200).  The north star's own
+``roofline`` of the dominant kernel.  Batches of >= 24 queries run on the tensor-core scan
+            (HAMMING: tcgen05.mma kind::mxf4 on rows expanded bit -> +-1.0 e2m1 in shared memory, exact
+            fp32 sums): bound "tensor", achieved = 2 N Q 8W ops / kernel time, peak = 4 x the measured
+            bf16 cuBLAS rate of MEASURED_PEAKS.json (e2m1 issues at four times the bf16 rate on B200;
+            the int8 form of the same kernel is timed beside it under ``extra``).  The north star's own
             roofline (popcount work at the INT-pipe peak, corpus bytes at HBM bandwidth) is kept
             beside it as ``north_star_view``; the HBM-bound regime (1-2 queries) is ``roofline_hbm``.
 ``cpu_baseline`` the oracle's torch-op port of the reference's EmbeddingModel.search
@@ -370,10 +371,10 @@ def run_ours(args):
     popc_peak, _ = _capi.microbench(0, 8192, device=local_rank)           # lane-POPC/s, measured live
     alg_bytes = rows * w + rows / 8 + nq * w + nq * k * 12
     alg_popc = rows * nq * (w / 4)
-    alg_int8_ops = 2.0 * rows * nq * (w * 8)
+    alg_mac_ops = 2.0 * rows * nq * (w * 8)
     t_hbm = alg_bytes / (hbm_peak * 1e9)
     t_int = alg_popc / popc_peak
-    int8_peak = 2.0 * peaks["bf16"]                                        # TOP/s
+    tensor_peak = 4.0 * peaks["bf16"]                                        # e2m1 dense: 4 x the bf16 rate (TOP/s)
     traffic, traffic_src, pipes = None, None, None
     tpath = os.path.join(ROOT, "profiles", "traffic_cfg2.json")
     if os.path.exists(tpath):       # a STATIC number: read from the committed ncu --set full capture of this kernel + workload
@@ -381,24 +382,25 @@ def run_ours(args):
         traffic = tj.get("dram_bytes_per_launch")
         traffic_src = f"not measured in this run: committed ncu capture profiles/{tj.get('source', '?')} of the same kernel and workload"
         pipes = {kk: tj[kk] for kk in ("tensor_pipe_pct", "alu_pipe_pct", "xu_pipe_pct", "fma_pipe_pct", "issue_slots_pct") if kk in tj}
-    achieved_tops = alg_int8_ops / (scan_avg_ms * 1e-3) / 1e12
+    achieved_tops = alg_mac_ops / (scan_avg_ms * 1e-3) / 1e12
     roofline = {
-        "bound": "tensor", "achieved": achieved_tops, "peak": int8_peak, "unit": "TFLOP/s",
-        "frac": achieved_tops / int8_peak, "traffic": traffic, "traffic_source": traffic_src,
+        "bound": "tensor", "achieved": achieved_tops, "peak": tensor_peak, "unit": "TFLOP/s",
+        "frac": achieved_tops / tensor_peak, "traffic": traffic, "traffic_source": traffic_src,
         "pipe_utilisation_ncu": pipes,
-        "kernel": "mma_scan_kernel<W=128, CG=2, lists> (tcgen05.mma.cta_group::2.kind::i8, TMEM accumulators)",
+        "kernel": "mma_scan_kernel<W=128, CG=2, lists, e2m1> (tcgen05.mma.cta_group::2.kind::mxf4.block_scale, unit scales, fp32 TMEM accumulators)",
         "kernel_ms": scan_avg_ms,
-        "algorithmic": {"int8_ops_per_launch": alg_int8_ops, "bytes_per_launch": alg_bytes, "popc_per_launch": alg_popc,
-                        "per_unit": "per (query,row) pair at W=128: 1024 int8 MAC = 2048 ops (tensor view), "
+        "algorithmic": {"mac_ops_per_launch": alg_mac_ops, "bytes_per_launch": alg_bytes, "popc_per_launch": alg_popc,
+                        "per_unit": "per (query,row) pair at W=128: 1024 +-1 MAC = 2048 ops (tensor view), "
                                     "32 32-bit POPC (north-star INT view), W = 128 corpus bytes per row once per batch"},
-        "peak_source": ("int8 dense = 2 x bf16: 2 x " + f"{peaks['bf16']:.1f}" + " TFLOP/s cuBLAS bf16 burst, " + peaks["src"] +
-                        "; the unit is int8 TOP/s (integer ops, exact s32 accumulation)"),
+        "peak_source": ("e2m1 (kind::mxf4) dense = 4 x bf16: 4 x " + f"{peaks['bf16']:.1f}" + " TFLOP/s cuBLAS bf16 burst, " + peaks["src"] +
+                        " (nominal 9000; scripts/umma_probe.cu issues 8920 from fixed operands, profiles/r2_umma_probe.log); the unit is "
+                        "TOP/s of exact +-1 multiply-adds (fp32 accumulation of integers < 2^24)"),
         "north_star_view": {"bound": "int_pipe" if t_int >= t_hbm else "hbm",
                             "achieved": alg_popc / (scan_avg_ms * 1e-3) / 1e12, "peak": popc_peak / 1e12, "unit": "TPOPC/s",
                             "frac": max(t_hbm, t_int) / (scan_avg_ms * 1e-3),
                             "note": "north_star's roofline = slower of corpus bytes at HBM bandwidth and popcount work at "
                                     "the INT-pipe peak (POPC peak: vl_microbench live in this run).  frac >> 1 because the "
-                                    "popcount work runs on the tensor pipe as an exact int8 contraction instead"},
+                                    "popcount work runs on the tensor pipe as an exact +-1 contraction instead"},
         "hbm_view": {"achieved": rows * w / (scan_avg_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
                      "frac": rows * w / (scan_avg_ms * 1e-3) / 1e9 / hbm_peak},
     }
@@ -460,6 +462,10 @@ def run_ours(args):
         t, s_ = timed(_capi.XORSUM, 1)
         extra["xorsum_integer_pipe_kernel"] = {"ms_per_step": t, "scan_ms": s_, "qps": nq / (t * 1e-3),
                                                "kernel": "scan_topk_kernel<128,XORSUM,8,8> (LOP3 + IDP4A)"}
+        t, s_ = timed(_capi.HAMMING, 6)
+        extra["int8_tensor_kernel_same_workload"] = {
+            "ms_per_step": t, "scan_ms": s_, "qps": nq / (t * 1e-3),
+            "kernel": "mma_scan_kernel<128,2,lists,HAMMING,int8> (tcgen05.mma kind::i8, 256-row tiles): round 2's first tensor-core form"}
         t, s_ = timed(_capi.HAMMING, 1)
         extra["integer_pipe_kernel_same_workload"] = {
             "ms_per_step": t, "scan_ms": s_, "qps": nq / (t * 1e-3), "kernel": "scan_topk_kernel<128,HAMMING,8,8> (LOP3 carry-save + POPC)",
@@ -512,7 +518,7 @@ def run_ours(args):
             "metric": "queries_per_sec", "value": value, "unit": "queries/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "s8 x s8 -> s32 (packed bits expanded to +-1 int8 in shared memory; exact)",
+            "dtype": "e2m1 x e2m1 -> f32 (packed bits expanded to +-1.0 4-bit floats in shared memory; every sum an exact integer)",
             "data": "synthetic", "config": workload_config(world),
             "e2e": {"value": e2e_value, "unit": "queries/s", "h2d_bytes_per_step": nq * w,
                     "d2h_bytes_per_step": nq * k * 12, "ms_per_step": e2e_ms},

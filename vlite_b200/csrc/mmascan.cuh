@@ -39,7 +39,7 @@ constexpr int kMmaQT = 128;          // queries per CTA = TMEM lanes = UMMA M pe
 constexpr int kMmaRows = 128;        // corpus rows one CTA expands per tile
 constexpr int kMmaMaxBStages = 8;
 constexpr int kMmaPkStages = 2;      // packed row boxes in flight
-constexpr int kMmaThreads = 512;     // warps 0 TMA, 1 MMA, 2 TMEM alloc, 3 idle | 4-7 epilogue | 8-15 expanders
+constexpr int kMmaThreads = 512;     // warps 0 TMA, 1 MMA, 2 TMEM alloc, 3 idle | 4-7 epilogue | 8-15 expanders (e2m1: 8-11 expanders, 12-15 epilogue)
 constexpr int kMmaExpWarps = 8;
 constexpr int kMmaListCap = 16;      // k <= 16 per-thread register list
 constexpr int kMmaSlabBytes = 128 * 128;
@@ -63,6 +63,11 @@ struct MmaCfg {
     static constexpr int PK_BYTES = ROWS * W;
     static constexpr int PK_STRIDE = (PK_BYTES + 1023) & ~1023;   // swizzled boxes start on the swizzle period
     static constexpr int SF_COLS = F4 ? 32 : 0;     // scale factors: 16 columns for A, 16 for B
+    // F4: expansion is 2 instructions per 8 elements and the MMAs take half the time, so the accumulator read-out is
+    // the critical role: 4 expander warps (one thread per row) and TWO epilogue groups of 4 warps (warps 4-7: even
+    // 32-column chunks, warps 12-15: odd ones), each thread with its own k-list -> 2 lists per (split, query)
+    static constexpr int EXP_WARPS = F4 ? 4 : kMmaExpWarps;
+    static constexpr int EPI_GROUPS = F4 ? 2 : 1;
     static constexpr int TMEM_COLS = F4 ? 512 : 2 * NT;   // two accumulator buffers [| scale factors]; a power of two
     // expanded K slabs in flight.  One slab hand-off (b_empty wake -> expand -> st.shared -> fence.proxy.async
     // -> arrive -> MMA thread wake -> 4 MMAs -> commit) is ~4x longer than the slab's 512 tensor clocks, so
@@ -318,6 +323,7 @@ mma_scan_kernel(const __grid_constant__ CUtensorMap tmap, const ScanParams p) {
     using Cfg = MmaCfg<W, CG, F4>;
     if (p.gate != nullptr && *p.gate == 0) return;   // uniform over the grid (and over a cluster)
     constexpr int SLABS = Cfg::SLABS, NT = Cfg::NT, MW = Cfg::MW, ROWS = Cfg::ROWS;
+    constexpr int EXPW = Cfg::EXP_WARPS, EG = Cfg::EPI_GROUPS;
     constexpr int CHUNKS = W / 16;
     constexpr bool XS = METRIC == kXorSum;
     static_assert(!(F4 && XS), "the 4-bit contraction is +-1 only");
@@ -364,15 +370,15 @@ mma_scan_kernel(const __grid_constant__ CUtensorMap tmap, const ScanParams p) {
         tma_prefetch_desc(&tmap);
         for (int s = 0; s < kMmaPkStages; ++s) {
             mbar_init(&pk_full[s], 1);
-            mbar_init(&pk_empty[s], kMmaExpWarps);
+            mbar_init(&pk_empty[s], EXPW);
         }
         for (int s = 0; s < Cfg::BSTAGES; ++s) {
-            mbar_init(&b_full[s], kMmaExpWarps * CG);
+            mbar_init(&b_full[s], EXPW * CG);
             mbar_init(&b_empty[s], 1);
         }
         for (int b = 0; b < 2; ++b) {
             mbar_init(&acc_full[b], 1);
-            mbar_init(&acc_empty[b], 4 * CG);
+            mbar_init(&acc_empty[b], 4 * EG * CG);
         }
         mbar_fence_init();
         *s_done = 0;
@@ -507,8 +513,9 @@ mma_scan_kernel(const __grid_constant__ CUtensorMap tmap, const ScanParams p) {
             }
         }
         __syncwarp();
-    } else if (warp >= 4 && warp < 8) {
-        // ===================== epilogue: one query per thread =====================
+    } else if ((warp >= 4 && warp < 8) || (EG == 2 && warp >= 12)) {
+        // ===================== epilogue: one query per thread (and per group) =====================
+        const int grp = (warp >= 12) ? 1 : 0;   // which 32-column chunks of every tile: ch % EG == grp
         const uint32_t lane_base = (uint32_t)(warp & 3) * 32u;
         const int ql = (int)lane_base + lane;
         const int qg = q0 + ql;
@@ -576,14 +583,14 @@ mma_scan_kernel(const __grid_constant__ CUtensorMap tmap, const ScanParams p) {
             tc_fence_after();
             if (tracing && warp == 4 && lane == 0 && i < 3) p.trace[i == 0 ? 4 : 12 + i] = global_ns();   // accumulator 0 / 1 / 2 ready
 #pragma unroll 1
-            for (int ch = 0; ch < NT / 32; ++ch) {
+            for (int ch = grp; ch < NT / 32; ch += EG) {
                 uint32_t vu[32];
                 __syncwarp();   // tcgen05.ld is warp-aligned: reconverge after a divergent insert
                 VL_DCHECK(buf * NT + (uint32_t)ch * 32u + 32u <= (uint32_t)Cfg::TMEM_COLS, 202);
                 tmem_ld32(tmem_base + (lane_base << 16) + buf * NT + (uint32_t)ch * 32u, vu);
                 tmem_ld_wait();
-                if (ch == NT / 32 - 1) {
-                    // the accumulator buffer is in registers now: hand it back to the MMA thread
+                if (ch + EG >= NT / 32) {
+                    // this group's last chunk of the accumulator buffer is in registers now: hand it back to the MMA thread
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) {
@@ -669,7 +676,7 @@ mma_scan_kernel(const __grid_constant__ CUtensorMap tmap, const ScanParams p) {
         if (lane == 0) atomicAdd(s_done, 1u);
         if constexpr (!COLLECT) {
             if (q_ok) {
-                const size_t o = ((size_t)split * p.n_queries + qg) * k;
+                const size_t o = ((size_t)(split * EG + grp) * p.n_queries + qg) * k;
 #pragma unroll
                 for (int e = 0; e < kMmaListCap; ++e)
                     if (e < k) {
@@ -696,7 +703,7 @@ mma_scan_kernel(const __grid_constant__ CUtensorMap tmap, const ScanParams p) {
             // the fresher bound saves.
             uint32_t nap = p.poll_ns ? p.poll_ns : 8000u, polls = 0;
             const uint32_t steady_polls = p.poll_steady ? p.poll_steady : 1u;
-            while (*reinterpret_cast<volatile uint32_t*>(s_done) < 4u) {
+            while (*reinterpret_cast<volatile uint32_t*>(s_done) < 4u * EG) {
                 for (int qq = h; qq < kMmaQT; qq += 64) {
                     const int qg = q0 + qq;
                     if (qg >= p.n_queries) continue;
@@ -736,17 +743,17 @@ mma_scan_kernel(const __grid_constant__ CUtensorMap tmap, const ScanParams p) {
                     if (x >= 0 && x < kHistFine - 1) s_bound[qq] = ((uint32_t)x + 1u) << p.hist_shift;   // k-th best < this
                 }
                 // sleep in slices so that the end of the scan is noticed within ~2 us
-                for (uint32_t slept = 0; slept < nap && *reinterpret_cast<volatile uint32_t*>(s_done) < 4u; slept += 2000)
+                for (uint32_t slept = 0; slept < nap && *reinterpret_cast<volatile uint32_t*>(s_done) < 4u * EG; slept += 2000)
                     __nanosleep(min(nap - slept, 2000u));
                 if (++polls > steady_polls) nap = min(nap + nap / 2, 64000u);
             }
         }
         __syncwarp();
-    } else if (warp >= 8) {
-        // ===================== expanders: packed rows -> int8 K slabs =====================
+    } else if (warp >= 8 && warp < 8 + EXPW) {
+        // ===================== expanders: packed rows -> int8 / e2m1 K slabs =====================
         const int ew = warp - 8;
         const int rgrp = ew & 3;            // 32 rows of the CTA's 128
-        const int half = ew >> 2;           // chunks [4 half, 4 half + 4) of every slab
+        const int half = ew >> 2;           // int8: chunks [4 half, 4 half + 4) of every slab (e2m1: one thread does all 8)
         const int r = rgrp * 32 + lane;
         const bool r_ok = r < ROWS;         // (F4 pairs: 112 rows per CTA, the last 16 row slots idle)
         const uint32_t n_mask_words = (p.n_rows + 31u) >> 5;
@@ -781,7 +788,48 @@ mma_scan_kernel(const __grid_constant__ CUtensorMap tmap, const ScanParams p) {
                 if (has_filter) wv &= m[MW + mword];
                 keep = ((wv >> lane) & 1u) ? 0xFFFFFFFFu : 0u;
             }
-            // the whole packed row goes to registers (every slab needs one bit plane of ALL its bytes) and
+            if constexpr (F4) {
+                // slab j <- the row's packed 16-byte chunks 2 j and 2 j + 1 (8 words -> 8 output chunks), loaded slab by
+                // slab: 8 live registers instead of the whole row.  The box goes back to the TMA producer with the last
+                // slab's loads -- and only once they have RETURNED: an mbarrier arrive does not wait for the thread's own
+                // outstanding shared-memory loads (SASS: LDS.128, then SYNCS.ARRIVE with no scoreboard wait), and with the
+                // producer one wake-up away the next box was seen to land before slow wavefronts of those loads had read
+                // the old one: rows of tile i carried chunks of tile i + 2 (scripts/mma_stress.py).  Making the barrier
+                // address depend on the loaded words makes the arrive wait for them.
+#pragma unroll 1
+                for (int j = 0; j < SLABS; ++j, ++g) {
+                    const uint32_t st = g % kMmaBStages;
+                    if (g >= kMmaBStages) mbar_wait(&b_empty[st], ((g / kMmaBStages) - 1) & 1);
+                    const uint32_t row_saddr = b_saddr + st * kMmaSlabBytes;
+                    VL_DCHECK(CG == 2 || !mbar_test_wait(&b_full[st], (g / kMmaBStages) & 1), 207);
+                    const uint32_t src = pk_saddr + (uint32_t)s * Cfg::PK_STRIDE;
+                    const uint4 x0 = lds128(src + ((((uint32_t)(2 * j)) ^ rot) << 4));
+                    const uint4 x1 = lds128(src + ((((uint32_t)(2 * j + 1)) ^ rot) << 4));
+                    if (j == SLABS - 1) {
+                        const uint32_t h = (x0.x ^ x0.y ^ x0.z ^ x0.w ^ x1.x ^ x1.y ^ x1.z ^ x1.w) & (p.one - 1u);   // == 0 at run time
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&pk_empty[s] + h);
+                    }
+                    if (r_ok) {
+                        emit_chunk_f4(x0.x, keep, row_saddr + ((0u ^ r7) << 4));
+                        emit_chunk_f4(x0.y, keep, row_saddr + ((1u ^ r7) << 4));
+                        emit_chunk_f4(x0.z, keep, row_saddr + ((2u ^ r7) << 4));
+                        emit_chunk_f4(x0.w, keep, row_saddr + ((3u ^ r7) << 4));
+                        emit_chunk_f4(x1.x, keep, row_saddr + ((4u ^ r7) << 4));
+                        emit_chunk_f4(x1.y, keep, row_saddr + ((5u ^ r7) << 4));
+                        emit_chunk_f4(x1.z, keep, row_saddr + ((6u ^ r7) << 4));
+                        emit_chunk_f4(x1.w, keep, row_saddr + ((7u ^ r7) << 4));
+                    }
+                    fence_proxy_async_smem();
+                    __syncwarp();
+                    if (lane == 0) {
+                        if constexpr (CG == 2) mbar_arrive_cluster(b_full_remote + st * 8u);
+                        else mbar_arrive(&b_full[st]);
+                    }
+                }
+                continue;
+            }
+            // int8: the whole packed row goes to registers (every slab needs one bit plane of ALL its bytes) and
             // the packed box is handed back to the TMA producer before the expansion starts
             uint32_t pk[W / 4];
             VL_DCHECK(rot < (uint32_t)CHUNKS && r < kMmaRows, 205);
@@ -790,12 +838,7 @@ mma_scan_kernel(const __grid_constant__ CUtensorMap tmap, const ScanParams p) {
                 const uint4 x = lds128(pk_saddr + (uint32_t)s * Cfg::PK_STRIDE + (((uint32_t)c ^ rot) << 4));
                 pk[4 * c] = x.x, pk[4 * c + 1] = x.y, pk[4 * c + 2] = x.z, pk[4 * c + 3] = x.w;
             }
-            // The box may only be handed back once the loads have RETURNED.  An mbarrier arrive does not wait for the
-            // thread's own outstanding shared-memory loads (SASS: LDS.128 x8, then SYNCS.ARRIVE with no scoreboard
-            // wait), and with the TMA producer one wake-up away the next box was seen to land before the last
-            // wavefronts of those loads had read the old one: rows of tile i carried chunks of tile i + 2
-            // (found with the e2m1 path, whose later slabs use the loaded words late; scripts/fp4_debug.py).  Making
-            // the barrier address depend on every loaded word makes the arrive wait for them.
+            // (hand-back only once the loads have returned: see the e2m1 branch above)
             uint32_t h = 0;
 #pragma unroll
             for (int c = 0; c < W / 4; ++c) h ^= pk[c];
@@ -809,21 +852,7 @@ mma_scan_kernel(const __grid_constant__ CUtensorMap tmap, const ScanParams p) {
                 const uint32_t row_saddr = b_saddr + st * kMmaSlabBytes;
                 // ring protocol: nobody may have declared THIS generation of the slab full before it is written
                 VL_DCHECK(CG == 2 || !mbar_test_wait(&b_full[st], (g / kMmaBStages) & 1), 207);
-                if constexpr (F4) {
-                    // slab j <- packed words [8 j, 8 j + 8); this thread's four chunks [4 half, + 4).  The word
-                    // index must be static (registers): the slab switch is unrolled (SLABS <= 4).
-                    if (r_ok) {
-#pragma unroll
-                        for (int jj = 0; jj < SLABS; ++jj) {
-                            if (j != jj) continue;
-#pragma unroll
-                            for (int cc = 0; cc < 4; ++cc) {
-                                const uint32_t x = half == 0 ? pk[8 * jj + cc] : pk[8 * jj + 4 + cc];
-                                emit_chunk_f4(x, keep, row_saddr + ((((uint32_t)(4 * half + cc)) ^ r7) << 4));
-                            }
-                        }
-                    }
-                } else if (half == 0)
+                if (half == 0)
                     emit_half_slab_rows<W, 0>(pk, j, keep, row_saddr, r7);
                 else
                     emit_half_slab_rows<W, 1>(pk, j, keep, row_saddr, r7);

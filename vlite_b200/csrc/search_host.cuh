@@ -144,7 +144,7 @@ int launch_mma_cfg(vl_corpus* c, ScanParams& p, int nq, int k, ScanPlan* plan_ou
     S = std::min<long>(S, std::max<long>(1, p.n_tiles));
     S = std::min<long>(S, 65535);
     const size_t smem = Cfg::SMEM;
-    if (plan_out) *plan_out = ScanPlan{0, 0, 1, kMmaQT * CG, T, (int)S, Cfg::BSTAGES, 1, smem};
+    if (plan_out) *plan_out = ScanPlan{0, 0, Cfg::EPI_GROUPS, kMmaQT * CG, T, (int)S, Cfg::BSTAGES, 1, smem};   // WR = lists per (split, query)
     if (dry) return VL_OK;
     p.stages = c->tune_stages;   // 0 = the configuration's own ring depth
     TRY(allow_max_smem(kern, c->device));
