@@ -25,6 +25,7 @@ for n, nq, k in shapes:
     rel = (done[:nt] - t0) / 1000.0
     d = np.diff(np.concatenate([[0.0], rel]))
     print(f"n={n} nq={nq} k={k}: scan_ms={c.last_timing()[1]:.4f}, tiles traced {nt}, exit at {(int(head[3]) - t0) / 1000:.1f} us")
+    print("  first 24 tiles, us each:", " ".join(f"{x:.1f}" for x in d[:24]), "| inserts:", " ".join(str(int(x & 0xFFFF)) for x in cnt[:24]))
     for lo in range(0, nt, 16):
         hi = min(nt, lo + 16)
         print(f"  tiles {lo:3d}-{hi - 1:3d}: end {rel[hi - 1]:8.1f} us, us/tile {d[lo:hi].mean():6.2f}, rare chunks/tile {(cnt[lo:hi] >> 16).mean():5.2f} of 8, insert iterations/tile {(cnt[lo:hi] & 0xFFFF).mean():6.2f}")

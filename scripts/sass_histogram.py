@@ -9,9 +9,9 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = os.path.join(ROOT, "vlite_b200", "lib", "libvlite_b200.so")
-COLS = ["UTCIMMA", "UTCBAR", "LDTM", "UTCATOMSWS", "UTMALDG", "UBLKCP", "SYNCS", "UCGABAR", "PRMT", "LOP3", "POPC",
-        "IDP", "IMAD", "VIMNMX3", "DFMA", "STS", "LDS", "REDG|RED|ATOM"]
-NOTE = {"UTCIMMA": "tcgen05.mma kind::i8", "UTCBAR": "tcgen05.commit", "LDTM": "tcgen05.ld", "UTCATOMSWS": "tcgen05.alloc",
+COLS = ["UTCIMMA", "UTCOMMA", "UTCBAR", "LDTM", "UTCATOMSWS", "UTMALDG", "UBLKCP", "SYNCS", "UCGABAR", "PRMT", "LOP3", "POPC",
+        "IDP", "IMAD", "VIMNMX3", "FMNMX3|FMNMX", "STTM", "DFMA", "STS", "LDS", "REDG|RED|ATOM"]
+NOTE = {"UTCIMMA": "tcgen05.mma kind::i8", "UTCOMMA": "tcgen05.mma kind::mxf4 block_scale", "UTCBAR": "tcgen05.commit", "LDTM": "tcgen05.ld", "UTCATOMSWS": "tcgen05.alloc",
         "UTMALDG": "cp.async.bulk.tensor (TMA)", "UBLKCP": "cp.async.bulk (TMA 1-D)", "SYNCS": "mbarrier ops",
         "UCGABAR": "barrier.cluster", "IDP": "dp4a", "VIMNMX3": "3-input max", "DFMA": "fp64 fma"}
 
@@ -40,7 +40,7 @@ out = sys.argv[1] if len(sys.argv) > 1 else os.path.join(ROOT, "profiles", "r2_s
 with open(out, "w") as f:
     f.write("# SASS mnemonic counts per kernel of libvlite_b200.so (cuobjdump -sass, sm_100a)\n\n")
     f.write("Static instruction counts (not executed counts).  " + "; ".join(f"`{k}` = {v}" for k, v in NOTE.items()) + ".\n")
-    f.write("No `HMMA`/`IMMA`/`HGMMA` anywhere: the only tensor-core path is tcgen05 (`UTCIMMA`).\n\n")
+    f.write("No `HMMA`/`IMMA`/`HGMMA` anywhere: the only tensor-core path is tcgen05 (`UTCIMMA` int8, `UTCOMMA` block-scaled e2m1).\n\n")
     f.write("| kernel | SASS instrs | " + " | ".join(c.split("|")[0] for c in COLS) + " |\n|---|---:|" + "---:|" * len(COLS) + "\n")
     legacy = 0
     for n in sorted(names, key=lambda x: short[x]):

@@ -616,6 +616,9 @@ mma_scan_kernel(const __grid_constant__ CUtensorMap tmap, const ScanParams p) {
                 uint32_t hm = 0;
 #pragma unroll
                 for (int c = 0; c < 32; ++c) hm |= (v[c] > thrd) ? (1u << c) : 0u;
+                // a 32-column chunk is one word of the tile's eligibility mask: ineligible rows (tombstone, filter,
+                // past the end -- they were expanded to zeros and score K / 2) leave the hit mask here, once
+                hm &= __shfl_sync(kFullMask, vw, ch);
                 while (__any_sync(kFullMask, hm != 0u)) {
                     if (tracing && warp == 4 && lane == 0 && i < 256) p.trace[16 + 256 + i] += 1u;   // insert-loop iterations
                     const bool mine = hm != 0u;
@@ -634,8 +637,7 @@ mma_scan_kernel(const __grid_constant__ CUtensorMap tmap, const ScanParams p) {
                     const AccT pv = (pc & 1) ? s2[1] : s2[0];
                     const uint32_t rit = (uint32_t)ch * 32u + (uint32_t)pc;      // row in tile
                     VL_DCHECK(rit < (uint32_t)NT && (rit >> 5) < (uint32_t)MW, 203);
-                    const uint32_t wv = __shfl_sync(kFullMask, vw, (int)(rit >> 5));
-                    if (mine && pv > thrd && ((wv >> (rit & 31)) & 1u)) {
+                    if (mine && pv > thrd) {
                         const uint32_t score = (uint32_t)(K - (int)pv) >> 1;
                         const uint32_t lrow = t * (uint32_t)NT + rit;
                         const uint64_t key = ((uint64_t)score << 32) | lrow;
