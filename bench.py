@@ -458,7 +458,7 @@ def run_ours(args):
             return float(np.mean(tt)), float(np.mean(ts))
         t, s_ = timed(_capi.XORSUM, 0)
         extra["xorsum_same_workload"] = {"ms_per_step": t, "scan_ms": s_, "qps": nq / (t * 1e-3),
-                                         "kernel": "mma_scan_kernel<128,2,lists,XORSUM> (weighted +-1 contraction, bit 7 as 64 + 64)"}
+                                         "kernel": "mma_scan_kernel<128,2,lists,XORSUM,e2m1> (kind::mxf4, plane-major K, bit weights 2^(7-p) as the query operand's UE8M0 block scales)"}
         t, s_ = timed(_capi.XORSUM, 1)
         extra["xorsum_integer_pipe_kernel"] = {"ms_per_step": t, "scan_ms": s_, "qps": nq / (t * 1e-3),
                                                "kernel": "scan_topk_kernel<128,XORSUM,8,8> (LOP3 + IDP4A)"}

@@ -219,11 +219,11 @@ int vl_debug_checks(int device, uint32_t* failures_out, uint32_t* first_id_out);
 /* which scan kernel answers vl_search on this handle.  0 = automatic (default): batches of at least 24
  * queries (16 for W <= 64) go to the tensor-core kernel -- k <= 16 on its register lists, larger k through its
  * sampled + collect passes -- the rest to the integer-pipe kernel (LOP3 + POPC / DP4A).  On the tensor cores
- * HAMMING is a +-1 contraction in 4-bit floats (tcgen05.mma kind::mxf4: rows expanded bit -> e2m1 in shared
- * memory, unit block scales, fp32 sums of integers below 2^24: exact), XORSUM a weighted +-1 contraction in
- * int8 (kind::i8, exact int32).  1 = integer-pipe kernel only; 2 / 3 = tensor-core kernel with one CTA / a
- * CTA pair per query tile whenever the call is eligible (any batch size); 5 / 6 = the same with HAMMING in
- * its int8 form.  Results are bit-identical on every path (tests/test_gpu_mma_scan.py).  Replaces the same
+ * both metrics are +-1 contractions in 4-bit floats (tcgen05.mma kind::mxf4: rows expanded bit -> e2m1 in shared
+ * memory, fp32 sums of integers below 2^24: exact; HAMMING with unit block scales, XORSUM with the bit weights
+ * 2^(7-p) as the query operand's block scales; XORSUM at W = 32 as weighted int8, kind::i8, exact int32).
+ * 1 = integer-pipe kernel only; 2 / 3 = tensor-core kernel with one CTA / a CTA pair per query tile whenever
+ * the call is eligible (any batch size); 5 / 6 = the same in the int8 form.  Results are bit-identical on every path (tests/test_gpu_mma_scan.py).  Replaces the same
  * reference lines as vl_search: vlite/model.py:71-74 + :84-85. */
 int vl_set_scan_path(vl_corpus* c, int path);
 

@@ -52,7 +52,7 @@ constexpr int kTraceWords = 16 + 512 + 2 * kTraceCtas;   // vl_scan_trace: 16 st
 // an expanded row is 4 W bytes instead of 8 W, and the expansion is 2 instructions per 8 elements instead of
 // 3 per 4.  HAMMING only: XORSUM's bit weights do not fit e2m1.  The 32 scale-factor columns need TMEM room
 // beside the two accumulators, so a CTA pair scores 224 rows per tile (112 per CTA) instead of 256.
-template <int W, int CG, bool F4 = false>
+template <int W, int CG, bool F4 = false, int METRIC = kHamming>
 struct MmaCfg {
     static constexpr int K = W * 8;                 // elements per row
     static constexpr int SLABS = F4 ? W / 32 : W / 16;   // K slabs: 128 B per row = 256 e2m1 / 128 int8
@@ -62,7 +62,7 @@ struct MmaCfg {
     static constexpr int A_BYTES = SLABS * kMmaSlabBytes;
     static constexpr int PK_BYTES = ROWS * W;
     static constexpr int PK_STRIDE = (PK_BYTES + 1023) & ~1023;   // swizzled boxes start on the swizzle period
-    static constexpr int SF_COLS = F4 ? 32 : 0;     // scale factors: 16 columns for A, 16 for B
+    static constexpr int SF_COLS = F4 ? 48 : 0;     // scale factors: 32 columns for A (XORSUM: 4 per bit plane), 16 for B
     // F4: expansion is 2 instructions per 8 elements and the MMAs take half the time, so the accumulator read-out is
     // the critical role: 4 expander warps (one thread per row) and TWO epilogue groups of 4 warps (warps 4-7: even
     // 32-column chunks, warps 12-15: odd ones), each thread with its own k-list -> 2 lists per (split, query)
@@ -239,6 +239,30 @@ __device__ __forceinline__ void emit_chunk_f4(uint32_t x, uint32_t keep, uint32_
     sts128(chunk_saddr, ((x << 3) & sgn) | one, ((x << 2) & sgn) | one, ((x << 1) & sgn) | one, (x & sgn) | one);
 }
 
+// XORSUM as e2m1: K order = bit planes (element p * W + byte), so that every 32-element block lies in ONE plane and
+// the plane's weight 2^(7 - p) can ride the query operand's UE8M0 block scale (127 + 7 - p); rows and queries are
+// plain +-1.  One 16-byte output chunk = plane p of 32 consecutive bytes (8 packed words): output word t takes the
+// bytes of words 2 t (even nibbles) and 2 t + 1 (odd nibbles); s = 7 - p selects the bit.
+__device__ __forceinline__ uint32_t plane_word_f4(uint32_t xa, uint32_t xb, uint32_t s, uint32_t keep) {
+    // bit s of byte i -> the sign bit of nibble 2 i (position 8 i + 3) / 2 i + 1 (8 i + 7): one rotate each -- whatever
+    // wraps around lands on positions the masks drop -- then two LOP3 (masks pre-ANDed with keep): 4 instructions
+    const uint32_t ra = __funnelshift_r(xa, xa, s - 3u), rb = __funnelshift_r(xb, xb, s - 7u);
+    return ((ra & (0x08080808u & keep)) | (0x22222222u & keep)) | (rb & (0x80808080u & keep));
+}
+__device__ __forceinline__ void emit_plane_chunk_f4(uint32_t x0, uint32_t x1, uint32_t x2, uint32_t x3, uint32_t x4, uint32_t x5,
+                                                    uint32_t x6, uint32_t x7, uint32_t s, uint32_t keep, uint32_t chunk_saddr) {
+    sts128(chunk_saddr, plane_word_f4(x0, x1, s, keep), plane_word_f4(x2, x3, s, keep), plane_word_f4(x4, x5, s, keep),
+           plane_word_f4(x6, x7, s, keep));
+}
+// 16 registers -> 32 lanes x 16 consecutive 32-bit columns of TMEM (lane = thread)
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+        "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]), "r"(v[10]),
+        "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
+        : "memory");
+}
+
 // ---- bit -> int8 expansion -----------------------------------------------------------------------
 // Element order of an expanded row ("bit planes"): e = p * W + byte, p = 0..7 <-> bit (7 - p) of every
 // byte -- the same permutation of K for corpus rows and queries, so the contraction is unchanged.
@@ -320,13 +344,14 @@ __device__ __forceinline__ void emit_half_slab_rt(int j, const uint32_t (&pk)[W 
 template <int W, int CG, bool COLLECT, int METRIC, bool F4 = false>
 __global__ void __launch_bounds__(kMmaThreads, 1)
 mma_scan_kernel(const __grid_constant__ CUtensorMap tmap, const ScanParams p) {
-    using Cfg = MmaCfg<W, CG, F4>;
+    using Cfg = MmaCfg<W, CG, F4, METRIC>;
     if (p.gate != nullptr && *p.gate == 0) return;   // uniform over the grid (and over a cluster)
     constexpr int SLABS = Cfg::SLABS, NT = Cfg::NT, MW = Cfg::MW, ROWS = Cfg::ROWS;
     constexpr int EXPW = Cfg::EXP_WARPS, EG = Cfg::EPI_GROUPS;
     constexpr int CHUNKS = W / 16;
     constexpr bool XS = METRIC == kXorSum;
-    static_assert(!(F4 && XS), "the 4-bit contraction is +-1 only");
+    static_assert(!(F4 && XS && W < 64), "XORSUM as e2m1: a K = 64 step must lie inside one bit plane (one block scale)");
+    constexpr bool F4H = F4 && !XS, F4X = F4 && XS;   // e2m1 forms: HAMMING (word-major K order) / XORSUM (plane-major, scaled)
     using AccT = typename std::conditional<F4, float, int>::type;   // accumulator type as the epilogue compares it
     constexpr int K = XS ? 255 * W : 8 * W;      // score = (K - dot) / 2: the dot product of a perfect match
     const bool tracing = p.trace != nullptr && blockIdx.x == 0 && blockIdx.y == 0;
@@ -387,7 +412,28 @@ mma_scan_kernel(const __grid_constant__ CUtensorMap tmap, const ScanParams p) {
     if (warp == 2) tmem_alloc<CG>(s_tmem, (uint32_t)Cfg::TMEM_COLS);
 
     // ---- A operand: expand this CTA's queries once (zeros past n_queries; XORSUM: weighted) ----
-    if constexpr (F4) {
+    if constexpr (F4X) {
+        // plane-major: chunk G of the expanded query = plane G / (W / 32) of bytes [32 (G % (W / 32)), + 32)
+        constexpr int CPP = W / 32;                 // chunks per plane
+        const int ql = threadIdx.x % kMmaQT;
+        const int part = threadIdx.x / kMmaQT;
+        const int qg = q0 + ql;
+        const uint32_t keep = qg < p.n_queries ? 0xFFFFFFFFu : 0u;
+        const uint32_t row_saddr = smem_u32(sA) + (uint32_t)ql * 128u;
+        const uint32_t r7 = (uint32_t)(ql & 7);
+        for (int G = part; G < SLABS * 8; G += kMmaThreads / kMmaQT) {
+            const int pl = G / CPP, bb = G % CPP;
+            uint4 xa = make_uint4(0u, 0u, 0u, 0u), xb = xa;
+            if (keep) {
+                const uint4* src = reinterpret_cast<const uint4*>(p.queries + (size_t)qg * W + (size_t)bb * 32);
+                xa = src[0];
+                xb = src[1];
+            }
+            emit_plane_chunk_f4(xa.x, xa.y, xa.z, xa.w, xb.x, xb.y, xb.z, xb.w, (uint32_t)(7 - pl), keep,
+                                row_saddr + (uint32_t)(G >> 3) * kMmaSlabBytes + ((((uint32_t)(G & 7)) ^ r7) << 4));
+        }
+        fence_proxy_async_smem();
+    } else if constexpr (F4H) {
         const int ql = threadIdx.x % kMmaQT;        // 4 threads per query, each a quarter of the half-slabs
         const int part = threadIdx.x / kMmaQT;
         const int qg = q0 + ql;
@@ -433,13 +479,26 @@ mma_scan_kernel(const __grid_constant__ CUtensorMap tmap, const ScanParams p) {
         fence_proxy_async_smem();
     }
     if constexpr (F4) {
-        // unit block scales (UE8M0 0x7F = 2^0) in every byte of the 32 scale-factor columns of all 128 lanes:
+        // unit block scales (UE8M0 0x7F = 2^0) in every byte of the 48 scale-factor columns of all 128 lanes:
         // whatever bytes an MMA reads for its A and B scale vectors, it reads 1.0
         __syncthreads();                               // s_tmem is written
         if (warp >= 4 && warp < 8) {
             const uint32_t sf = *s_tmem + ((uint32_t)((warp & 3) * 32) << 16) + 2u * NT;
-            tmem_fill16(sf, 0x7F7F7F7Fu);
-            tmem_fill16(sf + 16u, 0x7F7F7F7Fu);
+            if constexpr (F4X) {
+                // the query operand's scales: plane p = 2^(7 - p) in every byte of columns [4 p, 4 p + 4) (a scale
+                // address must be 4-column aligned; both 32-element blocks of a K = 64 step lie in one plane)
+                uint32_t sv[16];
+#pragma unroll
+                for (int c = 0; c < 16; ++c) sv[c] = (uint32_t)(127 + 7 - c / 4) * 0x01010101u;
+                tmem_st16(sf, sv);
+#pragma unroll
+                for (int c = 0; c < 16; ++c) sv[c] = (uint32_t)(127 + 3 - c / 4) * 0x01010101u;
+                tmem_st16(sf + 16u, sv);
+            } else {
+                tmem_fill16(sf, 0x7F7F7F7Fu);
+                tmem_fill16(sf + 16u, 0x7F7F7F7Fu);
+            }
+            tmem_fill16(sf + 32u, 0x7F7F7F7Fu);        // the row operand: 1.0
             tmem_st_wait();
         }
     }
@@ -476,7 +535,7 @@ mma_scan_kernel(const __grid_constant__ CUtensorMap tmap, const ScanParams p) {
         // ===================== MMA issuer: one thread of the leader CTA =====================
         if (rank == 0 && lane == 0) {
             constexpr uint32_t idesc = F4 ? umma_idesc_mxf4(kMmaQT * CG, NT) : umma_idesc_i8(kMmaQT * CG, NT);
-            const uint32_t sfa = tmem_base + 2u * NT, sfb = sfa + 16u;
+            const uint32_t sfa = tmem_base + 2u * NT, sfb = sfa + 32u;
             const uint32_t a_saddr = smem_u32(sA), b_saddr = smem_u32(sB);
             uint32_t g = 0;   // slab counter
             for (uint32_t i = 0; i < my_tiles; ++i) {
@@ -498,7 +557,9 @@ mma_scan_kernel(const __grid_constant__ CUtensorMap tmap, const ScanParams p) {
 #pragma unroll
                     for (int kk = 0; kk < 4; ++kk) {   // K = 32 int8 (64 e2m1) = 32 B per instruction: +2 in the address field
                         if constexpr (F4) {
-                            umma_mxf4<CG>(d_tmem, ad + (uint64_t)(kk * 2), bd + (uint64_t)(kk * 2), idesc, (j | kk) != 0 ? 1u : 0u, sfa, sfb);
+                            // XORSUM: this K = 64 step is elements [64 (4 j + kk), + 64) = plane 64 (4 j + kk) / W: its scale column
+                            const uint32_t sfa_k = F4X ? sfa + 4u * (uint32_t)((64 * (4 * j + kk)) / W) : sfa;
+                            umma_mxf4<CG>(d_tmem, ad + (uint64_t)(kk * 2), bd + (uint64_t)(kk * 2), idesc, (j | kk) != 0 ? 1u : 0u, sfa_k, sfb);
                             continue;
                         }
                         umma_i8<CG>(d_tmem, ad + (uint64_t)(kk * 2), bd + (uint64_t)(kk * 2), idesc, (j | kk) != 0 ? 1u : 0u);
@@ -791,13 +852,15 @@ mma_scan_kernel(const __grid_constant__ CUtensorMap tmap, const ScanParams p) {
                 keep = ((wv >> lane) & 1u) ? 0xFFFFFFFFu : 0u;
             }
             if constexpr (F4) {
-                // slab j <- the row's packed 16-byte chunks 2 j and 2 j + 1 (8 words -> 8 output chunks), loaded slab by
-                // slab: 8 live registers instead of the whole row.  The box goes back to the TMA producer with the last
-                // slab's loads -- and only once they have RETURNED: an mbarrier arrive does not wait for the thread's own
-                // outstanding shared-memory loads (SASS: LDS.128, then SYNCS.ARRIVE with no scoreboard wait), and with the
-                // producer one wake-up away the next box was seen to land before slow wavefronts of those loads had read
-                // the old one: rows of tile i carried chunks of tile i + 2 (scripts/mma_stress.py).  Making the barrier
-                // address depend on the loaded words makes the arrive wait for them.
+                // Packed chunks are loaded slab by slab (8 live registers instead of the whole row).  HAMMING: slab j <-
+                // the row's packed 16-byte chunks 2 j and 2 j + 1 (8 words -> 8 output chunks).  XORSUM (plane-major K):
+                // slab j = bit planes [j PPS, + PPS) of ALL the row's bytes: every 32-byte block bb (two packed chunks)
+                // is read once per slab and gives one output chunk per plane.  The box goes back to the TMA producer
+                // with the last slab's loads -- and only once they have RETURNED: an mbarrier arrive does not wait for
+                // the thread's own outstanding shared-memory loads (SASS: LDS.128, then SYNCS.ARRIVE with no scoreboard
+                // wait), and with the producer one wake-up away the next box was seen to land before slow wavefronts of
+                // those loads had read the old one: rows of tile i carried chunks of tile i + 2 (scripts/mma_stress.py).
+                // Making the barrier address depend on the loaded words makes the arrive wait for them.
 #pragma unroll 1
                 for (int j = 0; j < SLABS; ++j, ++g) {
                     const uint32_t st = g % kMmaBStages;
@@ -805,22 +868,39 @@ mma_scan_kernel(const __grid_constant__ CUtensorMap tmap, const ScanParams p) {
                     const uint32_t row_saddr = b_saddr + st * kMmaSlabBytes;
                     VL_DCHECK(CG == 2 || !mbar_test_wait(&b_full[st], (g / kMmaBStages) & 1), 207);
                     const uint32_t src = pk_saddr + (uint32_t)s * Cfg::PK_STRIDE;
-                    const uint4 x0 = lds128(src + ((((uint32_t)(2 * j)) ^ rot) << 4));
-                    const uint4 x1 = lds128(src + ((((uint32_t)(2 * j + 1)) ^ rot) << 4));
-                    if (j == SLABS - 1) {
-                        const uint32_t h = (x0.x ^ x0.y ^ x0.z ^ x0.w ^ x1.x ^ x1.y ^ x1.z ^ x1.w) & (p.one - 1u);   // == 0 at run time
-                        __syncwarp();
-                        if (lane == 0) mbar_arrive(&pk_empty[s] + h);
+                    uint32_t h = 0;
+                    if constexpr (F4X) {
+                        constexpr int CPP = W / 32, PPS = 8 / CPP;   // chunks per plane, planes per slab
+#pragma unroll
+                        for (int bb = 0; bb < CPP; ++bb) {
+                            const uint4 x0 = lds128(src + ((((uint32_t)(2 * bb)) ^ rot) << 4));
+                            const uint4 x1 = lds128(src + ((((uint32_t)(2 * bb + 1)) ^ rot) << 4));
+                            h ^= x0.x ^ x0.y ^ x0.z ^ x0.w ^ x1.x ^ x1.y ^ x1.z ^ x1.w;
+                            if (r_ok) {
+#pragma unroll
+                                for (int pp = 0; pp < PPS; ++pp)
+                                    emit_plane_chunk_f4(x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w, 7u - (uint32_t)(j * PPS + pp), keep,
+                                                        row_saddr + ((((uint32_t)(pp * CPP + bb)) ^ r7) << 4));
+                            }
+                        }
+                    } else {
+                        const uint4 x0 = lds128(src + ((((uint32_t)(2 * j)) ^ rot) << 4));
+                        const uint4 x1 = lds128(src + ((((uint32_t)(2 * j + 1)) ^ rot) << 4));
+                        h = x0.x ^ x0.y ^ x0.z ^ x0.w ^ x1.x ^ x1.y ^ x1.z ^ x1.w;
+                        if (r_ok) {
+                            emit_chunk_f4(x0.x, keep, row_saddr + ((0u ^ r7) << 4));
+                            emit_chunk_f4(x0.y, keep, row_saddr + ((1u ^ r7) << 4));
+                            emit_chunk_f4(x0.z, keep, row_saddr + ((2u ^ r7) << 4));
+                            emit_chunk_f4(x0.w, keep, row_saddr + ((3u ^ r7) << 4));
+                            emit_chunk_f4(x1.x, keep, row_saddr + ((4u ^ r7) << 4));
+                            emit_chunk_f4(x1.y, keep, row_saddr + ((5u ^ r7) << 4));
+                            emit_chunk_f4(x1.z, keep, row_saddr + ((6u ^ r7) << 4));
+                            emit_chunk_f4(x1.w, keep, row_saddr + ((7u ^ r7) << 4));
+                        }
                     }
-                    if (r_ok) {
-                        emit_chunk_f4(x0.x, keep, row_saddr + ((0u ^ r7) << 4));
-                        emit_chunk_f4(x0.y, keep, row_saddr + ((1u ^ r7) << 4));
-                        emit_chunk_f4(x0.z, keep, row_saddr + ((2u ^ r7) << 4));
-                        emit_chunk_f4(x0.w, keep, row_saddr + ((3u ^ r7) << 4));
-                        emit_chunk_f4(x1.x, keep, row_saddr + ((4u ^ r7) << 4));
-                        emit_chunk_f4(x1.y, keep, row_saddr + ((5u ^ r7) << 4));
-                        emit_chunk_f4(x1.z, keep, row_saddr + ((6u ^ r7) << 4));
-                        emit_chunk_f4(x1.w, keep, row_saddr + ((7u ^ r7) << 4));
+                    if (j == SLABS - 1) {
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&pk_empty[s] + (h & (p.one - 1u)));   // (the offset is 0 at run time)
                     }
                     fence_proxy_async_smem();
                     __syncwarp();

@@ -134,7 +134,7 @@ int mma_path_for(const vl_corpus* c, const ScanParams& p, int nq, int k, int met
 
 template <int W, int CG, bool COLLECT, int METRIC, bool F4 = false>
 int launch_mma_cfg(vl_corpus* c, ScanParams& p, int nq, int k, ScanPlan* plan_out, bool dry) {
-    using Cfg = MmaCfg<W, CG, F4>;
+    using Cfg = MmaCfg<W, CG, F4, METRIC>;
     auto kern = mma_scan_kernel<W, CG, COLLECT, METRIC, F4>;
     const uint32_t all_tiles = (uint32_t)((p.n_rows + Cfg::NT - 1) / Cfg::NT);
     p.n_tiles = (all_tiles + p.tile_stride - 1) / p.tile_stride;
@@ -167,8 +167,8 @@ int launch_mma_cfg(vl_corpus* c, ScanParams& p, int nq, int k, ScanPlan* plan_ou
     return VL_OK;
 }
 
-// HAMMING runs the +-1 contraction in 4-bit floats (kind::mxf4, exact) unless VLITE_B200_FP4=0 or the
-// scan path asks for the int8 form (vl_set_scan_path 5 / 6)
+// The +-1 contraction runs in 4-bit floats (kind::mxf4, exact; XORSUM with its bit weights as block scales, W >= 64)
+// unless VLITE_B200_FP4=0 or the scan path asks for the int8 form (vl_set_scan_path 5 / 6)
 bool mma_use_f4(const vl_corpus* c) {
     static const bool env_on = [] { const char* e = getenv("VLITE_B200_FP4"); return !(e && atoi(e) == 0); }();
     return env_on && c->scan_path != 5 && c->scan_path != 6;
@@ -177,7 +177,7 @@ bool mma_use_f4(const vl_corpus* c) {
 template <int W, int METRIC>
 int launch_mma_wm(vl_corpus* c, ScanParams& p, int nq, int k, int cg, ScanPlan* plan, bool dry) {
     const bool collect = p.collect_thr != nullptr;
-    if constexpr (METRIC == kHamming) {
+    if constexpr (METRIC == kHamming || W >= 64) {   // (XORSUM as e2m1 needs a K = 64 step inside one bit plane: W >= 64)
         if (mma_use_f4(c)) {
             if (cg == 2)
                 return collect ? launch_mma_cfg<W, 2, true, METRIC, true>(c, p, nq, k, plan, dry)
