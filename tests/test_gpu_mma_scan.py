@@ -3,8 +3,8 @@ expanded bit -> int8 in shared memory) through the C ABI against the CPU oracle.
 
 Bar: bit-exact scores and row lists under the (score, row) tie-break, identical to the
 integer-pipe kernel on every shape.  vl_set_scan_path forces the kernel: 2 = one CTA per query
-tile, 3 = CTA pairs (cta_group::2); HAMMING then runs as a 4-bit-float contraction (kind::mxf4, 224-row
-tiles for pairs), 5 / 6 ask for its int8 form (kind::i8, 256-row tiles)."""
+tile, 3 = CTA pairs (cta_group::2); both metrics then run as 4-bit-float contractions (kind::mxf4, 224-row
+tiles for pairs; XORSUM with its bit weights as block scales), 5 / 6 ask for the int8 form (kind::i8, 256-row tiles)."""
 import numpy as np
 import pytest
 
@@ -13,7 +13,7 @@ from oracle import cscan, synth
 pytestmark = pytest.mark.gpu
 
 HAMMING, XORSUM = 0, 1
-PATHS = [2, 3, 5, 6]   # 2 / 3: HAMMING as e2m1 (kind::mxf4), XORSUM as int8; 5 / 6: HAMMING as int8 (kind::i8)
+PATHS = [2, 3, 5, 6]   # 2 / 3: e2m1 (kind::mxf4; XORSUM with block-scale weights, int8 at W = 32); 5 / 6: int8 (kind::i8)
 
 
 def _check(c, corpus, queries, k, mask_words=None, base_row=0, metric=HAMMING):
