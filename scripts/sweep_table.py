@@ -25,7 +25,7 @@ if __name__ == "__main__":
     recs = [json.loads(line) for line in open(sys.argv[1]) if line.strip()]
     _, n_main, n_k = shapes()
     main, ksw, k1 = recs[:n_main], recs[n_main:n_main + n_k], recs[n_main + n_k:]
-    out = ["# Scan sweep, one B200 (round 1, final kernels)", "",
+    out = ["# Scan sweep, one B200 (final kernels of the round that wrote this file)", "",
            "`scripts/scan_bench.py $(python scripts/sweep_table.py shapes)`: device-resident queries and outputs, CUDA events",
            "inside the library around scan + merge, median of 5 after 2 warm-ups, k = 10 unless stated. The 500k-row corpora",
            "(32-64 MB) stay in L2 between repetitions; the 32M-row ones (2-4 GB) do not. `roof` = max(N*W / 6554.9 GB/s,",
@@ -38,7 +38,7 @@ if __name__ == "__main__":
         out.append(f"| {r['n']:,} | {r['w']} | {'HAMMING' if r['metric'] == 0 else 'XORSUM'} | {r['nq']} | {r['scan_ms']:.4f} "
                    f"| {r['total_ms']:.4f} | {r['qps']:,} | {r['GBps']:,} | {r['Tpopc']:.2f} | {r['roof_frac']:.2f} |")
     out += ["", "## k sweep at config 2 (500k x 128 B, 1024 queries, HAMMING)", "",
-            "k <= 32: per-warp register lists; k > 32: sampled threshold + collect + select.", "",
+            "k <= 16: per-thread register lists of the tensor-core kernel; larger k: sampled threshold + collect + select.", "",
             "| k | scan ms | total ms | queries/s | roof |", "|---:|---:|---:|---:|---:|"]
     for r in ksw:
         out.append(f"| {r['k']} | {r['scan_ms']:.4f} | {r['total_ms']:.4f} | {r['qps']:,} | {r['roof_frac']:.2f} |")
