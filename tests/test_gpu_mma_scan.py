@@ -201,3 +201,64 @@ def test_many_tiles_per_cta_repeated(gpu, path, nq):
             s, r = c.search(queries, 10, HAMMING)
             np.testing.assert_array_equal(s, es)
             np.testing.assert_array_equal(r, er)
+
+
+@pytest.mark.parametrize("k", [1000, 2048])
+def test_large_k_batch_does_not_fall_back(gpu, k):
+    """Regression: the sampled threshold of the large-k path used to be the 16th best of its sample; one query in
+    ~7000 then has fewer than k rows at or below it, and ONE such query in a batch sends ALL of it to the exact
+    multi-pass fallback (k = 2048 at 500k x 1024 queries: 0.8 -> 166 ms).  The tensor-core pass now takes the 64th
+    best of the merged lists: three different batches must all stay on the fast path (a 20x margin on time) and
+    agree with the oracle."""
+    torch = pytest.importorskip("torch")
+    n, w, nq = 500_000, 128, 1024
+    host = synth.corpus_rows(0, 0, n, w)
+    with gpu.Corpus(w, capacity_rows=n) as c:
+        c.fill_synthetic(0, 0, n)
+        c.set_timing(True)
+        ds = torch.empty((nq, k), dtype=torch.int32, device="cuda")
+        dr = torch.empty((nq, k), dtype=torch.int64, device="cuda")
+        for seed in (1, 2, 3):
+            q = synth.uniform_queries(seed, nq, w)
+            dq = torch.from_numpy(q).cuda()
+            for _ in range(2):
+                c.search(dq, k, HAMMING, None, ds, dr)
+            total_ms, _ = c.last_timing()
+            assert total_ms < 20.0, f"k={k} seed={seed}: {total_ms:.1f} ms -- the exact fallback ran"
+            sub = np.r_[0:4, nq - 4:nq]
+            es, er = cscan.search(q[sub], host, k, HAMMING)
+            np.testing.assert_array_equal(ds.cpu().numpy().view(np.uint32)[sub], es)
+            np.testing.assert_array_equal(dr.cpu().numpy().view(np.uint64)[sub], er)
+
+
+@pytest.mark.parametrize("nq,k", [(1024, 1000), (4096, 256)])
+def test_large_k_many_tiles_per_cta_stays_on_the_fast_path(gpu, nq, k):
+    """The sampled pass merges its 16-entry lists to the 64 best of their union: the bound the CTAs share must then
+    stand for rank 64 as well (with the rank-16 bound, lists of CTAs that visit many sampled tiles keep only rows
+    in the global top 16, the 64th of the union is junk, every buffer overflows and the batch falls back: 245 ms
+    instead of 5 ms at 4M rows).  2M rows = 20+ sampled tiles per CTA; results checked by size-independent
+    properties (sorted, unique rows, scores re-computed on the host from the generator)."""
+    torch = pytest.importorskip("torch")
+    n, w = 2_000_000, 128
+    q = synth.uniform_queries(5, nq, w)
+    with gpu.Corpus(w, capacity_rows=n) as c:
+        c.fill_synthetic(0, 0, n)
+        c.set_timing(True)
+        dq = torch.from_numpy(q).cuda()
+        ds = torch.empty((nq, k), dtype=torch.int32, device="cuda")
+        dr = torch.empty((nq, k), dtype=torch.int64, device="cuda")
+        for _ in range(2):
+            c.search(dq, k, HAMMING, None, ds, dr)
+        total_ms, _ = c.last_timing()
+        assert total_ms < 60.0, f"{total_ms:.1f} ms -- the exact fallback ran"
+        s = ds.cpu().numpy().view(np.uint32)
+        r = dr.cpu().numpy().view(np.uint64)
+    for qi in (0, nq // 2, nq - 1):
+        rows = r[qi].astype(np.int64)
+        assert len(np.unique(rows)) == k and rows.max() < n
+        key = (s[qi].astype(np.uint64) << np.uint64(32)) | r[qi]
+        assert np.all(np.diff(key.astype(np.float64)) >= 0) and np.all(key[1:] > key[:-1])
+        sub = np.stack([synth.corpus_rows(0, int(x), 1, w)[0] for x in rows[:: max(1, k // 50)]])
+        true = np.unpackbits(sub ^ q[qi], axis=1).sum(axis=1)
+        np.testing.assert_array_equal(true, s[qi][:: max(1, k // 50)])
+

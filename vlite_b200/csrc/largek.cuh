@@ -15,6 +15,7 @@ namespace vl {
 
 constexpr int kSelectThreads = 512;
 constexpr int kLargeKSample = 32;   // sample list length cap: the register-list fast path of the scan
+constexpr int kLargeKThrRank = 64;  // tensor-core sampled pass: the threshold is the 64th best of the merged 16-entry lists
 
 __global__ void extract_thr_kernel(const uint32_t* __restrict__ sample_scores, const uint64_t* __restrict__ sample_rows,
                                    int n_queries, int ks, uint32_t* __restrict__ thr) {

@@ -605,7 +605,10 @@ mma_scan_kernel(const __grid_constant__ CUtensorMap tmap, const ScanParams p) {
         };
         AccT thrd = to_dot(thr);
         const uint32_t n_mask_words = (p.n_rows + 31u) >> 5;
-        const bool use_tau = !COLLECT && q_ok;
+        // (tau = the smallest k-th best of any list: a bound on the k-th best row only.  When the caller wants the
+        // k_bound best of the lists' union it would prune rows ranked k + 1 .. k_bound: the histogram bound alone
+        // is shared then, with k_bound as its target count)
+        const bool use_tau = !COLLECT && q_ok && p.k_bound <= p.k;
         uint32_t* tau_ptr = p.tau + (q_ok ? qg : 0);
         uint32_t tau_pref = kSentinelScore;
         bool dirty = false;
@@ -759,7 +762,7 @@ mma_scan_kernel(const __grid_constant__ CUtensorMap tmap, const ScanParams p) {
         // it (two L2 round trips per query) and publish bound + 1 to shared memory, off the epilogue's path.
         if (!COLLECT && p.hist != nullptr) {
             const int h = (warp - 2) * 32 + lane;
-            const int k = p.k;
+            const int k = p.k_bound > p.k ? p.k_bound : p.k;   // the rank the published bound stands for
             // the bound tightens like 1 / (rows seen): poll at geometrically growing intervals (8 us .. 64 us).
             // Measured on one box (cfg2 scan): first interval 1 / 8 / 16 us -> 0.4455 / 0.4385 / 0.4361 ms, a
             // fixed 3 us for the first 32 polls -> 0.452 ms: polling more often costs more L2 traffic than

@@ -294,11 +294,15 @@ int merge_levels(cudaStream_t st, const uint32_t* in_s, const uint64_t* in_r, si
 // k <= 128: one scan + merge.  Larger k: ceil(k/128) passes, each returning the next 128 keys after
 // a per-query cursor (exact and deterministic for any tie pattern).  `p` arrives with the corpus,
 // queries and masks filled in.
+// k_merge > k (single pass only): the final merge keeps the k_merge best of the union of the k-entry lists (the
+// sampled pass of large k wants a deeper rank than a register list holds)
 int search_lists(vl_corpus* c, ScanParams p, int n_queries, int k, int metric, uint32_t* o_s, uint64_t* o_r,
-                 int out_stride = 0, const int* gate = nullptr) {
+                 int out_stride = 0, const int* gate = nullptr, int k_merge = 0) {
     p.gate = gate;
     cudaStream_t st = c->stream;
-    if (out_stride == 0) out_stride = k;
+    if (k_merge <= k || k > kWarpListMaxK) k_merge = 0;
+    if (out_stride == 0) out_stride = k_merge ? k_merge : k;
+    p.k_bound = k_merge;
     const int n_pass = (k + kWarpListMaxK - 1) / kWarpListMaxK;
     // tau[Q] | cursor score[Q] | cursor row[Q] | histogram[Q][1056] (k <= 32, not for huge batches)
     // (the histogram is read only by the one-warp-per-query configuration, Q > 32; the shared bound
@@ -348,7 +352,8 @@ int search_lists(vl_corpus* c, ScanParams p, int n_queries, int k, int metric, u
         p.fuse_keys = nullptr;
         const size_t n_lists = (size_t)plan.S * plan.WR;
         const size_t dense = (size_t)n_queries * k_pass;
-        const size_t n_part = (n_lists + merge_tmp_lists(n_lists)) * dense;
+        const int k_out = k_merge ? k_merge : k_pass;
+        const size_t n_part = n_lists * dense + merge_tmp_lists(n_lists) * (size_t)n_queries * k_out;
         TRY(c->part_s.ensure(n_part * 4));
         TRY(c->part_r.ensure(n_part * 8));
         p.part_scores = static_cast<uint32_t*>(c->part_s.p);
@@ -360,7 +365,7 @@ int search_lists(vl_corpus* c, ScanParams p, int n_queries, int k, int metric, u
         if (p.hist) CU(cudaMemsetAsync(p.hist, 0, hist_bytes, st));
         TRY(launch_scan(c, p, n_queries, k_pass, metric, nullptr, /*dry=*/false));
         if (c->timing && pass == 0 && p.tile_stride == 1 && gate == nullptr) CU(cudaEventRecord(c->ev1, st));
-        TRY(merge_levels(st, p.part_scores, p.part_rows, n_lists, dense, dense, n_queries, k_pass, k_pass, o_s, o_r,
+        TRY(merge_levels(st, p.part_scores, p.part_rows, n_lists, dense, dense, n_queries, k_pass, k_out, o_s, o_r,
                          out_stride, pass * kWarpListMaxK, p.part_scores + n_lists * dense,
                          p.part_rows + n_lists * dense, gate));
         if (pass + 1 < n_pass) {
@@ -404,16 +409,25 @@ int search_large_k(vl_corpus* c, ScanParams p, int n_queries, int k, int metric,
     // between the ~3k rows expected at or below it and both failure modes (fewer than k: fallback;
     // more than cap >= 6k: fallback)
     // (16 whenever the tensor-core kernel can take the sampled pass: its register lists hold 16)
-    const int ks = mma_path_for(c, p, n_queries, kMmaListCap, metric) ? kMmaListCap
-                                                                     : std::min(kLargeKSample, std::max(16, k / 4));
+    const bool mma_sample = mma_path_for(c, p, n_queries, kMmaListCap, metric) != 0;
+    const int ks = mma_sample ? kMmaListCap : std::min(kLargeKSample, std::max(16, k / 4));
+    // The threshold's rank in the sample.  A 16-deep estimate is too noisy for a batch: the k-th best row lies
+    // above the threshold of one query in ~7000 (P[Poisson(16/3) >= 16]), and ONE such query sends the whole
+    // batch to the exact fallback (seen: k = 2048 at 500k x 1024 queries, 0.8 -> 166 ms).  The tensor-core pass
+    // therefore merges its 16-entry lists (two per row split) to the 64 best of their union and samples four
+    // times as many tiles: relative spread 12.5 %, both failure modes below 1e-10 per query.  (A list that holds
+    // more than 16 of those 64 only raises the threshold: more candidates, never fewer.)
+    // (k <= 213: the 5 % sampling floor -- every 20th tile -- already puts k / 20 <= 10.7 of the true top k in the
+    // sample: rank 32 is as safe there (P[Poisson(10.7) >= 32] ~ 1e-7) and collects 640 rows per query, not 1280)
+    const int thr_rank = mma_sample ? ((3 * k) / 32 < 20 ? 32 : kLargeKThrRank) : ks;
     // sample every `stride`-th tile: at least 3k expected candidates, and never more than 5 % of a scan
-    const uint32_t stride = std::max<uint32_t>(20u, (3u * (uint32_t)k) / (uint32_t)ks);
+    const uint32_t stride = std::max<uint32_t>(20u, (3u * (uint32_t)k) / (uint32_t)thr_rank);
     TRY(c->lk_keys.ensure(key_bytes));
-    TRY(c->lk_misc.ensure((size_t)n_queries * (4 + 4 + kLargeKSample * 12) + 64));
+    TRY(c->lk_misc.ensure((size_t)n_queries * (4 + 4 + kLargeKThrRank * 12) + 64));
     uint32_t* thr = static_cast<uint32_t*>(c->lk_misc.p);
     uint32_t* cnt = thr + n_queries;
     uint64_t* smp_r = reinterpret_cast<uint64_t*>(cnt + n_queries);  // 8*Q bytes in: 8-byte aligned
-    uint32_t* smp_s = reinterpret_cast<uint32_t*>(smp_r + (size_t)n_queries * kLargeKSample);
+    uint32_t* smp_s = reinterpret_cast<uint32_t*>(smp_r + (size_t)n_queries * kLargeKThrRank);
     int* flags = c->d_err + 1;   // the fallback gate (d_err[0] is the repack error flag)
     if (c->count <= cap) {
         // the whole shard fits a buffer: no sampling, collect every eligible row
@@ -421,8 +435,8 @@ int search_large_k(vl_corpus* c, ScanParams p, int n_queries, int k, int metric,
     } else {
         ScanParams ps = p;
         ps.tile_stride = stride;
-        TRY(search_lists(c, ps, n_queries, ks, metric, smp_s, smp_r));
-        extract_thr_kernel<<<(n_queries + 127) / 128, 128, 0, st>>>(smp_s, smp_r, n_queries, ks, thr);
+        TRY(search_lists(c, ps, n_queries, ks, metric, smp_s, smp_r, 0, nullptr, thr_rank));
+        extract_thr_kernel<<<(n_queries + 127) / 128, 128, 0, st>>>(smp_s, smp_r, n_queries, thr_rank, thr);
         LAUNCHED();
     }
     CU(cudaMemsetAsync(cnt, 0, (size_t)n_queries * 4, st));
