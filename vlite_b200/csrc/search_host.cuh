@@ -109,25 +109,29 @@ int launch_scan_wm(vl_corpus* c, ScanParams& p, int nq, int k, ScanPlan* plan, b
 // a value <= 0 disables the path).  Measured crossover against the integer-pipe kernel on 500k rows:
 // W = 128: Q = 16 0.133 vs 0.122 ms, Q = 24 0.132 vs 0.192 ms; W = 64: Q = 16 0.098 vs 0.113 ms -- a
 // 128-query tile costs the same whether it holds 16 queries or 128.
-int mma_min_q(int w) {
+// XORSUM on shards of more than ~1M rows: its integer-pipe kernel (LOP3 + IDP4A) costs 0.0030 / 0.0017 ns per
+// (row, query) at W = 128 / 64 against 0.127 / 0.067 ns per row for a 128-query tensor-core tile, so the crossover
+// sits near 43 / 40 queries (32M rows, Q = 32: 2.6 vs 4.1 ms); below ~1M rows the tile kernel's smaller fixed cost
+// keeps the lower threshold right (500k rows, Q = 32: 0.104 vs 0.131 ms).  profiles/r1_sweep.md / r2_sweep.md.
+int mma_min_q(const vl_corpus* c, int metric) {
     static int v = [] {
         const char* e = getenv("VLITE_B200_MMA_MINQ");
         return e ? atoi(e) : -1;
     }();
     if (v != -1) return v;
-    return w >= 128 ? 24 : 16;
+    if (metric == VL_METRIC_XORSUM && c->w >= 64 && c->count > (1u << 20)) return c->w >= 128 ? 44 : 40;
+    return c->w >= 128 ? 24 : 16;
 }
 
 // 0 = not eligible, 1 = one CTA per query tile, 2 = CTA pairs (cta_group::2)
 int mma_path_for(const vl_corpus* c, const ScanParams& p, int nq, int k, int metric) {
-    (void)metric;   // both metrics: XORSUM runs as a weighted +-1 contraction (mmascan.cuh)
     if (p.cur_score != nullptr) return 0;
     const bool collect = p.collect_thr != nullptr;
     if (!collect && k > kMmaListCap) return 0;
     if (c->scan_path == 1) return 0;
     if (c->scan_path == 2 || c->scan_path == 5) return 1;
     if (c->scan_path == 3 || c->scan_path == 6) return 2;
-    const int mq = mma_min_q(c->w);
+    const int mq = mma_min_q(c, metric);
     if (mq <= 0 || nq < mq) return 0;
     return nq > kMmaQT ? 2 : 1;
 }
