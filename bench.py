@@ -13,7 +13,7 @@ own 500k-row shard of an N x 500k corpus, all ranks scan all queries.
             arm reports the SAME unit, so the driver's ratio compares like with like at every N;
             ``qps_over_whole_corpus`` is the plain queries/s over the N x 500k corpus.
 ``e2e``     the same metric through the C ABI with HOST buffers (pinned queries in, results out).
-``roofline`` of the dominant kernel.  Batches of >= 24 queries run on the tensor-core scan
+``roofline`` of the dominant kernel.  Batches of >= 16 queries run on the tensor-core scan
             (HAMMING: tcgen05.mma kind::mxf4 on rows expanded bit -> +-1.0 e2m1 in shared memory, exact
             fp32 sums): bound "tensor", achieved = 2 N Q 8W ops / kernel time, peak = 4 x the measured
             bf16 cuBLAS rate of MEASURED_PEAKS.json (e2m1 issues at four times the bf16 rate on B200;

@@ -216,8 +216,8 @@ int vl_set_tuning(vl_corpus* c, int row_splits, int stages);
  * bounds / protocol assertions failed on `device` so far and the id of the first (0 = none).  The
  * shipped build returns VL_EINVAL.  Stands in for compute-sanitizer, which the GPU pool keeps closed. */
 int vl_debug_checks(int device, uint32_t* failures_out, uint32_t* first_id_out);
-/* which scan kernel answers vl_search on this handle.  0 = automatic (default): batches of at least 24
- * queries (16 for W <= 64) go to the tensor-core kernel -- k <= 16 on its register lists, larger k through its
+/* which scan kernel answers vl_search on this handle.  0 = automatic (default): batches of at least 16
+ * queries (XORSUM on shards over ~1M rows: 44, 40 at W = 64) go to the tensor-core kernel -- k <= 16 on its register lists, larger k through its
  * sampled + collect passes -- the rest to the integer-pipe kernel (LOP3 + POPC / DP4A).  On the tensor cores
  * both metrics are +-1 contractions in 4-bit floats (tcgen05.mma kind::mxf4: rows expanded bit -> e2m1 in shared
  * memory, fp32 sums of integers below 2^24: exact; HAMMING with unit block scales, XORSUM with the bit weights

@@ -147,7 +147,7 @@ def test_large_k_collect_pass_on_tensor_cores(gpu, path, metric, k):
 
 
 def test_automatic_dispatch_is_bit_identical(gpu):
-    """auto mode: Q >= 24 (16 at W <= 64) with k <= 16 goes to the tensor-core kernel (both metrics),
+    """auto mode: Q >= 16 with k <= 16 goes to the tensor-core kernel (both metrics; XOR-sum on big shards later),
     everything else to the integer-pipe kernel."""
     n = 50_000
     corpus = synth.corpus_rows(18, 0, n, 64)

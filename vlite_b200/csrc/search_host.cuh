@@ -106,9 +106,9 @@ int launch_scan_wm(vl_corpus* c, ScanParams& p, int nq, int k, ScanPlan* plan, b
 // ---- tensor-core scan (mmascan.cuh) ----------------------------------------------
 
 // smallest batch the tensor-core scan takes in automatic mode (tuning override: VLITE_B200_MMA_MINQ;
-// a value <= 0 disables the path).  Measured crossover against the integer-pipe kernel on 500k rows:
-// W = 128: Q = 16 0.133 vs 0.122 ms, Q = 24 0.132 vs 0.192 ms; W = 64: Q = 16 0.098 vs 0.113 ms -- a
-// 128-query tile costs the same whether it holds 16 queries or 128.
+// a value <= 0 disables the path).  A 128-query tile costs the same whether it holds 16 queries or 128; measured
+// crossover of the e2m1 HAMMING form against the integer-pipe kernel (profiles/r2_sweep.md): W = 128: Q = 16
+// 0.080 vs 0.100 ms on 500k rows, 2.81 vs 2.70 ms on 32M (Q = 24: 2.81 vs 4.0); W = 64: Q = 16 0.063 vs 0.080 ms.
 // XORSUM on shards of more than ~1M rows: its integer-pipe kernel (LOP3 + IDP4A) costs 0.0030 / 0.0017 ns per
 // (row, query) at W = 128 / 64 against 0.127 / 0.067 ns per row for a 128-query tensor-core tile, so the crossover
 // sits near 43 / 40 queries (32M rows, Q = 32: 2.6 vs 4.1 ms); below ~1M rows the tile kernel's smaller fixed cost
@@ -120,7 +120,7 @@ int mma_min_q(const vl_corpus* c, int metric) {
     }();
     if (v != -1) return v;
     if (metric == VL_METRIC_XORSUM && c->w >= 64 && c->count > (1u << 20)) return c->w >= 128 ? 44 : 40;
-    return c->w >= 128 ? 24 : 16;
+    return 16;
 }
 
 // 0 = not eligible, 1 = one CTA per query tile, 2 = CTA pairs (cta_group::2)
