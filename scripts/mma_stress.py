@@ -10,14 +10,15 @@ HAMMING = 0
 n, w = 150_003, 128
 corpus = synth.corpus_rows(11, 0, n, w)
 reps = int(os.environ.get("REPS", "20"))
-for nq, path, k in ((128, 2, 10), (1024, 2, 10), (1024, 3, 10), (200, 3, 16), (128, 5, 10), (1024, 6, 10)):
+for nq, path, k, metric in ((128, 2, 10, 0), (1024, 2, 10, 0), (1024, 3, 10, 0), (200, 3, 16, 0), (128, 5, 10, 0), (1024, 6, 10, 0),
+                            (128, 2, 10, 1), (1024, 3, 10, 1), (1024, 6, 10, 1)):
     queries, src = synth.clustered_queries(12, 0, n, nq, w)
-    es, er = cscan.search(queries, corpus, k, HAMMING, None)
+    es, er = cscan.search(queries, corpus, k, metric, None)
     with _capi.Corpus(w) as c:
         c.append(corpus)
         c.set_scan_path(path)
         bad = 0; tot = 0
         for rep in range(reps):
-            s, r = c.search(queries, k, HAMMING, None)
+            s, r = c.search(queries, k, metric, None)
             b = int(((s != es) | (r != er)).sum()); bad += b > 0; tot += b
-        print(f"nq={nq} path={path} k={k}: {bad}/{reps} launches wrong ({tot} entries)", flush=True)
+        print(f"nq={nq} path={path} k={k} metric={metric}: {bad}/{reps} launches wrong ({tot} entries)", flush=True)

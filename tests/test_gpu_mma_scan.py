@@ -184,8 +184,8 @@ def test_k_17_to_32_batches_take_the_collect_path(gpu, k, period, width, metric)
 
 
 @pytest.mark.parametrize("path", PATHS)
-@pytest.mark.parametrize("nq", [128, 1024])
-def test_many_tiles_per_cta_repeated(gpu, path, nq):
+@pytest.mark.parametrize("nq,metric", [(128, HAMMING), (1024, HAMMING), (1024, XORSUM)])
+def test_many_tiles_per_cta_repeated(gpu, path, nq, metric):
     """Regression: 8+ tiles per CTA, launched repeatedly.  The packed-row box used to be handed back to the TMA
     producer while the expanders' shared-memory loads of it were still in flight (an mbarrier arrive does not
     wait for them): with the fast e2m1 pipeline rows of tile i then carried 16-byte chunks of tile i + 2 in
@@ -193,12 +193,12 @@ def test_many_tiles_per_cta_repeated(gpu, path, nq):
     n, w = 150_003, 128
     corpus = synth.corpus_rows(11, 0, n, w)
     queries, _ = synth.clustered_queries(12, 0, n, nq, w)
-    es, er = cscan.search(queries, corpus, 10, HAMMING)
+    es, er = cscan.search(queries, corpus, 10, metric)
     with gpu.Corpus(w) as c:
         c.append(corpus)
         c.set_scan_path(path)
         for _ in range(12):
-            s, r = c.search(queries, 10, HAMMING)
+            s, r = c.search(queries, 10, metric)
             np.testing.assert_array_equal(s, es)
             np.testing.assert_array_equal(r, er)
 
