@@ -893,6 +893,15 @@ extern "C" int vl_scan_trace_tiles(vl_corpus* c, uint64_t* out512_host) {
     CU(cudaMemcpy(out512_host, c->trace_dev + 16, 512 * 8, cudaMemcpyDeviceToHost));
     return VL_OK;
 }
+// ... and the role timeline of one steady-state tile (mmascan.cuh: kTraceTile), 64 words
+extern "C" int vl_scan_trace_roles(vl_corpus* c, uint64_t* out64_host) {
+    if (!c || !out64_host) return fail(VL_EINVAL, "NULL argument");
+    if (!c->trace_dev) return fail(VL_EINVAL, "tracing is off: call vl_scan_trace(h, NULL) first");
+    DeviceGuard g(c->device);
+    CU(cudaStreamSynchronize(c->stream));
+    CU(cudaMemcpy(out64_host, c->trace_dev + vl::kTraceRoleBase, 64 * 8, cudaMemcpyDeviceToHost));
+    return VL_OK;
+}
 // ... and entry [i] / exit [296 + i] stamps of every CTA (linear index, first 296)
 extern "C" int vl_scan_trace_ctas(vl_corpus* c, uint64_t* out592_host) {
     if (!c || !out592_host) return fail(VL_EINVAL, "NULL argument");

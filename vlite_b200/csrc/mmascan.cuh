@@ -44,7 +44,9 @@ constexpr int kMmaExpWarps = 8;
 constexpr int kMmaListCap = 16;      // k <= 16 per-thread register list
 constexpr int kMmaSlabBytes = 128 * 128;
 constexpr int kTraceCtas = 296;
-constexpr int kTraceWords = 16 + 512 + 2 * kTraceCtas;   // vl_scan_trace: 16 stamps | per-tile stamps + insert counts of 256 tiles | entry / exit of every CTA
+constexpr int kTraceTile = 64;      // the steady-state tile whose hand-offs every role of CTA (0,0) stamps
+constexpr int kTraceRoleBase = 16 + 512 + 2 * kTraceCtas;   // + 64 words: [0..7] TMA, [8..15] MMA, [16..31] expander warp 8, [32..47] / [48..63] epilogue warps 4 / 12
+constexpr int kTraceWords = kTraceRoleBase + 64;   // vl_scan_trace: 16 stamps | per-tile stamps + insert counts of 256 tiles | entry / exit of every CTA | one tile, every role
 
 // F4 = the +-1 contraction in 4-bit floats (tcgen05.mma kind::mxf4: e2m1 operands, +1.0 = 0x2, -1.0 = 0xA, two per
 // byte, unit UE8M0 block scales, fp32 accumulation -- exact: every product is +-1 and |sum| <= 1024 < 2^24).  The
@@ -356,6 +358,9 @@ mma_scan_kernel(const __grid_constant__ CUtensorMap tmap, const ScanParams p) {
     constexpr int K = XS ? 255 * W : 8 * W;      // score = (K - dot) / 2: the dot product of a perfect match
     const bool tracing = p.trace != nullptr && blockIdx.x == 0 && blockIdx.y == 0;
     if (tracing && threadIdx.x == 0) p.trace[0] = global_ns();
+    auto stamp = [&](uint32_t i, int slot) {   // role timeline of tile kTraceTile (and the one after it: slot + 4 .. for i + 1 where noted)
+        if (tracing && i == (uint32_t)kTraceTile) p.trace[kTraceRoleBase + slot] = global_ns();
+    };
     const uint32_t cta_lin = blockIdx.y * gridDim.x + blockIdx.x;
     if (p.trace != nullptr && threadIdx.x == 0 && cta_lin < (uint32_t)kTraceCtas) p.trace[16 + 512 + cta_lin] = global_ns();
 
@@ -514,7 +519,9 @@ mma_scan_kernel(const __grid_constant__ CUtensorMap tmap, const ScanParams p) {
             const uint64_t policy = p.evict_first ? l2_policy_evict_first() : l2_policy_evict_last();
             for (uint32_t i = 0; i < my_tiles; ++i) {
                 const int s = i % kMmaPkStages;
+                stamp(i, 0);
                 if (i >= kMmaPkStages) mbar_wait(&pk_empty[s], ((i / kMmaPkStages) - 1) & 1);
+                stamp(i, 1);
                 const uint32_t t = (tile_begin + i) * p.tile_stride;
                 if constexpr (F4) {
                     // (28-byte mask rows cannot ride a bulk copy: the expanders read their mask bits from global)
@@ -540,17 +547,20 @@ mma_scan_kernel(const __grid_constant__ CUtensorMap tmap, const ScanParams p) {
             uint32_t g = 0;   // slab counter
             for (uint32_t i = 0; i < my_tiles; ++i) {
                 const uint32_t buf = i & 1;
+                stamp(i, 8);
                 if (i >= 2) {
                     if constexpr (CG == 2) mbar_wait_cluster(&acc_empty[buf], ((i >> 1) - 1) & 1);
                     else mbar_wait(&acc_empty[buf], ((i >> 1) - 1) & 1);
                     tc_fence_after();
                 }
+                stamp(i, 9);
                 const uint32_t d_tmem = tmem_base + buf * NT;
 #pragma unroll 1
                 for (int j = 0; j < SLABS; ++j, ++g) {
                     const uint32_t st = g % kMmaBStages;
                     const uint32_t par = (g / kMmaBStages) & 1;
                     if constexpr (CG == 2) mbar_wait_cluster(&b_full[st], par); else mbar_wait(&b_full[st], par);
+                    stamp(i, 10 + (j < 4 ? j : 3));
                     tc_fence_after();
                     const uint64_t ad = umma_desc_sw128(a_saddr + (uint32_t)j * kMmaSlabBytes);
                     const uint64_t bd = umma_desc_sw128(b_saddr + st * kMmaSlabBytes);
@@ -571,6 +581,7 @@ mma_scan_kernel(const __grid_constant__ CUtensorMap tmap, const ScanParams p) {
                     umma_commit<CG>(&b_empty[st]);
                 }
                 umma_commit<CG>(&acc_full[buf]);
+                stamp(i, 14);
             }
         }
         __syncwarp();
@@ -643,8 +654,10 @@ mma_scan_kernel(const __grid_constant__ CUtensorMap tmap, const ScanParams p) {
                 vw = __ldg(p.live + (size_t)t * MW + lane);
                 if (has_filter) vw &= __ldg(p.filter + (size_t)t * MW + lane);
             }
+            if (lane == 0 && (warp == 4 || warp == 12)) stamp(i, (warp == 4 ? 32 : 48) + 0);
             mbar_wait(&acc_full[buf], (i >> 1) & 1);
             tc_fence_after();
+            if (lane == 0 && (warp == 4 || warp == 12)) stamp(i, (warp == 4 ? 32 : 48) + 1);
             if (tracing && warp == 4 && lane == 0 && i < 3) p.trace[i == 0 ? 4 : 12 + i] = global_ns();   // accumulator 0 / 1 / 2 ready
 #pragma unroll 1
             for (int ch = grp; ch < NT / 32; ch += EG) {
@@ -653,6 +666,7 @@ mma_scan_kernel(const __grid_constant__ CUtensorMap tmap, const ScanParams p) {
                 VL_DCHECK(buf * NT + (uint32_t)ch * 32u + 32u <= (uint32_t)Cfg::TMEM_COLS, 202);
                 tmem_ld32(tmem_base + (lane_base << 16) + buf * NT + (uint32_t)ch * 32u, vu);
                 tmem_ld_wait();
+                if (lane == 0 && (warp == 4 || warp == 12)) stamp(i, (warp == 4 ? 32 : 48) + 2 + (ch / EG));
                 if (ch + EG >= NT / 32) {
                     // this group's last chunk of the accumulator buffer is in registers now: hand it back to the MMA thread
                     tc_fence_before();
@@ -736,6 +750,7 @@ mma_scan_kernel(const __grid_constant__ CUtensorMap tmap, const ScanParams p) {
                 if (use_tau && thr != kSentinelScore && thr < tau_pref) atomicMin(tau_ptr, thr);
             }
             if (tracing && warp == 4 && lane == 0 && i < 256) p.trace[16 + i] = global_ns();
+            if (lane == 0 && (warp == 4 || warp == 12)) stamp(i, (warp == 4 ? 32 : 48) + 8);
         }
         __syncwarp();
         if (tracing && warp == 4 && lane == 0) p.trace[2] = global_ns();   // last tile's epilogue done
@@ -845,7 +860,9 @@ mma_scan_kernel(const __grid_constant__ CUtensorMap tmap, const ScanParams p) {
                     wv = __ldg(p.live + widx);
                     if (has_filter) wv &= __ldg(p.filter + widx);
                 }
+                if (warp == 8 && lane == 0) stamp(i, 16);
                 mbar_wait(&pk_full[s], (i / kMmaPkStages) & 1);
+                if (warp == 8 && lane == 0) stamp(i, 17);
                 keep = ((wv >> (bit & 31u)) & 1u) ? 0xFFFFFFFFu : 0u;
             } else {
                 mbar_wait(&pk_full[s], (i / kMmaPkStages) & 1);
@@ -868,6 +885,7 @@ mma_scan_kernel(const __grid_constant__ CUtensorMap tmap, const ScanParams p) {
                 for (int j = 0; j < SLABS; ++j, ++g) {
                     const uint32_t st = g % kMmaBStages;
                     if (g >= kMmaBStages) mbar_wait(&b_empty[st], ((g / kMmaBStages) - 1) & 1);
+                    if (warp == 8 && lane == 0) stamp(i, 18 + 2 * (j < 4 ? j : 3));
                     const uint32_t row_saddr = b_saddr + st * kMmaSlabBytes;
                     VL_DCHECK(CG == 2 || !mbar_test_wait(&b_full[st], (g / kMmaBStages) & 1), 207);
                     const uint32_t src = pk_saddr + (uint32_t)s * Cfg::PK_STRIDE;
@@ -907,6 +925,7 @@ mma_scan_kernel(const __grid_constant__ CUtensorMap tmap, const ScanParams p) {
                     }
                     fence_proxy_async_smem();
                     __syncwarp();
+                    if (warp == 8 && lane == 0) stamp(i, 19 + 2 * (j < 4 ? j : 3));
                     if (lane == 0) {
                         if constexpr (CG == 2) mbar_arrive_cluster(b_full_remote + st * 8u);
                         else mbar_arrive(&b_full[st]);
