@@ -40,19 +40,20 @@ __device__ __forceinline__ void umma_mxf4_ts(uint32_t d_tmem, uint32_t a_tmem, u
                  : "memory");
 }
 
-template <bool F4, int N, bool TS = false>
+template <bool F4, int N, bool TS = false, bool COMMIT_EACH = false>
 __global__ void __launch_bounds__(128, 1) probe_kernel(int iters, float* out, unsigned long long* ns_out) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint8_t* sA = smem;                 // 128 rows x 128 B
     uint8_t* sB = smem + 16384;         // N rows x 128 B
-    __shared__ uint64_t bar;
+    __shared__ uint64_t bar, bar2;
     __shared__ uint32_t s_tmem;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     fill_rows<F4>(sA, 128, 32, threadIdx.x, 128);
     fill_rows<F4>(sB, N, 16, threadIdx.x, 128);
     if (threadIdx.x == 0) {
         mbar_init(&bar, 1);
+        mbar_init(&bar2, 1);
         mbar_fence_init();
     }
     if (warp == 0) tmem_alloc<1>(&s_tmem, 512);
@@ -105,6 +106,7 @@ __global__ void __launch_bounds__(128, 1) probe_kernel(int iters, float* out, un
                 else if (F4) umma_mxf4<1>(tm, ad + (uint64_t)(kk * 2), bd + (uint64_t)(kk * 2), idesc, acc, tm + N, tm + N + 16);
                 else umma_i8<1>(tm, ad + (uint64_t)(kk * 2), bd + (uint64_t)(kk * 2), idesc, acc);
             }
+            if (COMMIT_EACH) umma_commit<1>(&bar2);   // the scan's per-slab hand-back of a ring slot
         }
         umma_commit<1>(&bar);
     }
@@ -133,13 +135,13 @@ __global__ void __launch_bounds__(128, 1) probe_kernel(int iters, float* out, un
     if (warp == 0) tmem_dealloc<1>(tm, 512);
 }
 
-template <bool F4, int N, bool TS = false>
+template <bool F4, int N, bool TS = false, bool COMMIT_EACH = false>
 int run(const char* name, int iters) {
     float* out;
     unsigned long long* ns;
     cudaMalloc(&out, 128 * N * sizeof(float));
     cudaMalloc(&ns, 148 * 8);
-    auto kern = probe_kernel<F4, N, TS>;
+    auto kern = probe_kernel<F4, N, TS, COMMIT_EACH>;
     const size_t smem = 16384 + N * 128 + 1024;
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     int bad = 0;
@@ -245,6 +247,8 @@ int main(int argc, char** argv) {
     bad += run<true, 224, true>("mxf4 M128 N224 K64, A in TMEM", iters);
     bad += run<true, 160, true>("mxf4 M128 N160 K64, A in TMEM", iters);
     bad += run<true, 160>("mxf4 M128 N160 K64", iters);
+    bad += run<true, 224, false, true>("mxf4 M128 N224 K64, tcgen05.commit after every 4 MMAs", iters);
+    bad += run<false, 256, false, true>("i8   M128 N256 K32, tcgen05.commit after every 4 MMAs", iters);
     run_ldtm<4, 1>(2000);
     run_ldtm<8, 1>(2000);
     run_ldtm<8, 2>(2000);

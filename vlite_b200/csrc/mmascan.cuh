@@ -186,6 +186,50 @@ __device__ __forceinline__ void tmem_fill16(uint32_t taddr, uint32_t x) {
         : "memory");
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+// The same instructions issued from CONVERGED warp code by one elected lane (elect.sync inside the asm).  A tcgen05
+// operand must sit in a uniform register: from a divergent `if (lane == 0)` region the compiler moves every operand
+// there with an ELECT / R2UR.BROADCAST / BRA.U.ANY loop -- 14 instructions per MMA on the one thread whose
+// bookkeeping paces the whole CTA pair; converged code needs a plain R2UR.
+template <int CG>
+__device__ __forceinline__ void umma_mxf4_elect(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate,
+                                                uint32_t sfa_tmem, uint32_t sfb_tmem) {
+    if constexpr (CG == 1)
+        asm volatile("{\n\t.reg .pred p, q;\n\telect.sync _|q, 0xffffffff;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                     "@q tcgen05.mma.cta_group::1.kind::mxf4.block_scale.scale_vec::2X [%0], %1, %2, %3, [%5], [%6], p;\n\t}" ::"r"(d_tmem),
+                     "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(sfa_tmem), "r"(sfb_tmem)
+                     : "memory");
+    else
+        asm volatile("{\n\t.reg .pred p, q;\n\telect.sync _|q, 0xffffffff;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                     "@q tcgen05.mma.cta_group::2.kind::mxf4.block_scale.scale_vec::2X [%0], %1, %2, %3, [%5], [%6], p;\n\t}" ::"r"(d_tmem),
+                     "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(sfa_tmem), "r"(sfb_tmem)
+                     : "memory");
+}
+template <int CG>
+__device__ __forceinline__ void umma_i8_elect(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    if constexpr (CG == 1)
+        asm volatile("{\n\t.reg .pred p, q;\n\telect.sync _|q, 0xffffffff;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                     "@q tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc),
+                     "r"(accumulate)
+                     : "memory");
+    else
+        asm volatile("{\n\t.reg .pred p, q;\n\telect.sync _|q, 0xffffffff;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                     "@q tcgen05.mma.cta_group::2.kind::i8 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc),
+                     "r"(accumulate)
+                     : "memory");
+}
+template <int CG>
+__device__ __forceinline__ void umma_commit_elect(uint64_t* bar) {
+    if constexpr (CG == 1)
+        asm volatile("{\n\t.reg .pred q;\n\telect.sync _|q, 0xffffffff;\n\t"
+                     "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(smem_u32(bar))
+                     : "memory");
+    else
+        asm volatile("{\n\t.reg .pred q;\n\telect.sync _|q, 0xffffffff;\n\t"
+                     "@q tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n\t}" ::"r"(
+                         smem_u32(bar)),
+                     "h"((uint16_t)3)
+                     : "memory");
+}
 // arrive on an mbarrier once every tcgen05 operation issued so far by this thread has completed;
 // CG = 2: the same barrier offset in both CTAs of the pair
 template <int CG>
@@ -371,7 +415,7 @@ mma_scan_kernel(const __grid_constant__ CUtensorMap tmap, const ScanParams p) {
     uint8_t* sB = sA + Cfg::A_BYTES;
     // ring depth: Cfg::BSTAGES unless a tuning run asks for fewer (p.stages in [2, BSTAGES]); the shared
     // memory layout always reserves BSTAGES slabs
-    const uint32_t kMmaBStages = (p.stages >= 2 && p.stages <= Cfg::BSTAGES) ? (uint32_t)p.stages : (uint32_t)Cfg::BSTAGES;
+    constexpr uint32_t kMmaBStages = (uint32_t)Cfg::BSTAGES;   // (a compile-time ring depth: the MMA thread's per-slab bookkeeping is on the critical path)
     uint8_t* sPk = sB + Cfg::BSTAGES * kMmaSlabBytes;
     uint32_t* sMask = reinterpret_cast<uint32_t*>(sPk + kMmaPkStages * Cfg::PK_STRIDE);   // [stage][live | filter][MW]
     uint64_t* bars = reinterpret_cast<uint64_t*>(sMask + kMmaPkStages * 2 * MW);
@@ -539,49 +583,55 @@ mma_scan_kernel(const __grid_constant__ CUtensorMap tmap, const ScanParams p) {
         }
         __syncwarp();   // reconverge: the teardown barrier / cluster barrier is warp-aligned
     } else if (warp == 1) {
-        // ===================== MMA issuer: one thread of the leader CTA =====================
-        if (rank == 0 && lane == 0) {
+        // ===================== MMA issuer: the leader CTA's warp 1, one elected lane per instruction =====================
+        if (rank == 0) {
             constexpr uint32_t idesc = F4 ? umma_idesc_mxf4(kMmaQT * CG, NT) : umma_idesc_i8(kMmaQT * CG, NT);
             const uint32_t sfa = tmem_base + 2u * NT, sfb = sfa + 32u;
             const uint32_t a_saddr = smem_u32(sA), b_saddr = smem_u32(sB);
-            uint32_t g = 0;   // slab counter
+            // One thread issues every MMA of the CTA pair, and its bookkeeping between two slabs -- not the tensor pipe --
+            // set the tile time (scripts/mma_trace_roles.py: 384 ns per slab of four 61 ns MMAs): ring slot and parity
+            // are carried instead of divided out, descriptors are one add from a base, the slab loop is unrolled.
+            const uint64_t ad0 = umma_desc_sw128(a_saddr), bd0 = umma_desc_sw128(b_saddr);
+            uint32_t st = 0, par = 0;   // ring slot of the next slab, parity of its generation
             for (uint32_t i = 0; i < my_tiles; ++i) {
                 const uint32_t buf = i & 1;
-                stamp(i, 8);
+                if (lane == 0) stamp(i, 8);
                 if (i >= 2) {
                     if constexpr (CG == 2) mbar_wait_cluster(&acc_empty[buf], ((i >> 1) - 1) & 1);
                     else mbar_wait(&acc_empty[buf], ((i >> 1) - 1) & 1);
                     tc_fence_after();
                 }
-                stamp(i, 9);
+                if (lane == 0) stamp(i, 9);
                 const uint32_t d_tmem = tmem_base + buf * NT;
-#pragma unroll 1
-                for (int j = 0; j < SLABS; ++j, ++g) {
-                    const uint32_t st = g % kMmaBStages;
-                    const uint32_t par = (g / kMmaBStages) & 1;
+#pragma unroll
+                for (int j = 0; j < SLABS; ++j) {
                     if constexpr (CG == 2) mbar_wait_cluster(&b_full[st], par); else mbar_wait(&b_full[st], par);
-                    stamp(i, 10 + (j < 4 ? j : 3));
+                    if (lane == 0) stamp(i, 10 + (j < 4 ? j : 3));
                     tc_fence_after();
-                    const uint64_t ad = umma_desc_sw128(a_saddr + (uint32_t)j * kMmaSlabBytes);
-                    const uint64_t bd = umma_desc_sw128(b_saddr + st * kMmaSlabBytes);
+                    const uint64_t ad = ad0 + (uint64_t)(j * (kMmaSlabBytes >> 4));
+                    const uint64_t bd = bd0 + (uint64_t)(st * (uint32_t)(kMmaSlabBytes >> 4));
 #pragma unroll
                     for (int kk = 0; kk < 4; ++kk) {   // K = 32 int8 (64 e2m1) = 32 B per instruction: +2 in the address field
                         if constexpr (F4) {
                             // XORSUM: this K = 64 step is elements [64 (4 j + kk), + 64) = plane 64 (4 j + kk) / W: its scale column
                             const uint32_t sfa_k = F4X ? sfa + 4u * (uint32_t)((64 * (4 * j + kk)) / W) : sfa;
-                            umma_mxf4<CG>(d_tmem, ad + (uint64_t)(kk * 2), bd + (uint64_t)(kk * 2), idesc, (j | kk) != 0 ? 1u : 0u, sfa_k, sfb);
+                            umma_mxf4_elect<CG>(d_tmem, ad + (uint64_t)(kk * 2), bd + (uint64_t)(kk * 2), idesc, (j | kk) != 0 ? 1u : 0u, sfa_k, sfb);
                             continue;
                         }
-                        umma_i8<CG>(d_tmem, ad + (uint64_t)(kk * 2), bd + (uint64_t)(kk * 2), idesc, (j | kk) != 0 ? 1u : 0u);
+                        umma_i8_elect<CG>(d_tmem, ad + (uint64_t)(kk * 2), bd + (uint64_t)(kk * 2), idesc, (j | kk) != 0 ? 1u : 0u);
                         // XORSUM: the elements of plane 0 (bit 7 of every byte, the first W of the row) weigh
                         // 128 = 64 + 64: their k-steps are accumulated twice
                         if (XS && j * 128 + kk * 32 < W)
-                            umma_i8<CG>(d_tmem, ad + (uint64_t)(kk * 2), bd + (uint64_t)(kk * 2), idesc, 1u);
+                            umma_i8_elect<CG>(d_tmem, ad + (uint64_t)(kk * 2), bd + (uint64_t)(kk * 2), idesc, 1u);
                     }
-                    umma_commit<CG>(&b_empty[st]);
+                    umma_commit_elect<CG>(&b_empty[st]);
+                    if (++st == kMmaBStages) {
+                        st = 0;
+                        par ^= 1u;
+                    }
                 }
-                umma_commit<CG>(&acc_full[buf]);
-                stamp(i, 14);
+                umma_commit_elect<CG>(&acc_full[buf]);
+                if (lane == 0) stamp(i, 14);
             }
         }
         __syncwarp();
