@@ -262,3 +262,19 @@ def test_large_k_many_tiles_per_cta_stays_on_the_fast_path(gpu, nq, k):
         true = np.unpackbits(sub ^ q[qi], axis=1).sum(axis=1)
         np.testing.assert_array_equal(true, s[qi][:: max(1, k // 50)])
 
+
+
+@pytest.mark.parametrize("nq", [2048 + 77, 4096, 5000])
+@pytest.mark.parametrize("metric,k", [(HAMMING, 10), (XORSUM, 10), (HAMMING, 100)])
+def test_big_batches_go_out_in_several_launches(gpu, nq, metric, k):
+    """8+ query tiles: the batch is scanned in several launches of fewer tiles each (ScanParams::q_offset) so that
+    tiles x row splits fills the SMs (4096 queries: 2 x (8 pairs x 9 splits) instead of 16 x 4).  Every query,
+    list mode and collect mode, both metrics, ragged last launch."""
+    n, w = 60_000, 128
+    corpus = synth.corpus_rows(71, 0, n, w)
+    queries = synth.uniform_queries(72, nq, w)
+    queries[0] = corpus[n - 1]
+    queries[nq - 1] = corpus[0]
+    with gpu.Corpus(w) as c:
+        c.append(corpus)
+        _check(c, corpus, queries, k, metric=metric)

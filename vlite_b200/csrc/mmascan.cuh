@@ -432,7 +432,7 @@ mma_scan_kernel(const __grid_constant__ CUtensorMap tmap, const ScanParams p) {
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     const uint32_t rank = (CG == 2) ? cluster_ctarank() : 0u;
-    const int q0 = (int)blockIdx.x * kMmaQT;     // blockIdx.x = pair * CG + rank
+    const int q0 = p.q_offset + (int)blockIdx.x * kMmaQT;     // blockIdx.x = pair * CG + rank
     const int split = blockIdx.y;
     const int n_splits = gridDim.y;
     const uint32_t tile_begin = (uint32_t)(((uint64_t)p.n_tiles * split) / n_splits);

@@ -86,6 +86,7 @@ struct ScanParams {
     // list of keys per query in fuse_keys[split][q][k], takes a ticket; the LAST CTA to finish merges all
     // splits and writes the final top-k -- one launch instead of scan + two merge levels.
     uint32_t poll_ns, poll_steady;   // tuning (0 = defaults): histogram poll interval and how many polls keep it
+    int q_offset;                    // tensor-core scan: first query of this launch (big batches go out in several launches)
     int k_bound;                     // tensor-core scan: rank the SHARED admission bound stands for (0 = k).  > k: the caller
                                      // will merge the k-entry lists to the k_bound best of their union (sampled pass of large k)
     unsigned long long* trace;       // optional (tuning): %globaltimer stamps of CTA (0,0) of the tensor-core scan

@@ -144,7 +144,23 @@ int launch_mma_cfg(vl_corpus* c, ScanParams& p, int nq, int k, ScanPlan* plan_ou
     p.n_tiles = (all_tiles + p.tile_stride - 1) / p.tile_stride;
     const int T = (nq + kMmaQT * CG - 1) / (kMmaQT * CG);   // clusters along the queries
     const long slots = std::max(1, c->sms / CG);             // clusters resident at once (one CTA per SM)
-    long S = c->tune_splits > 0 ? c->tune_splits : std::max<long>(1, slots / T);
+    // Query tiles per launch.  One launch of T tiles x floor(slots / T) row splits leaves SMs idle when T does not
+    // divide the slots well (4096 queries: 16 pairs x 4 splits = 128 of 148 SMs, ncu profiles/r2_collect_scan.md);
+    // several launches of fewer tiles each re-stream the packed rows (cheap: the scan is nowhere near HBM-bound
+    // at these batch sizes) but fill the machine: 2 x (8 pairs x 9 splits) = 144 SMs.  Only for batches of 8+
+    // tiles, whose launches are long; the number of row splits (= lists per query) is the same in every launch.
+    int Tl = T;
+    if (c->tune_splits <= 0 && T >= 8) {
+        double best = (double)1 / (double)std::max<long>(1, slots / T);
+        for (int t = T - 1; t >= 4; --t) {
+            const double cost = (double)((T + t - 1) / t) / (double)std::max<long>(1, slots / t);   // launches / splits
+            if (cost < best * 0.97) {
+                best = cost;
+                Tl = t;
+            }
+        }
+    }
+    long S = c->tune_splits > 0 ? c->tune_splits : std::max<long>(1, slots / Tl);
     S = std::min<long>(S, std::max<long>(1, p.n_tiles));
     S = std::min<long>(S, 65535);
     const size_t smem = Cfg::SMEM;
@@ -155,7 +171,7 @@ int launch_mma_cfg(vl_corpus* c, ScanParams& p, int nq, int k, ScanPlan* plan_ou
     CUtensorMap tmap;
     TRY(make_corpus_tmap(c, &tmap, Cfg::ROWS));
     cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3((unsigned)(T * CG), (unsigned)S);
+    cfg.gridDim = dim3((unsigned)(Tl * CG), (unsigned)S);
     cfg.blockDim = dim3(kMmaThreads);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = c->stream;
@@ -166,8 +182,13 @@ int launch_mma_cfg(vl_corpus* c, ScanParams& p, int nq, int k, ScanPlan* plan_ou
     at[0].val.clusterDim.z = 1;
     cfg.attrs = at;
     cfg.numAttrs = CG == 2 ? 1 : 0;
-    CU(cudaLaunchKernelEx(&cfg, kern, tmap, p));
-    LAUNCHED();
+    for (int t0 = 0; t0 < T; t0 += Tl) {
+        p.q_offset = t0 * kMmaQT * CG;
+        cfg.gridDim.x = (unsigned)(std::min(Tl, T - t0) * CG);
+        CU(cudaLaunchKernelEx(&cfg, kern, tmap, p));
+        LAUNCHED();
+    }
+    p.q_offset = 0;
     return VL_OK;
 }
 
